@@ -1,0 +1,102 @@
+/* libldn — C ABI of the B200-native SD1.5 sampling engine.
+ *
+ * Drop-in boundary for LightDiffusion-Next's sampler hot path.  Every entry point takes plain
+ * pointers / sizes (device pointers unless stated), launches asynchronously on the CUDA stream
+ * passed as `stream` (a cudaStream_t cast to void*; NULL = legacy default stream), returns 0 on
+ * success and non-zero on failure with a message available from ldn_last_error().
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   ldn_unet_denoise   <- BaseModel.apply_model          src/Model/ModelBase.py:72-133
+ *                         (called through model_options["model_function_wrapper"], src/cond/cond.py:254-265)
+ *   ldn_set_context    <- CrossAttention.to_k/to_v        src/Attention/Attention.py:118-121 (hoisted out of the loop)
+ *   ldn_cfg_step       <- cfg_function + sampler update   src/sample/CFG.py:55-60, src/sample/samplers.py:728-732,952-953
+ *   ldn_vae_decode     <- VAE.decode                      src/AutoEncoders/VariationalAE.py:690-722
+ *   ldn_clip_encode    <- CLIPTextModel_.forward          src/clip/CLIPTextModel.py:51-107
+ *   op-level entries   <- the torch library calls of      src/cond/cast.py:107,174,241,281 and
+ *                         optimized_attention             src/Attention/Attention.py:34-41
+ */
+#ifndef LDN_H
+#define LDN_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldn_engine* ldn_handle;
+
+/* dtype codes for weight ingest */
+enum { LDN_F32 = 0, LDN_F16 = 1, LDN_BF16 = 2 };
+
+typedef struct ldn_tensor {
+  const char* name;   /* SD1.5 / LDM state-dict key, e.g. "input_blocks.1.0.in_layers.2.weight" */
+  const void* data;   /* device pointer, contiguous */
+  int dtype;          /* LDN_F32 | LDN_F16 | LDN_BF16 */
+  int ndim;
+  int64_t shape[4];
+} ldn_tensor;
+
+typedef struct ldn_config {
+  int max_rows;       /* max UNet batch rows (cond+uncond rows, i.e. 2*bs) */
+  int max_h, max_w;   /* max latent height / width */
+  int max_ctx_tokens; /* max context tokens per row (77*k) */
+  int use_graph;      /* capture the UNet forward into a CUDA graph per (rows,h,w) */
+} ldn_config;
+
+const char* ldn_last_error(void);
+int ldn_version(void);
+
+/* ---- engine lifecycle */
+int ldn_create(const ldn_config* cfg, ldn_handle* out);
+void ldn_destroy(ldn_handle h);
+/* which: 0 = UNet ("model.diffusion_model." prefix stripped), 1 = VAE decoder ("first_stage_model." stripped),
+ *        2 = CLIP-L text model ("...text_model." stripped) */
+int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream);
+/* sigma table of the discrete schedule (ModelSamplingDiscrete.sigmas, src/sample/sampling.py:221-356), host ptr */
+int ldn_set_sigmas(ldn_handle h, const float* sigmas_host, int n);
+
+/* ---- UNet hot path */
+/* ctx: [rows, tokens, 768] fp32 (device). Pre-computes cross-attention K/V for all 16 transformer blocks. */
+int ldn_set_context(ldn_handle h, const float* ctx, int rows, int tokens, void* stream);
+/* x: [rows,4,h,w] fp32 NCHW; sigma: [rows] fp32; out: denoised = x - eps*sigma, [rows,4,h,w] fp32. */
+int ldn_unet_denoise(ldn_handle h, const float* x, const float* sigma, float* out, int rows, int lat_h, int lat_w,
+                     void* stream);
+/* Fused CFG combine + solver update, fp32 elementwise over n elements.
+ *  denoised = uncond + (cond - uncond) * cfg
+ *  mode 0 (dpmpp_2m_cfgpp as executed by the reference, first order): x' = c0*x - c1*denoised
+ *  mode 1 (euler ancestral): x' = x + (x - denoised) * c0 + noise * c1
+ *  mode 2: only write denoised */
+int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
+                 float c1, float c2, const float* noise, float* x_out, float* denoised_out, int64_t n, void* stream);
+
+/* ---- VAE decode / CLIP encode */
+/* z: [B,4,h,w] fp32 (already divided by 0.18215); rgb: [B,8h,8w,3] fp32 in [0,1] */
+int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, int lat_w, void* stream);
+/* ids: [S,77] int64 (device); out_last: [S,77,768] fp32 final-LN of last layer (may be NULL);
+ * out_penultimate: [S,77,768] fp32 final-LN of layer -2 (what SD1.5 uses) */
+int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultimate, float* out_last, void* stream);
+
+/* ---- op-level entries (used by the parity tests; same kernels the engine runs) */
+/* out[M,N] = [A0 | A1][M,K0+K1] * Wt[N,K]^T (+bias) (+rowbias[row / rows_per_batch]) (+residual); bf16 in/out.
+ * epi: 0 plain, 1 GEGLU (Wt/bias rows pre-interleaved in blocks of BN/2; out has N/2 columns).
+ * head_dim > 0: scatter output column n to (n / head_dim) * head_slot + n % head_dim. */
+int ldn_gemm_bf16(const void* A0, int64_t lda0, int K0, const void* A1, int64_t lda1, int K1, const void* Wt, int M,
+                  int N, const float* bias, const float* rowbias, int ld_rowbias, int rows_per_batch,
+                  const void* residual, int64_t ldr, void* out, int64_t ldo, float* out_f32, int epi, int head_dim,
+                  int head_slot, int BN, void* stream);
+/* x: NHWC bf16 [B,H,W,Cin]; Wt: [Cout, 3,3, Cin] bf16; out NHWC bf16 [B,H,W,Cout]; stride 1, pad 1. */
+int ldn_conv3x3_bf16(const void* x, const void* Wt, int B, int H, int W, int Cin, int Cout, const float* bias,
+                     const float* rowbias, int ld_rowbias, const void* residual, void* out, void* stream);
+/* Q: [B*Nq, heads*slot], K: [B*nk_pad, heads*slot], Vt: [vt_rows, B*nk_pad] (all bf16); out: [B*Nq, heads*d]. */
+int ldn_attention_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* Vt, int64_t ldvt,
+                       int64_t vt_rows, int B, int heads, int Nq, int Nk, int nk_pad, int d, int slot, int causal,
+                       float scale, void* out, int64_t ldo, void* stream);
+/* GroupNorm (+SiLU) over NHWC bf16, input may be a channel concat of x0 (C0) and x1 (C1, may be NULL/0). */
+int ldn_groupnorm_bf16(const void* x0, int C0, const void* x1, int C1, int B, int HW, int groups, float eps,
+                       const float* gamma, const float* beta, int silu, void* out, void* stream);
+int ldn_layernorm_bf16(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDN_H */

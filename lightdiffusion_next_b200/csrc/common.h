@@ -1,0 +1,178 @@
+// Host-side shared declarations for the engine's kernels (internal; the public C ABI is include/ldn.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+
+namespace ldn {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error handling: internal code throws, the C ABI catches and records ldn_last_error().
+struct Error : public std::runtime_error {
+  explicit Error(const std::string& s) : std::runtime_error(s) {}
+};
+void set_last_error(const std::string& s);
+#define LDN_CHECK(cond, msg)                                                                       \
+  do {                                                                                             \
+    if (!(cond)) throw ::ldn::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+  } while (0)
+#define LDN_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      throw ::ldn::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + \
+                         cudaGetErrorString(_e) + " in " #expr);                         \
+  } while (0)
+
+// ---- TMA tensor maps (driver entry point resolved lazily; libcuda is not linked)
+// 2-D row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle.
+CUtensorMap make_tmap_2d(const bf16* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// 4-D NHWC bf16 activation [B, H, W, C]; box = [bb, bh, bw, 64 channels], 128B swizzle, OOB -> 0 (conv padding).
+CUtensorMap make_tmap_nhwc(const bf16* base, int B, int H, int W, int C, int bb, int bh, int bw);
+
+// ---- GEMM / implicit-GEMM conv3x3 on tcgen05 (gemm.cu)
+struct GemmParams {
+  CUtensorMap tmA0, tmA1, tmB;
+  int M, N;          // logical output rows / weight rows
+  int BN;            // N tile (multiple of 16, <= 256)
+  int num_k_chunks;  // 64-wide K chunks in total
+  int a0_chunks;     // GEMM mode: chunks taken from tmA0, the rest from tmA1 (virtual concat along K)
+  int stages;
+  int tmem_cols;
+  // conv3x3 geometry (conv != 0): A is a 4-D NHWC map, K = 9 taps x Cin
+  int conv;
+  int H, W, B, cin_chunks, BW, BH, BB, tiles_x, tiles_y;
+  // epilogue
+  int epi;  // 0: out = acc (+bias) (+rowbias) (+residual);  1: GEGLU (value | gate halves of the tile)
+  bf16* out;
+  long long ldo;
+  float* out_f32;  // if non-null, write fp32 here instead of bf16 `out`
+  const float* bias;
+  const float* rowbias;  // [batch, ld_rowbias] added per (batch(row), col)
+  int ld_rowbias;
+  int rows_per_batch;
+  const bf16* residual;
+  long long ldr;
+  int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
+};
+
+struct GemmPlan {
+  GemmParams p;
+  dim3 grid;
+  int smem_bytes;
+};
+
+struct GemmArgs {
+  // operands
+  const bf16* A0 = nullptr;  // [M, K0] (ld lda0), or NHWC activation for conv
+  long long lda0 = 0;
+  int K0 = 0;
+  const bf16* A1 = nullptr;  // optional second K-segment [M, K1]
+  long long lda1 = 0;
+  int K1 = 0;
+  const bf16* Wt = nullptr;  // [N, K] K-major (conv: K = tap*Cin + c)
+  int M = 0, N = 0;
+  // conv
+  bool conv = false;
+  int B = 0, H = 0, W = 0, Cin = 0;
+  // epilogue
+  int epi = 0;
+  bf16* out = nullptr;
+  long long ldo = 0;
+  float* out_f32 = nullptr;
+  const float* bias = nullptr;
+  const float* rowbias = nullptr;
+  int ld_rowbias = 0;
+  int rows_per_batch = 0;
+  const bf16* residual = nullptr;
+  long long ldr = 0;
+  int head_dim = 0, head_slot = 0;
+  int BN = 0;  // 0 = choose
+};
+
+GemmPlan make_gemm_plan(const GemmArgs& a);
+void launch_gemm(const GemmPlan& plan, cudaStream_t stream);
+
+// ---- attention (attention.cu)
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmVt;
+  int heads;
+  int Nq, Nk;        // tokens per (batch) for queries / keys
+  int nk_pad;        // key rows per batch in the K buffer / columns per batch in Vt (>= Nk)
+  int d;             // head dim (output columns per head)
+  int dqk;           // K extent of S = Q K^T, multiple of 16 (>= d)
+  int dv;            // N extent of O = P V, multiple of 16 (>= d)
+  int slot;          // per-head column slot width in the Q / K buffers (multiple of 64)
+  int causal;
+  int kv_stages;
+  float scale_log2;  // softmax scale * log2(e)
+  bf16* out;         // [B*Nq, heads*d]
+  long long ldo;
+};
+struct AttnPlan {
+  AttnParams p;
+  dim3 grid;
+  int smem_bytes;
+};
+struct AttnArgs {
+  const bf16* Q;   // [B*Nq, heads*slot]
+  long long ldq;
+  const bf16* K;   // [B*nk_pad, heads*slot]
+  long long ldk;
+  const bf16* Vt;  // [heads*d (+pad), B*nk_pad], keys contiguous
+  long long ldvt;
+  long long vt_rows;
+  int B, heads, Nq, Nk, nk_pad, d, slot;
+  int causal = 0;
+  float scale;
+  bf16* out;
+  long long ldo;
+};
+AttnPlan make_attn_plan(const AttnArgs& a);
+void launch_attn(const AttnPlan& plan, cudaStream_t stream);
+
+// ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)
+// GroupNorm over NHWC bf16 input that may be a virtual concat of two tensors along C.
+// stats: workspace of 2*B*groups floats (mean, rstd).
+void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
+                      const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws,
+                      cudaStream_t stream);
+void launch_layernorm(const bf16* x, int rows, int C, float eps, const float* gamma, const float* beta, bf16* out,
+                      cudaStream_t stream);
+// out[b, n] = act_in(x[b, :]) . W[n, :] + bias[n]   (tiny-M linear; W bf16 [N, K], x fp32 [Bn, K])
+void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
+                         bool silu_out, float* out, cudaStream_t stream);
+// sigma[B] -> nearest discrete timestep index -> sinusoidal embedding [B, dim] fp32
+void launch_timestep_embed(const float* sigma, int Bn, const float* log_sigmas, int n_sigmas, int dim, float* out,
+                           float* t_index_out, cudaStream_t stream);
+// x NCHW fp32 [B,C,H,W] * 1/sqrt(sigma^2+1) -> NHWC bf16 padded to Cpad channels (zeros)
+void launch_scale_in(const float* x, const float* sigma, int B, int C, int H, int W, int Cpad, bf16* out,
+                     cudaStream_t stream);
+// conv_in: 3x3, Cin=4 (NCHW fp32 input scaled by 1/sqrt(sigma^2+1)), Cout=N -> NHWC bf16
+void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const float* bias, int B, int H, int W,
+                    int Cin, int Cout, bf16* out, cudaStream_t stream);
+// conv_out: 3x3 Cin -> 4 on NHWC bf16 input; writes denoised = x - eps*sigma (NCHW fp32) and optionally eps
+void launch_conv_out(const bf16* h, const bf16* Wt, const float* bias, const float* x, const float* sigma, int B,
+                     int H, int W, int Cin, int Cout, float* denoised, float* eps_out, cudaStream_t stream);
+void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);
+// stride-2 3x3 pad-1 im2col gather: [B,H,W,C] -> [B*(H/2)*(W/2), 9*C]
+void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);
+void launch_fill_bf16(bf16* p, size_t n, float v, cudaStream_t stream);
+// weight ingest: src is fp32 or fp16 (src_dtype 0 = f32, 1 = f16, 2 = bf16)
+void launch_convert_to_bf16(const void* src, int src_dtype, size_t n, bf16* dst, cudaStream_t stream);
+void launch_convert_to_f32(const void* src, int src_dtype, size_t n, float* dst, cudaStream_t stream);
+// OIHW [O,I,kh,kw] -> [O, kh, kw, I] bf16
+void launch_repack_conv_weight(const void* src, int src_dtype, int O, int I, int kh, int kw, bf16* dst,
+                               cudaStream_t stream);
+// CFG combine + sampler update (fp32, elementwise):  see pointwise.cu
+void launch_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
+                     float c1, float c2, const float* noise, float* x_out, float* denoised_out, size_t n,
+                     cudaStream_t stream);
+void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
+                         cudaStream_t stream);
+
+}  // namespace ldn

@@ -1,0 +1,369 @@
+// tcgen05 GEMM and implicit-GEMM conv3x3 for sm_100a.
+//
+//   out[M, N] = A[M, K] * Wt[N, K]^T  (+ bias[N]) (+ rowbias[batch(row), N]) (+ residual[M, N])
+//
+// Replaces, on the reference's UNet path, the cuBLAS/cuDNN library calls made through
+//   src/cond/cast.py:107 (F.linear) and :174 (Conv2d._conv_forward)            [reference file:line]
+// for: ResBlock conv3x3 (src/AutoEncoders/ResBlock.py:251-292), 1x1 skip / proj_in / proj_out
+// (ResBlock.py:294-299, src/NeuralNetwork/transformer.py:294-335), attention projections
+// (src/Attention/Attention.py:85-98) and the GEGLU feed-forward (src/cond/Activation.py:6-31).
+//
+// Design (one 128 x BN output tile per CTA, 2 CTAs resident per SM so one tile's epilogue overlaps the
+// other's main loop):
+//   warp 0      TMA producer: A tile 128 rows x 64 K (bf16, 128B swizzle) + B tile BN x 64 K per stage.
+//               conv3x3 mode: A is a 4-D NHWC tensor map; K chunk = (tap, 64 input channels); the tile is
+//               a (BB, BH, BW) pixel box shifted by the tap offset; TMA out-of-bounds zero fill supplies
+//               the conv padding -> no im2col buffer ever exists.
+//               GEMM mode: A may be a virtual concat of two matrices along K (skip-connection concat).
+//   warp 1      allocates TMEM; lane 0 issues tcgen05.mma (M=128, N=BN, K=16) x 4 per stage, fp32 accum in TMEM,
+//               tcgen05.commit releases the smem stage / publishes the accumulator.
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns, fused bias / time-embedding row bias / residual /
+//               GEGLU (value * gelu_erf(gate)), bf16 (or fp32) store.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ldn {
+
+static constexpr int kBM = 128;
+static constexpr int kBK = 64;
+static constexpr int kGemmThreads = 192;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  const uint32_t a_bytes = kBM * kBK * 2;
+  const uint32_t b_bytes = (uint32_t)BN * kBK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int stages = p.stages;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* acc_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  // tile coordinates
+  const int n0 = blockIdx.x * BN;
+  int m0 = 0, x0 = 0, y0 = 0, b0 = 0;
+  if (p.conv) {
+    int t = blockIdx.y;
+    int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    int ty = t % p.tiles_y;
+    int tb = t / p.tiles_y;
+    x0 = tx * p.BW;
+    y0 = ty * p.BH;
+    b0 = tb * p.BB;
+  } else {
+    m0 = blockIdx.y * kBM;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmB);
+    if (!p.conv && p.a0_chunks < p.num_k_chunks) tma_prefetch_desc(&p.tmA1);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nk = p.num_k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % stages;
+        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+        uint8_t* b_dst = a_dst + a_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        if (p.conv) {
+          const int tap = kc / p.cin_chunks;
+          const int cc = kc - tap * p.cin_chunks;
+          const int dy = tap / 3 - 1;
+          const int dx = tap - (tap / 3) * 3 - 1;
+          tma_load_4d(a_dst, &p.tmA0, &full_bar[s], cc * kBK, x0 + dx, y0 + dy, b0);
+        } else if (kc < p.a0_chunks) {
+          tma_load_2d(a_dst, &p.tmA0, &full_bar[s], kc * kBK, m0);
+        } else {
+          tma_load_2d(a_dst, &p.tmA1, &full_bar[s], (kc - p.a0_chunks) * kBK, m0);
+        }
+        tma_load_2d(b_dst, &p.tmB, &full_bar[s], kc * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBM, (uint32_t)BN);
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % stages;
+        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+        const uint64_t b_desc = make_smem_desc_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+          tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                      (kc > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(acc_bar);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+
+    long long out_row;  // output row index (pixel / token), -1 if masked
+    int batch;
+    if (p.conv) {
+      const int bx = r % p.BW;
+      const int by = (r / p.BW) % p.BH;
+      const int bb = r / (p.BW * p.BH);
+      const int x = x0 + bx, y = y0 + by, b = b0 + bb;
+      const bool ok = (x < p.W) && (y < p.H) && (b < p.B);
+      out_row = ok ? ((long long)(b * p.H + y) * p.W + x) : -1;
+      batch = b;
+    } else {
+      const int m = m0 + r;
+      out_row = (m < p.M) ? m : -1;
+      batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
+    }
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    if (p.epi == 0) {
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (out_row >= 0 && n < p.N) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(p.bias + n + i);
+            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+          }
+        }
+        if (p.rowbias) {
+          const float* rb = p.rowbias + (long long)batch * p.ld_rowbias + n;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(rb + i);
+            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+          }
+        }
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + n);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 rv = rp[h];
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[h * 8 + 2 * i] += bf16_lo(w[i]);
+              f[h * 8 + 2 * i + 1] += bf16_hi(w[i]);
+            }
+          }
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldo + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            int col = n + h * 8;
+            if (p.head_dim > 0) col = (col / p.head_dim) * p.head_slot + (col % p.head_dim);
+            uint4 ov;
+            ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
+            ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
+            ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
+            ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
+            *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + col) = ov;
+          }
+        }
+        }
+        __syncwarp();
+      }
+    } else {
+      // GEGLU: weight rows were interleaved at load time so that this tile holds BN/2 value columns followed
+      // by the BN/2 matching gate columns (Activation.py:30-31: x, gate = proj(x).chunk(2); x * gelu(gate)).
+      const int half = BN / 2;
+      const int o0 = n0 / 2;
+      for (int c = 0; c < half; c += 16) {
+        uint32_t va[16], vg[16];
+        tmem_ld16(t_lane + (uint32_t)c, va);
+        tmem_ld16(t_lane + (uint32_t)(half + c), vg);
+        tmem_ld_wait();
+        if (out_row >= 0 && (n0 + c) < p.N) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = __uint_as_float(va[i]);
+          float g = __uint_as_float(vg[i]);
+          if (p.bias) {
+            a += p.bias[n0 + c + i];
+            g += p.bias[n0 + half + c + i];
+          }
+          f[i] = a * gelu_erf(g);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 ov;
+          ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
+          ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
+          ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
+          ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
+          *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + o0 + c + h * 8) = ov;
+        }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------------- host side
+
+static int pick_bn(int N, bool geglu) {
+  // Prefer tiles that divide N exactly (N in the UNet is 5*64*{1,2,4,8,...}); 160 wastes nothing for 320/640/1280.
+  if (geglu) {
+    const int cands[] = {160, 128, 256, 192, 96, 64, 32};
+    for (int c : cands)
+      if (N % c == 0) return c;
+    return 128;
+  }
+  if (N <= 256 && N % 16 == 0) return N;
+  const int cands[] = {160, 128, 192, 256, 224, 96, 64};
+  for (int c : cands)
+    if (N % c == 0) return c;
+  return 128;
+}
+
+GemmPlan make_gemm_plan(const GemmArgs& a) {
+  GemmPlan plan;
+  GemmParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  LDN_CHECK(a.Wt && a.A0 && (a.out || a.out_f32), "gemm: null operand");
+  LDN_CHECK(a.N % 16 == 0 || a.N % 8 == 0, "gemm: N must be a multiple of 8");
+  int BN = a.BN ? a.BN : pick_bn(a.N, a.epi == 1);
+  if (a.epi == 1) LDN_CHECK(a.N % BN == 0 && BN % 32 == 0, "geglu: N must be a multiple of BN, BN of 32");
+  LDN_CHECK(BN % 16 == 0 && BN >= 16 && BN <= 256, "gemm: bad BN");
+  p.BN = BN;
+  p.M = a.M;
+  p.N = a.N;
+  p.conv = a.conv ? 1 : 0;
+  int K;
+  if (a.conv) {
+    LDN_CHECK(a.Cin % kBK == 0, "conv3x3: Cin must be a multiple of 64");
+    K = 9 * a.Cin;
+    p.cin_chunks = a.Cin / kBK;
+    p.num_k_chunks = 9 * p.cin_chunks;
+    p.a0_chunks = p.num_k_chunks;
+    p.H = a.H;
+    p.W = a.W;
+    p.B = a.B;
+    // pixel box of 128 rows
+    int BW = 1;
+    while (BW < a.W && BW < 128) BW <<= 1;
+    int BH = 1;
+    while (BW * BH < 128 && BH < a.H) BH <<= 1;
+    int BB = 128 / (BW * BH);
+    LDN_CHECK(BW * BH * BB == 128, "conv3x3: cannot form a 128-pixel box");
+    p.BW = BW;
+    p.BH = BH;
+    p.BB = BB;
+    p.tiles_x = (a.W + BW - 1) / BW;
+    p.tiles_y = (a.H + BH - 1) / BH;
+    const int tiles_b = (a.B + BB - 1) / BB;
+    p.tmA0 = make_tmap_nhwc(a.A0, a.B, a.H, a.W, a.Cin, BB, BH, BW);
+    p.tmA1 = p.tmA0;
+    p.M = a.B * a.H * a.W;
+    plan.grid = dim3((a.N + BN - 1) / BN, p.tiles_x * p.tiles_y * tiles_b, 1);
+  } else {
+    LDN_CHECK(a.K0 % 8 == 0 && a.K1 % 8 == 0, "gemm: K must be a multiple of 8");
+    if (a.A1) LDN_CHECK(a.K0 % kBK == 0, "gemm: first K segment must be a multiple of 64");
+    K = a.K0 + (a.A1 ? a.K1 : 0);
+    p.a0_chunks = (a.K0 + kBK - 1) / kBK;
+    p.num_k_chunks = p.a0_chunks + (a.A1 ? (a.K1 + kBK - 1) / kBK : 0);
+    p.tmA0 = make_tmap_2d(a.A0, a.M, a.K0, a.lda0, kBM);
+    p.tmA1 = a.A1 ? make_tmap_2d(a.A1, a.M, a.K1, a.lda1, kBM) : p.tmA0;
+    plan.grid = dim3((a.N + BN - 1) / BN, (a.M + kBM - 1) / kBM, 1);
+  }
+  p.tmB = make_tmap_2d(a.Wt, a.N, K, K, BN);
+  p.epi = a.epi;
+  p.out = a.out;
+  p.ldo = a.ldo;
+  p.out_f32 = a.out_f32;
+  p.bias = a.bias;
+  p.rowbias = a.rowbias;
+  p.ld_rowbias = a.ld_rowbias;
+  p.rows_per_batch = a.rows_per_batch;
+  p.residual = a.residual;
+  p.ldr = a.ldr;
+  p.head_dim = a.head_dim;
+  p.head_slot = a.head_slot;
+  if (a.head_dim > 0) LDN_CHECK(a.head_dim % 8 == 0, "gemm: head_dim must be a multiple of 8");
+
+  int cols = 32;
+  while (cols < BN) cols <<= 1;
+  p.tmem_cols = cols;
+  const int stage_bytes = kBM * kBK * 2 + BN * kBK * 2;
+  // 2 CTAs per SM: (227 KB - 2 KB reserve) / 2 per CTA, minus alignment slack and barriers.
+  const int budget = 113 * 1024 - 1024 - 256;
+  int stages = budget / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  if (stages > p.num_k_chunks) stages = p.num_k_chunks < 1 ? 1 : p.num_k_chunks;
+  p.stages = stages;
+  plan.smem_bytes = stages * stage_bytes + 1024 + 256;
+  return plan;
+}
+
+void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  gemm_tc_kernel<<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+  LDN_CUDA(cudaGetLastError());
+}
+
+}  // namespace ldn

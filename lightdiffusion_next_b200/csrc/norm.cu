@@ -1,0 +1,244 @@
+// GroupNorm(+SiLU) and LayerNorm for token-major (NHWC) bf16 activations. HBM-bound kernels.
+//
+// Reference call sites replaced: F.group_norm via src/cond/cast.py:241 (ResBlock in/out layers
+// src/AutoEncoders/ResBlock.py:252,280 eps 1e-5 + SiLU; SpatialTransformer.norm src/NeuralNetwork/transformer.py:286-293
+// eps 1e-6; VAE Normalize eps 1e-6) and F.layer_norm via cast.py:281 (transformer.py:154-157).
+//
+// GroupNorm input may be the *virtual* channel concat [x0 | x1] of the UNet skip connection
+// (torch.cat([h, hs.pop()], 1), src/NeuralNetwork/unet.py:750): groups may straddle the boundary (C=960, 1920),
+// which is why statistics are accumulated per channel-vector and folded into groups afterwards.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ldn {
+
+// ------------------------------------------------------------------ GroupNorm statistics
+// grid: (splits, B); block: (C/8) * R threads. stats[b][g] = {sum, sumsq} in double (pre-zeroed).
+__global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
+                                int cpg, int rows_per_block, double* __restrict__ stats) {
+  const int C = C0 + C1;
+  const int nvec = C >> 3;
+  const int R = blockDim.x / nvec;
+  const int cv = threadIdx.x % nvec;
+  const int prow = threadIdx.x / nvec;
+  const int b = blockIdx.y;
+  __shared__ float s_sum[32], s_sq[32];
+  if (threadIdx.x < 32) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  if (prow < R) {
+    const int c = cv * 8;
+    const bf16* src;
+    int ld;
+    if (c < C0) {
+      src = x0 + (size_t)b * HW * C0 + c;
+      ld = C0;
+    } else {
+      src = x1 + (size_t)b * HW * C1 + (c - C0);
+      ld = C1;
+    }
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    const int p_begin = blockIdx.x * rows_per_block;
+    const int p_end = min(HW, p_begin + rows_per_block);
+    for (int pix = p_begin + prow; pix < p_end; pix += R) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)pix * ld);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = bf16_lo(w[i]), bb = bf16_hi(w[i]);
+        s[2 * i] += a;
+        q[2 * i] += a * a;
+        s[2 * i + 1] += bb;
+        q[2 * i + 1] += bb * bb;
+      }
+    }
+    // fold the 8 channels into their groups (a vector may straddle two groups)
+    int g_prev = c / cpg;
+    float as = 0.f, aq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / cpg;
+      if (g != g_prev) {
+        atomicAdd(&s_sum[g_prev], as);
+        atomicAdd(&s_sq[g_prev], aq);
+        as = aq = 0.f;
+        g_prev = g;
+      }
+      as += s[i];
+      aq += q[i];
+    }
+    atomicAdd(&s_sum[g_prev], as);
+    atomicAdd(&s_sq[g_prev], aq);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    atomicAdd(&stats[((size_t)b * 32 + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
+    atomicAdd(&stats[((size_t)b * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  }
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------ GroupNorm apply (+SiLU)
+// grid: (pixel chunks, B); dynamic smem: 2*C floats (per-channel scale / shift)
+__global__ void gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
+                                int cpg, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                int silu, const double* __restrict__ stats, bf16* __restrict__ out,
+                                int rows_per_block) {
+  extern __shared__ float s_ab[];
+  const int C = C0 + C1;
+  float* s_a = s_ab;
+  float* s_b = s_ab + C;
+  const int b = blockIdx.y;
+  const double n = (double)HW * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double sum = stats[((size_t)b * 32 + g) * 2 + 0];
+    const double sq = stats[((size_t)b * 32 + g) * 2 + 1];
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float a = rstd * gamma[c];
+    s_a[c] = a;
+    s_b[c] = beta[c] - (float)mean * a;
+  }
+  __syncthreads();
+  const int nvec = C >> 3;
+  const int p_begin = blockIdx.x * rows_per_block;
+  const int p_end = min(HW, p_begin + rows_per_block);
+  const int total = (p_end - p_begin) * nvec;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pix = p_begin + idx / nvec;
+    const int c = (idx % nvec) * 8;
+    const bf16* src = (c < C0) ? x0 + ((size_t)b * HW + pix) * C0 + c : x1 + ((size_t)b * HW + pix) * C1 + (c - C0);
+    const uint4 v = *reinterpret_cast<const uint4*>(src);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = bf16_lo(w[i]) * s_a[c + 2 * i] + s_b[c + 2 * i];
+      float bb = bf16_hi(w[i]) * s_a[c + 2 * i + 1] + s_b[c + 2 * i + 1];
+      if (silu) {
+        a = silu_f(a);
+        bb = silu_f(bb);
+      }
+      o[i] = pack_bf16x2(a, bb);
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t)b * HW + pix) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
+                      const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws,
+                      cudaStream_t stream) {
+  const int C = C0 + C1;
+  LDN_CHECK(groups == 32, "groupnorm: only 32 groups supported");
+  LDN_CHECK(C % 32 == 0 && C % 8 == 0 && C0 % 8 == 0, "groupnorm: channel counts must be multiples of 8/32");
+  LDN_CHECK(C / 8 <= 1024, "groupnorm: too many channels");
+  const int cpg = C / groups;
+  double* stats = reinterpret_cast<double*>(stats_ws);
+  LDN_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * 32 * B, stream));
+  const int nvec = C / 8;
+  int R = 1024 / nvec;
+  if (R > 16) R = 16;
+  const int threads = nvec * R;
+  // enough blocks to fill the machine: ~4 waves of 148 SMs split over B
+  int splits = (148 * 4 + B - 1) / B;
+  int rows_per_block = (HW + splits - 1) / splits;
+  if (rows_per_block < R) rows_per_block = R;
+  splits = (HW + rows_per_block - 1) / rows_per_block;
+  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, stats);
+  LDN_CUDA(cudaGetLastError());
+  int rpb2 = (HW + splits - 1) / splits;
+  const size_t smem = sizeof(float) * 2 * C;
+  gn_apply_kernel<<<dim3((HW + rpb2 - 1) / rpb2, B), 512, smem, stream>>>(x0, C0, x1, C1, HW, cpg, eps, gamma, beta,
+                                                                          silu ? 1 : 0, stats, out, rpb2);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ LayerNorm: one warp per row, row held in registers
+template <int MAXV>
+__global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int C, float eps, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, bf16* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C >> 3;
+  const bf16* src = x + (size_t)warp * C;
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src + vi * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[k][2 * i] = bf16_lo(w[i]);
+        v[k][2 * i + 1] = bf16_hi(w[i]);
+        sum += v[k][2 * i] + v[k][2 * i + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[k][i] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  bf16* dst = out + (size_t)warp * C;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < nvec) {
+      const int c = vi * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        o[i] = pack_bf16x2((v[k][2 * i] - mean) * rstd * g[2 * i] + bb[2 * i],
+                           (v[k][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bb[2 * i + 1]);
+      *reinterpret_cast<uint4*>(dst + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+void launch_layernorm(const bf16* x, int rows, int C, float eps, const float* gamma, const float* beta, bf16* out,
+                      cudaStream_t stream) {
+  LDN_CHECK(C % 8 == 0 && C <= 8 * 32 * 6, "layernorm: C must be a multiple of 8 and <= 1536");
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  const int nvec = C / 8;
+  if (nvec <= 64)
+    layernorm_kernel<2><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
+  else if (nvec <= 96)
+    layernorm_kernel<3><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
+  else
+    layernorm_kernel<6><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
+  LDN_CUDA(cudaGetLastError());
+}
+
+}  // namespace ldn
