@@ -51,8 +51,9 @@ void ldn_destroy(ldn_handle h);
 /* which: 0 = UNet ("model.diffusion_model." prefix stripped), 1 = VAE decoder ("first_stage_model." stripped),
  *        2 = CLIP-L text model ("...text_model." stripped) */
 int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream);
-/* sigma table of the discrete schedule (ModelSamplingDiscrete.sigmas, src/sample/sampling.py:221-356), host ptr */
-int ldn_set_sigmas(ldn_handle h, const float* sigmas_host, int n);
+/* Discrete schedule tables (ModelSamplingDiscrete.sigmas / .log_sigmas, src/sample/sampling.py:221-356): host
+ * pointers, n entries each. log_sigmas is passed separately because the reference computes it in float64. */
+int ldn_set_sigmas(ldn_handle h, const float* sigmas_host, const float* log_sigmas_host, int n);
 
 /* ---- UNet hot path */
 /* ctx: [rows, tokens, 768] fp32 (device). Pre-computes cross-attention K/V for all 16 transformer blocks. */

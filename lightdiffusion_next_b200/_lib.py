@@ -41,7 +41,7 @@ SIGNATURES = {
     "ldn_create": [C.POINTER(ldn_config), C.POINTER(_p)],
     "ldn_destroy": [_p],
     "ldn_load_weights": [_p, _i, C.POINTER(ldn_tensor), _i, _p],
-    "ldn_set_sigmas": [_p, C.POINTER(C.c_float), _i],
+    "ldn_set_sigmas": [_p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i],
     "ldn_set_context": [_p, _p, _i, _i, _p],
     "ldn_unet_denoise": [_p, _p, _p, _p, _i, _i, _i, _p],
     "ldn_cfg_step": [_p, _p, _p, _f, _i, _f, _f, _f, _p, _p, _p, _l, _p],

@@ -1,0 +1,217 @@
+// Engine lifecycle, weight ingest and program execution (C ABI side: ldn_create / ldn_load_weights / ...).
+#include "engine.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace ldn {
+
+void* Arena::alloc(size_t bytes, bool zero) {
+  if (bytes == 0) bytes = 16;
+  bytes = (bytes + 255) & ~size_t(255);
+  void* p = nullptr;
+  LDN_CUDA(cudaMalloc(&p, bytes));
+  if (zero) LDN_CUDA(cudaMemset(p, 0, bytes));
+  blocks.push_back(p);
+  total += bytes;
+  return p;
+}
+void Arena::release() {
+  for (void* p : blocks) cudaFree(p);
+  blocks.clear();
+  total = 0;
+}
+
+void run_program(Program& prog, bool use_graph, cudaStream_t stream) {
+  if (!prog.warmed || !use_graph) {
+    for (auto& s : prog.steps) s(stream);
+    prog.warmed = true;
+    return;
+  }
+  if (!prog.graph) {
+    // Capture on a private stream so the caller's stream state is untouched, then launch on the caller's stream.
+    cudaStream_t cs;
+    LDN_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    LDN_CUDA(cudaStreamSynchronize(stream));
+    LDN_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    try {
+      for (auto& s : prog.steps) s(cs);
+    } catch (...) {
+      cudaStreamEndCapture(cs, &g);
+      if (g) cudaGraphDestroy(g);
+      cudaStreamDestroy(cs);
+      throw;
+    }
+    LDN_CUDA(cudaStreamEndCapture(cs, &g));
+    LDN_CUDA(cudaGraphInstantiate(&prog.graph, g, 0));
+    cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+  }
+  LDN_CUDA(cudaGraphLaunch(prog.graph, stream));
+}
+
+}  // namespace ldn
+
+using namespace ldn;
+
+ldn_engine::ldn_engine() {}
+ldn_engine::~ldn_engine() {}
+
+const DevTensor& ldn_engine::W(int which, const std::string& name) const {
+  auto it = w[which].find(name);
+  LDN_CHECK(it != w[which].end(), "missing weight: " + name);
+  return it->second;
+}
+
+#define LDN_API_BEGIN try {
+#define LDN_API_END                       \
+  }                                       \
+  catch (const std::exception& e) {       \
+    ldn::set_last_error(e.what());        \
+    return 1;                             \
+  }                                       \
+  catch (...) {                           \
+    ldn::set_last_error("unknown error"); \
+    return 2;                             \
+  }                                       \
+  return 0;
+
+extern "C" {
+
+int ldn_create(const ldn_config* cfg, ldn_handle* out) {
+  LDN_API_BEGIN
+  LDN_CHECK(cfg && out, "ldn_create: null argument");
+  int ndev = 0;
+  LDN_CUDA(cudaGetDeviceCount(&ndev));
+  LDN_CHECK(ndev > 0, "ldn_create: no CUDA device (this engine has no CPU fallback)");
+  int dev = 0;
+  LDN_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  LDN_CUDA(cudaGetDeviceProperties(&prop, dev));
+  LDN_CHECK(prop.major == 10, std::string("ldn_create: needs an sm_100 (B200) device, found sm_") +
+                                  std::to_string(prop.major) + std::to_string(prop.minor));
+  ldn_engine* e = new ldn_engine();
+  e->cfg = *cfg;
+  *out = e;
+  LDN_API_END
+}
+
+void ldn_destroy(ldn_handle h) {
+  if (h) delete h;
+}
+
+int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream_) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && tensors && which >= 0 && which < 3, "ldn_load_weights: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  for (int i = 0; i < n; ++i) {
+    const ldn_tensor& t = tensors[i];
+    LDN_CHECK(t.name && t.data && t.ndim >= 1 && t.ndim <= 4, "ldn_load_weights: malformed tensor");
+    std::string name(t.name);
+    DevTensor d;
+    size_t numel = 1;
+    for (int k = 0; k < t.ndim; ++k) numel *= (size_t)t.shape[k];
+    const bool keep_f32 = t.ndim == 1 || name.find("embedding") != std::string::npos;
+    if (keep_f32) {
+      d.is_bf16 = false;
+      d.shape.assign(t.shape, t.shape + t.ndim);
+      d.p = h->weights_arena.alloc(numel * sizeof(float));
+      launch_convert_to_f32(t.data, t.dtype, numel, d.f(), stream);
+    } else if (t.ndim == 4 && t.shape[2] * t.shape[3] > 1) {
+      // OIHW -> [O, kh*kw*I], K index = (ky*kw + kx)*I + c  (K-major operand of the implicit GEMM)
+      d.is_bf16 = true;
+      d.shape = {t.shape[0], t.shape[2] * t.shape[3] * t.shape[1]};
+      d.p = h->weights_arena.alloc(numel * sizeof(bf16));
+      launch_repack_conv_weight(t.data, t.dtype, (int)t.shape[0], (int)t.shape[1], (int)t.shape[2], (int)t.shape[3],
+                                d.b(), stream);
+    } else {
+      d.is_bf16 = true;
+      if (t.ndim == 4)
+        d.shape = {t.shape[0], t.shape[1]};
+      else
+        d.shape.assign(t.shape, t.shape + t.ndim);
+      d.p = h->weights_arena.alloc(numel * sizeof(bf16));
+      launch_convert_to_bf16(t.data, t.dtype, numel, d.b(), stream);
+    }
+    h->w[which][name] = d;
+  }
+  h->finalized[which] = false;
+  LDN_CUDA(cudaStreamSynchronize(stream));
+  LDN_API_END
+}
+
+int ldn_set_sigmas(ldn_handle h, const float* sigmas_host, const float* log_sigmas_host, int n) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && sigmas_host && log_sigmas_host && n > 0, "ldn_set_sigmas: bad argument");
+  h->log_sigmas = h->weights_arena.get<float>(n);
+  h->n_sigmas = n;
+  LDN_CUDA(cudaMemcpy(h->log_sigmas, log_sigmas_host, sizeof(float) * n, cudaMemcpyHostToDevice));
+  LDN_API_END
+}
+
+int ldn_set_context(ldn_handle h, const float* ctx, int rows, int tokens, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && ctx, "ldn_set_context: bad argument");
+  if (!h->finalized[0]) unet_finalize(h, (cudaStream_t)stream);
+  unet_set_context(h, ctx, rows, tokens, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_unet_denoise(ldn_handle h, const float* x, const float* sigma, float* out, int rows, int lat_h, int lat_w,
+                     void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && x && sigma && out, "ldn_unet_denoise: bad argument");
+  if (!h->finalized[0]) unet_finalize(h, (cudaStream_t)stream);
+  unet_denoise(h, x, sigma, out, rows, lat_h, lat_w, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
+                 float c1, float c2, const float* noise, float* x_out, float* denoised_out, int64_t n, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(den_uncond && den_cond, "ldn_cfg_step: bad argument");
+  launch_cfg_step(x, den_uncond, den_cond, cfg, mode, c0, c1, c2, noise, x_out, denoised_out, (size_t)n,
+                  (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, int lat_w, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && z && rgb, "ldn_vae_decode: bad argument");
+  if (!h->finalized[1]) vae_finalize(h, (cudaStream_t)stream);
+  vae_decode(h, z, rgb, B, lat_h, lat_w, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultimate, float* out_last, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && ids, "ldn_clip_encode: bad argument");
+  if (!h->finalized[2]) clip_finalize(h, (cudaStream_t)stream);
+  clip_encode(h, ids, S, out_penultimate, out_last, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_groupnorm_bf16(const void* x0, int C0, const void* x1, int C1, int B, int HW, int groups, float eps,
+                       const float* gamma, const float* beta, int silu, void* out, void* stream) {
+  LDN_API_BEGIN
+  static thread_local float* ws = nullptr;
+  static thread_local int ws_b = 0;
+  if (ws_b < B) {
+    if (ws) cudaFree(ws);
+    LDN_CUDA(cudaMalloc(&ws, sizeof(double) * 64 * B));
+    ws_b = B;
+  }
+  launch_groupnorm((const bf16*)x0, C0, (const bf16*)x1, C1, B, HW, groups, eps, gamma, beta, silu != 0, (bf16*)out, ws,
+                   (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_layernorm_bf16(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
+                       void* stream) {
+  LDN_API_BEGIN
+  launch_layernorm((const bf16*)x, rows, C, eps, gamma, beta, (bf16*)out, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+}  // extern "C"

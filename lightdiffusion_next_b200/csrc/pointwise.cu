@@ -1,0 +1,461 @@
+// Small / HBM-bound kernels around the tensor-core path: time embedding, tiny-M linears, conv_in / conv_out,
+// nearest 2x upsample, stride-2 patch gather, CFG + solver step, weight ingest.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ldn {
+
+__device__ __forceinline__ float silu_p(float x) { return x / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float load_as_f32(const void* src, int dtype, size_t i) {
+  if (dtype == 0) return reinterpret_cast<const float*>(src)[i];
+  if (dtype == 1) return __half2float(reinterpret_cast<const __half*>(src)[i]);
+  return __bfloat162float(reinterpret_cast<const bf16*>(src)[i]);
+}
+
+// ------------------------------------------------------------------ timestep embedding
+// Reference: ModelSamplingDiscrete.timestep (src/sample/sampling.py:309-320): t = argmin_k |log(sigma) - log_sigmas[k]|;
+// timestep_embedding (src/sample/sampling_util.py:56-76): cat(cos(t*f), sin(t*f)), f_i = exp(-ln(1e4) * i / half).
+// grid: B blocks of 256 threads.
+__global__ void timestep_embed_kernel(const float* __restrict__ sigma, const float* __restrict__ log_sigmas,
+                                      int n_sigmas, int dim, float* __restrict__ out, float* __restrict__ t_out) {
+  const int b = blockIdx.x;
+  __shared__ float s_val[256];
+  __shared__ int s_idx[256];
+  const float ls = logf(sigma[b]);
+  float best = INFINITY;
+  int besti = 0x7fffffff;
+  for (int k = threadIdx.x; k < n_sigmas; k += blockDim.x) {
+    const float d = fabsf(ls - log_sigmas[k]);
+    if (d < best) {  // strided ascending k per thread: first minimum kept
+      best = d;
+      besti = k;
+    }
+  }
+  s_val[threadIdx.x] = best;
+  s_idx[threadIdx.x] = besti;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float v2 = s_val[threadIdx.x + o];
+      const int i2 = s_idx[threadIdx.x + o];
+      if (v2 < s_val[threadIdx.x] || (v2 == s_val[threadIdx.x] && i2 < s_idx[threadIdx.x])) {
+        s_val[threadIdx.x] = v2;
+        s_idx[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  const float t = (float)s_idx[0];
+  if (threadIdx.x == 0 && t_out) t_out[b] = t;
+  const int half = dim / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf(-9.210340371976184f * (float)i / (float)half);  // ln(10000)
+    const float a = t * f;
+    out[(size_t)b * dim + i] = cosf(a);
+    out[(size_t)b * dim + half + i] = sinf(a);
+  }
+}
+
+void launch_timestep_embed(const float* sigma, int Bn, const float* log_sigmas, int n_sigmas, int dim, float* out,
+                           float* t_index_out, cudaStream_t stream) {
+  timestep_embed_kernel<<<Bn, 256, 0, stream>>>(sigma, log_sigmas, n_sigmas, dim, out, t_index_out);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ tiny-M linear: one warp per output feature
+__global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, const bf16* __restrict__ W,
+                                    const float* __restrict__ bias, int N, int silu_in, int silu_out,
+                                    float* __restrict__ out) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const bf16* w = W + (size_t)n * K;
+  for (int b0 = 0; b0 < Bn; b0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 u = *reinterpret_cast<const uint4*>(w + k);
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+      float wf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        wf[2 * i] = bf16_lo(ww[i]);
+        wf[2 * i + 1] = bf16_hi(ww[i]);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (b0 + r < Bn) {
+          const float* xr = x + (size_t)(b0 + r) * K + k;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float xv = xr[i];
+            if (silu_in) xv = silu_p(xv);
+            acc[r] = fmaf(xv, wf[i], acc[r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float v = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && b0 + r < Bn) {
+        v += bias ? bias[n] : 0.f;
+        if (silu_out) v = silu_p(v);
+        out[(size_t)(b0 + r) * N + n] = v;
+      }
+    }
+  }
+}
+
+void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
+                         bool silu_out, float* out, cudaStream_t stream) {
+  LDN_CHECK(K % 8 == 0, "small_linear: K must be a multiple of 8");
+  const int threads = 256;
+  const int blocks = (N * 32 + threads - 1) / threads;
+  small_linear_kernel<<<blocks, threads, 0, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ conv_in: 3x3, tiny Cin, NCHW fp32 -> NHWC bf16
+// Fuses BaseModel.apply_model's input scaling x / sqrt(sigma^2 + 1) (src/sample/sampling.py:29-40).
+// Wt: [Cout, 3, 3, Cin] bf16. thread = (pixel, 8 output channels).
+__global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
+                               const bf16* __restrict__ Wt, const float* __restrict__ bias, int B, int H, int W, int Cin,
+                               int Cout, bf16* __restrict__ out) {
+  extern __shared__ float s_w[];  // [Cout][9*Cin]
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) s_w[i] = __bfloat162float(Wt[i]);
+  __syncthreads();
+  const int groups = Cout / 8;
+  const size_t total = (size_t)B * H * W * groups;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const size_t pix = idx / groups;
+    const int xw = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int b = (int)(pix / ((size_t)W * H));
+    const float sg = sigma ? sigma[b] : 0.f;
+    const float scale = sigma ? rsqrtf(sg * sg + 1.f) : 1.f;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bias ? bias[g * 8 + i] : 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = xw + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        for (int c = 0; c < Cin; ++c) {
+          const float v = x[(((size_t)b * Cin + c) * H + yy) * W + xx] * scale;
+          const int k = (ky * 3 + kx) * Cin + c;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, s_w[(g * 8 + i) * K + k], acc[i]);
+        }
+      }
+    }
+    uint4 ov;
+    ov.x = pack_bf16x2(acc[0], acc[1]);
+    ov.y = pack_bf16x2(acc[2], acc[3]);
+    ov.z = pack_bf16x2(acc[4], acc[5]);
+    ov.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + pix * Cout + g * 8) = ov;
+  }
+}
+
+void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const float* bias, int B, int H, int W,
+                    int Cin, int Cout, bf16* out, cudaStream_t stream) {
+  LDN_CHECK(Cout % 8 == 0, "conv_in: Cout must be a multiple of 8");
+  const size_t smem = sizeof(float) * Cout * 9 * Cin;
+  LDN_CHECK(smem <= 200 * 1024, "conv_in: weights do not fit in shared memory");
+  static bool attr = false;
+  if (!attr) {
+    LDN_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  const size_t total = (size_t)B * H * W * (Cout / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  conv_in_kernel<<<blocks, 256, smem, stream>>>(x, sigma, Wt, bias, B, H, W, Cin, Cout, out);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ conv_out: 3x3, Cin -> tiny Cout, one warp per pixel
+// Input is the already normalised+SiLU'd NHWC bf16 tensor. Fuses denoised = x - eps * sigma
+// (EPS.calculate_denoised, src/sample/sampling.py:42-56) and writes NCHW fp32.
+template <int COUT>
+__global__ void conv_out_kernel(const bf16* __restrict__ h, const bf16* __restrict__ Wt, const float* __restrict__ bias,
+                                const float* __restrict__ x, const float* __restrict__ sigma, int B, int H, int W,
+                                int Cin, float* __restrict__ denoised, float* __restrict__ eps_out) {
+  extern __shared__ float s_w[];  // [COUT][9*Cin]
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < COUT * K; i += blockDim.x) s_w[i] = __bfloat162float(Wt[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const size_t npix = (size_t)B * H * W;
+  const int nvec = Cin >> 3;
+  for (size_t pix = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < npix;
+       pix += (size_t)gridDim.x * warps_per_block) {
+    const int xw = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int b = (int)(pix / ((size_t)W * H));
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = xw + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const bf16* src = h + (((size_t)b * H + yy) * W + xx) * Cin;
+        const int kbase = (ky * 3 + kx) * Cin;
+        for (int v = lane; v < nvec; v += 32) {
+          const uint4 u = *reinterpret_cast<const uint4*>(src + v * 8);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[2 * i] = bf16_lo(w[i]);
+            f[2 * i + 1] = bf16_hi(w[i]);
+          }
+#pragma unroll
+          for (int o = 0; o < COUT; ++o) {
+            const float* wr = s_w + o * K + kbase + v * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[o] = fmaf(f[i], wr[i], acc[o]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float e = acc[o] + (bias ? bias[o] : 0.f);
+        const size_t oi = (((size_t)b * COUT + o) * H + y) * W + xw;
+        if (eps_out) eps_out[oi] = e;
+        if (denoised) denoised[oi] = x[oi] - e * sigma[b];
+      }
+    }
+  }
+}
+
+void launch_conv_out(const bf16* h, const bf16* Wt, const float* bias, const float* x, const float* sigma, int B,
+                     int H, int W, int Cin, int Cout, float* denoised, float* eps_out, cudaStream_t stream) {
+  LDN_CHECK(Cin % 8 == 0, "conv_out: Cin must be a multiple of 8");
+  const size_t smem = sizeof(float) * Cout * 9 * Cin;
+  LDN_CHECK(smem <= 200 * 1024, "conv_out: weights do not fit in shared memory");
+  const int blocks = 148 * 2;
+  if (Cout == 4) {
+    static bool attr = false;
+    if (!attr) {
+      LDN_CUDA(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    conv_out_kernel<4><<<blocks, 512, smem, stream>>>(h, Wt, bias, x, sigma, B, H, W, Cin, denoised, eps_out);
+  } else if (Cout == 3) {
+    static bool attr = false;
+    if (!attr) {
+      LDN_CUDA(cudaFuncSetAttribute(conv_out_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    conv_out_kernel<3><<<blocks, 512, smem, stream>>>(h, Wt, bias, x, sigma, B, H, W, Cin, denoised, eps_out);
+  } else {
+    LDN_CHECK(false, "conv_out: only Cout 3 or 4");
+  }
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ nearest 2x upsample (F.interpolate nearest, ResBlock.py:135)
+__global__ void upsample2x_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ out) {
+  const int nvec = C >> 3;
+  const size_t total = (size_t)B * (2 * H) * (2 * W) * nvec;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % nvec);
+    size_t pix = idx / nvec;
+    const int ox = (int)(pix % (2 * W));
+    const int oy = (int)((pix / (2 * W)) % (2 * H));
+    const int b = (int)(pix / ((size_t)4 * W * H));
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + (oy >> 1)) * W + (ox >> 1)) * C + v * 8);
+    *reinterpret_cast<uint4*>(out + pix * C + v * 8) = u;
+  }
+}
+void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream) {
+  LDN_CHECK(C % 8 == 0, "upsample: C % 8");
+  const size_t total = (size_t)B * 4 * H * W * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<blocks, 256, 0, stream>>>(x, B, H, W, C, out);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ stride-2 3x3 pad-1 patch gather (Downsample1, ResBlock.py:173-182)
+// out[(b,oy,ox), tap*C + c] = x[b, 2oy+ky-1, 2ox+kx-1, c]
+__global__ void im2col_s2_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int nvec = C >> 3;
+  const size_t total = (size_t)B * Ho * Wo * 9 * nvec;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % nvec);
+    size_t r = idx / nvec;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int ox = (int)(r % Wo);
+    const int oy = (int)((r / Wo) % Ho);
+    const int b = (int)(r / ((size_t)Wo * Ho));
+    const int yy = 2 * oy + tap / 3 - 1;
+    const int xx = 2 * ox + tap % 3 - 1;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      u = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + v * 8);
+    *reinterpret_cast<uint4*>(out + (r * 9 + tap) * C + v * 8) = u;
+  }
+}
+void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream) {
+  LDN_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad shape");
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col_s2_kernel<<<blocks, 256, 0, stream>>>(x, B, H, W, C, out);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ fills / conversions (weight ingest)
+__global__ void fill_bf16_kernel(bf16* p, size_t n, float v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = __float2bfloat16(v);
+}
+void launch_fill_bf16(bf16* p, size_t n, float v, cudaStream_t stream) {
+  if (n == 0) return;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fill_bf16_kernel<<<blocks, 256, 0, stream>>>(p, n, v);
+  LDN_CUDA(cudaGetLastError());
+}
+
+__global__ void to_bf16_kernel(const void* src, int dtype, size_t n, bf16* dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(load_as_f32(src, dtype, i));
+}
+__global__ void to_f32_kernel(const void* src, int dtype, size_t n, float* dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = load_as_f32(src, dtype, i);
+}
+void launch_convert_to_bf16(const void* src, int src_dtype, size_t n, bf16* dst, cudaStream_t stream) {
+  if (n == 0) return;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  to_bf16_kernel<<<blocks, 256, 0, stream>>>(src, src_dtype, n, dst);
+  LDN_CUDA(cudaGetLastError());
+}
+void launch_convert_to_f32(const void* src, int src_dtype, size_t n, float* dst, cudaStream_t stream) {
+  if (n == 0) return;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  to_f32_kernel<<<blocks, 256, 0, stream>>>(src, src_dtype, n, dst);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// OIHW -> O,kh,kw,I
+__global__ void repack_conv_kernel(const void* src, int dtype, int O, int I, int kh, int kw, bf16* dst) {
+  const size_t n = (size_t)O * I * kh * kw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // i indexes dst: ((o*kh + y)*kw + x)*I + c
+    const int c = (int)(i % I);
+    size_t r = i / I;
+    const int xk = (int)(r % kw);
+    r /= kw;
+    const int yk = (int)(r % kh);
+    const int o = (int)(r / kh);
+    dst[i] = __float2bfloat16(load_as_f32(src, dtype, (((size_t)o * I + c) * kh + yk) * kw + xk));
+  }
+}
+void launch_repack_conv_weight(const void* src, int src_dtype, int O, int I, int kh, int kw, bf16* dst,
+                               cudaStream_t stream) {
+  const size_t n = (size_t)O * I * kh * kw;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  repack_conv_kernel<<<blocks, 256, 0, stream>>>(src, src_dtype, O, I, kh, kw, dst);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ CFG combine + solver update
+// denoised = uncond + (cond - uncond) * cfg                     (torch.lerp, src/sample/CFG.py:55-60)
+// mode 0: x' = c0 * x - c1 * denoised                           (dpmpp_2m_cfgpp as executed: samplers.py:952-953,
+//                                                                 c0 = sigma_next/sigma, c1 = expm1(-h))
+// mode 1: d = (x - denoised) * c2 ; x' = x + d * c0 + noise*c1  (euler ancestral: samplers.py:728-732,
+//                                                                 c2 = 1/sigma, c0 = sigma_down - sigma, c1 = sigma_up)
+// mode 2: denoised only
+__global__ void cfg_step_kernel(const float* __restrict__ x, const float* __restrict__ du, const float* __restrict__ dc,
+                                float cfg, int mode, float c0, float c1, float c2, const float* __restrict__ noise,
+                                float* __restrict__ x_out, float* __restrict__ den_out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float u = du[i], c = dc[i];
+    // torch.lerp(start=u, end=c, weight=cfg): weight >= 0.5 uses end - (end-start)*(1-w)
+    const float diff = c - u;
+    const float den = (fabsf(cfg) < 0.5f) ? (u + cfg * diff) : (c - diff * (1.f - cfg));
+    if (den_out) den_out[i] = den;
+    if (mode == 0) {
+      x_out[i] = c0 * x[i] - c1 * den;
+    } else if (mode == 1) {
+      const float xv = x[i];
+      const float d = (xv - den) * c2;
+      float r = xv + d * c0;
+      if (noise) r += noise[i] * c1;
+      x_out[i] = r;
+    }
+  }
+}
+void launch_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
+                     float c1, float c2, const float* noise, float* x_out, float* denoised_out, size_t n,
+                     cudaStream_t stream) {
+  if (n == 0) return;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cfg_step_kernel<<<blocks, 256, 0, stream>>>(x, den_uncond, den_cond, cfg, mode, c0, c1, c2, noise, x_out,
+                                              denoised_out, n);
+  LDN_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ row softmax (VAE mid attention, materialised scores)
+// out[r, :] = softmax(in[r, :] * scale); one block per row.
+__global__ void softmax_rows_kernel(const bf16* __restrict__ in, long long ld_in, bf16* __restrict__ out,
+                                    long long ld_out, int cols, float scale) {
+  const bf16* src = in + (size_t)blockIdx.x * ld_in;
+  bf16* dst = out + (size_t)blockIdx.x * ld_out;
+  __shared__ float red[32];
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, __bfloat162float(src[c]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += __expf((__bfloat162float(src[c]) - mx) * scale);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    dst[c] = __float2bfloat16(__expf((__bfloat162float(src[c]) - mx) * scale) * inv);
+}
+void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
+                         cudaStream_t stream) {
+  softmax_rows_kernel<<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+  LDN_CUDA(cudaGetLastError());
+}
+
+}  // namespace ldn

@@ -1,0 +1,135 @@
+"""Python host for libldn.so: owns an engine handle, feeds it torch CUDA tensors by pointer.
+
+PyTorch is plumbing here (device memory, streams, RNG); every FLOP of the UNet / VAE / CLIP forward runs in the
+hand-written sm_100a kernels behind the C ABI (include/ldn.h).  There is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .schedule import DiscreteSchedule
+
+_DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+UNET, VAE, CLIP = 0, 1, 2
+
+
+class Engine:
+    """One engine per GPU (per process).  Thread-compatible, not thread-safe."""
+
+    def __init__(self, max_rows: int = 2, max_h: int = 128, max_w: int = 128, max_ctx_tokens: int = 77,
+                 use_graph: bool = True, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise L.LdnError("no CUDA device: the B200 engine has no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.lib = L.load()
+        cfg = L.ldn_config(max_rows, max_h, max_w, max_ctx_tokens, int(use_graph))
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.schedule = DiscreteSchedule()
+        sig = self.schedule.sigmas.contiguous()
+        lsig = self.schedule.log_sigmas.contiguous()
+        L.check(self.lib.ldn_set_sigmas(self.h, C.cast(sig.data_ptr(), C.POINTER(C.c_float)),
+                                        C.cast(lsig.data_ptr(), C.POINTER(C.c_float)), sig.numel()))
+        self._ctx_key = None
+        self._keep = []
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.ldn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, which: int, state_dict: Dict[str, torch.Tensor], chunk: int = 64) -> None:
+        """state_dict: LDM key names with the model prefix stripped; tensors on any device, fp32/fp16/bf16."""
+        items = list(state_dict.items())
+        with torch.cuda.device(self.device):
+            stream = L.cur_stream()
+            for i in range(0, len(items), chunk):
+                part = items[i:i + chunk]
+                arr = (L.ldn_tensor * len(part))()
+                keep = []
+                for j, (name, t) in enumerate(part):
+                    if t.dtype not in _DTYPE_CODE:
+                        t = t.float()
+                    t = t.detach().to(self.device, non_blocking=True).contiguous()
+                    keep.append(t)
+                    arr[j].name = name.encode()
+                    arr[j].data = t.data_ptr()
+                    arr[j].dtype = _DTYPE_CODE[t.dtype]
+                    arr[j].ndim = t.dim()
+                    for k, s in enumerate(t.shape):
+                        arr[j].shape[k] = s
+                L.check(self.lib.ldn_load_weights(self.h, which, arr, len(part), stream))
+                del keep
+        self._ctx_key = None
+
+    def load_unet(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        self.load_weights(UNET, state_dict)
+
+    def load_vae(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        self.load_weights(VAE, state_dict)
+
+    def load_clip(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        self.load_weights(CLIP, state_dict)
+
+    # ------------------------------------------------------------------ UNet hot path
+    def set_context(self, ctx: torch.Tensor) -> None:
+        """ctx: [rows, tokens, 768]; rows ordered as the UNet batch rows (uncond first, then cond)."""
+        ctx = ctx.to(self.device, torch.float32).contiguous()
+        rows, tokens, _ = ctx.shape
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_set_context(self.h, ctx.data_ptr(), rows, tokens, L.cur_stream()))
+        self._keep = [ctx]
+
+    def denoise(self, x: torch.Tensor, sigma: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [rows,4,h,w] fp32, sigma [rows] fp32 -> denoised = x - eps*sigma (BaseModel.apply_model semantics)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        sigma = sigma.to(self.device, torch.float32).contiguous()
+        if out is None:
+            out = torch.empty_like(x)
+        rows, _, h, w = x.shape
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_unet_denoise(self.h, x.data_ptr(), sigma.data_ptr(), out.data_ptr(), rows, h, w,
+                                              L.cur_stream()))
+        return out
+
+    def cfg_step(self, x, den_uncond, den_cond, cfg: float, mode: int, c0: float = 0.0, c1: float = 0.0,
+                 c2: float = 0.0, noise=None, x_out=None, denoised_out=None) -> None:
+        n = den_uncond.numel()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_cfg_step(L.ptr(x), den_uncond.data_ptr(), den_cond.data_ptr(), float(cfg), mode,
+                                          float(c0), float(c1), float(c2), L.ptr(noise), L.ptr(x_out),
+                                          L.ptr(denoised_out), n, L.cur_stream()))
+
+    # ------------------------------------------------------------------ VAE / CLIP
+    def vae_decode(self, z: torch.Tensor) -> torch.Tensor:
+        """z [B,4,h,w] fp32 (already / 0.18215) -> [B,8h,8w,3] fp32 in [0,1] (VAE.decode semantics)."""
+        z = z.to(self.device, torch.float32).contiguous()
+        B, _, h, w = z.shape
+        out = torch.empty(B, 8 * h, 8 * w, 3, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_vae_decode(self.h, z.data_ptr(), out.data_ptr(), B, h, w, L.cur_stream()))
+        return out
+
+    def clip_encode(self, ids: torch.Tensor):
+        """ids [S,77] int64 -> (penultimate-layer output after final LN, last-layer output after final LN)."""
+        ids = ids.to(self.device, torch.int64).contiguous()
+        S = ids.shape[0]
+        pen = torch.empty(S, 77, 768, device=self.device, dtype=torch.float32)
+        last = torch.empty(S, 77, 768, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_clip_encode(self.h, ids.data_ptr(), S, pen.data_ptr(), last.data_ptr(),
+                                             L.cur_stream()))
+        return pen, last
