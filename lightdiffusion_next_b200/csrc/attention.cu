@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
         uint8_t* v_dst = k_dst + k_bytes;
         mbar_arrive_expect_tx(&kv_full[s], stage_bytes);
         const int key0 = b * p.nk_pad + j * kTileK;
+        const int krow0 = b * p.k_batch_stride + j * kTileK;
         for (int a = 0; a < nqk_atoms; ++a)
-          tma_load_2d(k_dst + a * atom_bytes, &p.tmK, &kv_full[s], h * p.slot + a * 64, key0);
+          tma_load_2d(k_dst + a * atom_bytes, &p.tmK, &kv_full[s], h * p.slot + a * 64, krow0);
         tma_load_2d(v_dst, &p.tmVt, &kv_full[s], key0, h * p.d);
         tma_load_2d(v_dst + vt_atom_bytes, &p.tmVt, &kv_full[s], key0 + 64, h * p.d);
       }
@@ -275,6 +276,8 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   p.Nq = a.Nq;
   p.Nk = a.Nk;
   p.nk_pad = a.nk_pad;
+  p.k_batch_stride = a.kv_batch_stride > 0 ? a.kv_batch_stride : a.nk_pad;
+  LDN_CHECK(a.nk_pad % 8 == 0, "attention: V^T batch stride must be a multiple of 8 (16-byte TMA box alignment)");
   p.d = a.d;
   p.dqk = dp;
   p.dv = dp;
@@ -284,7 +287,7 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   p.out = a.out;
   p.ldo = a.ldo;
   p.tmQ = make_tmap_2d(a.Q, (uint64_t)a.B * a.Nq, (uint64_t)a.heads * a.slot, a.ldq, 128);
-  p.tmK = make_tmap_2d(a.K, (uint64_t)a.B * a.nk_pad, (uint64_t)a.heads * a.slot, a.ldk, 128);
+  p.tmK = make_tmap_2d(a.K, (uint64_t)a.B * p.k_batch_stride, (uint64_t)a.heads * a.slot, a.ldk, 128);
   p.tmVt = make_tmap_2d(a.Vt, (uint64_t)a.vt_rows, (uint64_t)a.B * a.nk_pad, a.ldvt, dp);
   const int nqk_atoms = (dp + 63) / 64;
   const int q_bytes = nqk_atoms * 16384;

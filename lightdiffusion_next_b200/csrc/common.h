@@ -102,7 +102,8 @@ struct AttnParams {
   CUtensorMap tmQ, tmK, tmVt;
   int heads;
   int Nq, Nk;        // tokens per (batch) for queries / keys
-  int nk_pad;        // key rows per batch in the K buffer / columns per batch in Vt (>= Nk)
+  int nk_pad;        // columns per batch in Vt (>= Nk)
+  int k_batch_stride; // key rows per batch in the K buffer
   int d;             // head dim (output columns per head)
   int dqk;           // K extent of S = Q K^T, multiple of 16 (>= d)
   int dv;            // N extent of O = P V, multiple of 16 (>= d)
@@ -127,6 +128,7 @@ struct AttnArgs {
   long long ldvt;
   long long vt_rows;
   int B, heads, Nq, Nk, nk_pad, d, slot;
+  int kv_batch_stride = 0;  // K rows per batch (0 = nk_pad)
   int causal = 0;
   float scale;
   bf16* out;

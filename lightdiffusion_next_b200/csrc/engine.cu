@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace ldn {
 
@@ -24,7 +25,15 @@ void Arena::release() {
 
 void run_program(Program& prog, bool use_graph, cudaStream_t stream) {
   if (!prog.warmed || !use_graph) {
-    for (auto& s : prog.steps) s(stream);
+    static const bool debug_sync = getenv("LDN_DEBUG_SYNC") != nullptr;
+    for (size_t i = 0; i < prog.steps.size(); ++i) {
+      prog.steps[i](stream);
+      if (debug_sync) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess)
+          throw Error("step " + std::to_string(i) + " (" + prog.names[i] + ") failed: " + cudaGetErrorString(e));
+      }
+    }
     prog.warmed = true;
     return;
   }

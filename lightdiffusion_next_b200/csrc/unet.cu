@@ -45,6 +45,19 @@ __global__ void pad_context_kernel(const float* __restrict__ ctx, int rows, int 
   }
 }
 
+// dst[c, b*nk_pad + k] = src[c, b*N + k]  (only used when N % 8 != 0: TMA box starts must be 16-byte aligned)
+__global__ void pad_vt_cols_kernel(const bf16* __restrict__ src, int C, int Bn, int N, int nk_pad,
+                                   bf16* __restrict__ dst) {
+  const size_t total = (size_t)C * Bn * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % N);
+    const size_t cb = i / N;
+    const int b = (int)(cb % Bn);
+    const size_t c = cb / Bn;
+    dst[(c * Bn + b) * nk_pad + k] = src[i];
+  }
+}
+
 }  // namespace ldn
 
 using namespace ldn;
@@ -316,7 +329,9 @@ struct Builder {
   int B, H0, W0;
   // scratch (sized for the largest layer)
   bf16 *sA = nullptr, *sB = nullptr, *sC = nullptr, *sO = nullptr, *sG = nullptr, *sVt = nullptr, *sCol = nullptr;
+  bf16* sVtPad = nullptr;  // zero-initialised, only used for levels whose token count is not a multiple of 8
   std::vector<bf16*> sQK;  // per level
+  size_t vt_pad_elems = 0;
   float* gn_ws = nullptr;
   float *temb = nullptr, *emb1 = nullptr, *emb = nullptr, *emb_all = nullptr;
 
@@ -416,6 +431,21 @@ struct Builder {
       at.Q = QK; at.ldq = ldqk; at.K = QK + (size_t)U.heads * s.slot; at.ldk = ldqk;
       at.Vt = sVt; at.ldvt = T; at.vt_rows = C;
       at.B = B; at.heads = U.heads; at.Nq = N; at.Nk = N; at.nk_pad = N; at.d = s.d; at.slot = s.slot;
+      if (N % 8 != 0) {
+        // per-batch key offsets b*N would start TMA boxes at non-16B-aligned addresses: re-lay V^T with padded batches
+        const int npad = (N + 7) / 8 * 8;
+        LDN_CHECK((size_t)C * B * npad <= vt_pad_elems, "V^T pad scratch too small");
+        const bf16* src = sVt;
+        bf16* dst = sVtPad;
+        const int Bn = B;
+        add(tb + ".attn1.vt_pad", [=](cudaStream_t st) {
+          pad_vt_cols_kernel<<<64, 256, 0, st>>>(src, C, Bn, N, npad, dst);
+          LDN_CUDA(cudaGetLastError());
+        });
+        at.Vt = sVtPad; at.ldvt = (long long)B * npad;
+        at.kv_batch_stride = N;  // K rows stay dense (row offsets have no alignment constraint)
+        at.nk_pad = npad;
+      }
       at.scale = scale; at.out = sO; at.ldo = C;
       AttnPlan plan = make_attn_plan(at);
       add(tb + ".attn1.sdpa", [plan](cudaStream_t st) { launch_attn(plan, st); });
@@ -500,6 +530,8 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
   bd.sC = A.get<bf16>(max_act);
   bd.sO = A.get<bf16>(max_act);
   bd.sVt = A.get<bf16>(max_act);
+  bd.vt_pad_elems = (size_t)1280 * B * 8 * 8;  // only tiny token counts (< 64) can be non-multiples of 8
+  bd.sVtPad = A.get<bf16>(bd.vt_pad_elems, true);
   bd.sG = A.get<bf16>(std::max<size_t>(max_geglu, 16));
   bd.sCol = A.get<bf16>(std::max<size_t>(max_col, 16));
   {
