@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the SD1.5 sampler hot path on B200 (metric of BASELINE.json: UNet sampler iterations / s).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+1 step ("it") = one sampler iteration of config 2 (SD1.5 1024x1024, dpmpp_2m_cfgpp, bs=1 per GPU): one CFG-batched
+(uncond+cond => 2 rows) UNet forward with EPS scaling + CFG combine + solver update.  Full resolution every step
+(multiscale off) so every step is the 9.348 TFLOP workload BASELINE.md quotes.  Synthetic seeded weights
+(no checkpoints exist offline).  N > 1: one process per GPU (torchrun), each rank owns its own image(s) for the whole
+trajectory, no data-path collective (weak scaling); value = all ranks' iterations / max-over-ranks device time.
+
+--impl reference: the CPU arm.  The reference is Python and cannot travel to the GPU box, so this times the oracle port
+(oracle/sd15_oracle.py, pinned against the reference's own outputs) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNET_TFLOP_1024 = 9.348  # per CFG step bs=1 (B=2), BASELINE.md §2 (measured on the reference module)
+UNET_TFLOP_512 = 1.607
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return dict(bf16=float(d.get("bf16_tflops", 1590.0)), bf16_sus=float(d.get("bf16_tflops_sustained", 1400.0)),
+                        hbm=float(d.get("hbm_gbs", 6650.0)), source="measured")
+        except Exception:
+            pass
+    return dict(bf16=1590.0, bf16_sus=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_step_time(lat: int, max_seconds: float, max_steps: int, warmup: int):
+    """Times oracle CFG steps (2-row UNet forward + lerp + dpmpp_2m update) on the host cores."""
+    import torch
+    from oracle import sd15_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_grad_enabled(False)
+    sd = O.synth_state_dict(O.unet_param_shapes())
+    g = torch.Generator().manual_seed(1234)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    x = torch.randn(1, 4, lat, lat, generator=g) * 14.6
+    tables = O.make_sigma_tables()
+    sig = O.calculate_sigmas("karras", 30)
+
+    def step(i, x):
+        s = sig[i] * x.new_ones([1])
+        den = O.cfg_denoise(lambda a, b, c: O.apply_model(sd, a, b, c, tables), x, s, ctx[1:2], ctx[0:1], 7.0)
+        return (sig[i + 1] / sig[i]) * x - torch.expm1(torch.log(sig[i + 1] / sig[i])) * den
+
+    t_start = time.time()
+    done_w = 0
+    for i in range(warmup):
+        if time.time() - t_start > max_seconds * 0.4:
+            break
+        x = step(i, x)
+        done_w += 1
+    t0 = time.time()
+    n = 0
+    while n < max_steps:
+        x = step(done_w + n, x)
+        n += 1
+        if time.time() - t_start > max_seconds:
+            break
+    dt = time.time() - t0
+    return n, dt, done_w, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    """CPU arm (see module docstring). Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lat = args.size // 8
+    n, dt, done_w, threads = cpu_oracle_step_time(lat, max_seconds=150.0, max_steps=max(1, args.steps), warmup=args.warmup)
+    v = n / dt
+    sample = (f"{n} timed + {done_w} warm-up full {args.size}x{args.size} CFG steps (2-row UNet fwd + CFG + dpmpp_2m update) "
+              f"of the oracle port (torch fp32 CPU), capped at 150 s wall")
+    line = {
+        "impl": "reference", "metric": "it/s (UNet sampler steps/sec)", "value": v, "unit": "it/s", "n_gpus": args.gpus,
+        "steps": n, "warmup": done_w, "ms_per_step": 1000.0 * dt / n, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SD1.5 txt2img {args.size}x{args.size} dpmpp_2m_cfgpp bs=1 (CFG pair, UNet batch 2), "
+                               "multiscale off", "sampler": "dpmpp_2m_cfgpp", "scheduler": "karras", "cfg": 7.0},
+        "cpu_baseline": {"value": v, "unit": "it/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ldn", choices=["ldn", "reference"])
+    ap.add_argument("--size", type=int, default=1024, help="image size in pixels (config 2 = 1024)")
+    ap.add_argument("--bs", type=int, default=1, help="images per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from lightdiffusion_next_b200 import _lib as L
+    from lightdiffusion_next_b200.engine import Engine
+    from lightdiffusion_next_b200.sampling import SamplerLoop
+    from lightdiffusion_next_b200.schedule import calculate_sigmas
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = args.steps
+    bs = args.bs
+    lat = args.size // 8
+    peaks = load_peaks()
+
+    # ---- weights: rank 0 generates the seeded synthetic state dict, NCCL-broadcasts it (north_star: weights broadcast once)
+    from lightdiffusion_next_b200.synth import unet_shapes, synth_tensor
+    shapes = unet_shapes()
+    eng = Engine(max_rows=2 * bs, max_h=lat, max_w=lat, max_ctx_tokens=77, use_graph=not args.no_graph, device=dev)
+    names = sorted(shapes)
+    sd = {}
+    for nme in names:
+        if rank == 0:
+            t = synth_tensor(nme, shapes[nme]).to(dev)
+        else:
+            t = torch.empty(shapes[nme], dtype=torch.float16, device=dev)
+        if world > 1:
+            dist.broadcast(t, 0)
+        sd[nme] = t
+    eng.load_unet(sd)
+    del sd
+    torch.cuda.empty_cache()
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    ctx_rows = torch.cat([ctx[0:1].expand(bs, -1, -1), ctx[1:2].expand(bs, -1, -1)]).contiguous().to(dev)
+    eng.set_context(ctx_rows)
+    sig = calculate_sigmas(eng.schedule, "karras", 30)
+    t_ = -torch.log(sig)
+    ratios = (torch.exp(-t_)[1:] / torch.exp(-t_)[:-1])
+    hexp = torch.expm1(-(t_[1:] - t_[:-1]))
+    cfg = 7.0
+    loop = SamplerLoop(eng, bs, lat, lat)
+    x0 = (torch.randn(bs, 4, lat, lat, generator=g) * float(sig[0])).to(dev)
+    den = torch.empty_like(x0)
+    stream = torch.cuda.current_stream()
+
+    def one_step(i, x):
+        j = i % 29  # never the terminal sigma=0 step, so every step is the same work
+        du, dc = loop.denoise_pair(x, float(sig[j]))
+        eng.cfg_step(x, du, dc, cfg, 0, c0=float(ratios[j]), c1=float(hexp[j]), x_out=loop.x_next, denoised_out=den)
+        x, loop.x_next = loop.x_next, x
+        return x
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident timing (`value`)
+    x = x0.clone()
+    for i in range(W):
+        x = one_step(i, x)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        x = one_step(i, x)
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    finite = bool(torch.isfinite(x).all().item())
+
+    # ---------------------------------------------------------------- end-to-end through the host API (`e2e`)
+    # every step: pinned-host latent + sigma -> device, UNet CFG step, result latent -> pinned host, sync.
+    hx = torch.empty(bs, 4, lat, lat).pin_memory()
+    hx.copy_(x0.cpu())
+    hout = torch.empty_like(hx).pin_memory()
+    dx = torch.empty_like(x0)
+
+    def e2e_step(i):
+        dx.copy_(hx, non_blocking=True)
+        y = one_step(i, dx)
+        hout.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hx.copy_(hout)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tt[0]), float(tt[1])
+    else:
+        e2e_ms = e2e_s * 1000.0
+    its = world * bs * K / (ms / 1000.0)
+    e2e_its = world * bs * K / (e2e_ms / 1000.0)
+
+    if rank == 0:
+        # ------------------------------------------------------------ roofline of the dominant kernel
+        # L0 self-attention (attn_tc_kernel<48>: N=16384 tokens, 8 heads, d=40, UNet batch 2): 42 % of step FLOPs.
+        lib = eng.lib
+        B2, H, N, d, slot = 2 * bs, 8, lat * lat, 40, 64
+        Qb = torch.randn(B2 * N, 2 * H * slot, device=dev).bfloat16()
+        Qb.view(B2 * N, 2 * H, slot)[:, :, d:] = 0
+        Vt = torch.randn(H * d, B2 * N, device=dev).bfloat16()
+        Ob = torch.empty(B2 * N, H * d, device=dev, dtype=torch.bfloat16)
+
+        def attn():
+            L.check(lib.ldn_attention_bf16(Qb.data_ptr(), 2 * H * slot, Qb.data_ptr() + 2 * H * slot, 2 * H * slot,
+                                           Vt.data_ptr(), B2 * N, H * d, B2, H, N, N, N, d, slot, 0, d ** -0.5,
+                                           Ob.data_ptr(), H * d, L.cur_stream()))
+        for _ in range(3):
+            attn()
+        torch.cuda.synchronize()
+        a0 = torch.cuda.Event(enable_timing=True)
+        a1 = torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a0.record(stream)
+        for _ in range(reps):
+            attn()
+        a1.record(stream)
+        torch.cuda.synchronize()
+        attn_ms = a0.elapsed_time(a1) / reps
+        attn_flops = 4.0 * B2 * H * N * N * d
+        achieved = attn_flops / (attn_ms / 1000.0) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("attn_l0_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        step_tflop = (UNET_TFLOP_1024 if args.size == 1024 else UNET_TFLOP_512 if args.size == 512 else None)
+        line = {
+            "metric": "it/s (UNet sampler steps/sec)", "value": its, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"SD1.5 txt2img {args.size}x{args.size} dpmpp_2m_cfgpp bs={bs}/GPU (CFG pair, UNet batch {2*bs}), "
+                                   "multiscale off (every step full resolution)",
+                       "sampler": "dpmpp_2m_cfgpp", "scheduler": "karras", "cfg": cfg, "images_per_gpu": bs,
+                       "weights": "seeded synthetic SD1.5 UNet (859.5M params, bf16 in HBM)",
+                       "l2": "working set per step (1.72 GB weights + activations) exceeds the 126 MB L2; no flush needed",
+                       "cuda_graph": not args.no_graph, "finite": finite},
+            "clocks": clk,
+            "e2e": {"value": e2e_its, "unit": "it/s", "h2d_bytes_per_step": int(hx.numel() * 4),
+                    "d2h_bytes_per_step": int(hout.numel() * 4), "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(K * (eng_launches(eng) + 1)),
+            "roofline": {"bound": "tensor", "kernel": "attn_tc_kernel<48> (L0 self-attention, N=%d, d=40, B*H=%d)" % (N, B2 * H),
+                         "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
+                         "traffic": traffic, "peak_source": peaks["source"] + " (burst, kernel timed alone)",
+                         "ms_per_launch": attn_ms, "launches_per_step": 5},
+        }
+        if step_tflop is not None:
+            whole = its / world / bs * step_tflop
+            line["step_roofline"] = {"bound": "tensor", "achieved": whole, "peak": peaks["bf16_sus"], "unit": "TFLOP/s",
+                                     "frac": whole / peaks["bf16_sus"], "tflop_per_step": step_tflop,
+                                     "peak_source": peaks["source"] + " (sustained)"}
+        if world == 1 and not args.no_cpu_baseline:
+            n, dt, done_w, threads = cpu_oracle_step_time(lat, max_seconds=60.0, max_steps=1, warmup=0)
+            line["cpu_baseline"] = {"value": n / dt, "unit": "it/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n} full {args.size}x{args.size} CFG step(s) of the oracle port "
+                                              "(torch fp32 CPU, all host threads), no warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def eng_launches(eng) -> int:
+    """Kernels per UNet program run, counted by the engine when it built the program."""
+    return int(eng.lib.ldn_unet_last_launches(eng.h))
+
+
+if __name__ == "__main__":
+    main()

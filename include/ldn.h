@@ -61,10 +61,12 @@ int ldn_set_context(ldn_handle h, const float* ctx, int rows, int tokens, void* 
 /* x: [rows,4,h,w] fp32 NCHW; sigma: [rows] fp32; out: denoised = x - eps*sigma, [rows,4,h,w] fp32. */
 int ldn_unet_denoise(ldn_handle h, const float* x, const float* sigma, float* out, int rows, int lat_h, int lat_w,
                      void* stream);
+/* number of kernels the last ldn_unet_denoise program launches per call (as counted when it was built) */
+int ldn_unet_last_launches(ldn_handle h);
 /* Fused CFG combine + solver update, fp32 elementwise over n elements.
  *  denoised = uncond + (cond - uncond) * cfg
  *  mode 0 (dpmpp_2m_cfgpp as executed by the reference, first order): x' = c0*x - c1*denoised
- *  mode 1 (euler ancestral): x' = x + (x - denoised) * c0 + noise * c1
+ *  mode 1 (euler ancestral): x' = x + (x - denoised) / c2 * c0 + noise * c1   (c2 = sigma)
  *  mode 2: only write denoised */
 int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
                  float c1, float c2, const float* noise, float* x_out, float* denoised_out, int64_t n, void* stream);

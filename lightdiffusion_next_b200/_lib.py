@@ -44,6 +44,7 @@ SIGNATURES = {
     "ldn_set_sigmas": [_p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i],
     "ldn_set_context": [_p, _p, _i, _i, _p],
     "ldn_unet_denoise": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "ldn_unet_last_launches": [_p],
     "ldn_cfg_step": [_p, _p, _p, _f, _i, _f, _f, _f, _p, _p, _p, _l, _p],
     "ldn_vae_decode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_clip_encode": [_p, _p, _i, _p, _p, _p],

@@ -92,6 +92,7 @@ struct GemmArgs {
   long long ldr = 0;
   int head_dim = 0, head_slot = 0;
   int BN = 0;  // 0 = choose
+  int wt_rows = 0;  // valid rows of Wt if fewer than N (the rest are zero-filled by TMA)
 };
 
 GemmPlan make_gemm_plan(const GemmArgs& a);
@@ -139,7 +140,8 @@ void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)
 // GroupNorm over NHWC bf16 input that may be a virtual concat of two tensors along C.
-// stats: workspace of 2*B*groups floats (mean, rstd).
+// stats_ws: workspace of groupnorm_ws_bytes(B) bytes.
+inline size_t groupnorm_ws_bytes(int B) { return (size_t)B * 1024 * 32 * 16 + (size_t)B * 32 * 8 + 256; }
 void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
                       const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws,
                       cudaStream_t stream);

@@ -14,20 +14,45 @@ void* Arena::alloc(size_t bytes, bool zero) {
   LDN_CUDA(cudaMalloc(&p, bytes));
   if (zero) LDN_CUDA(cudaMemset(p, 0, bytes));
   blocks.push_back(p);
+  sizes.push_back(bytes);
   total += bytes;
   return p;
 }
 void Arena::release() {
   for (void* p : blocks) cudaFree(p);
   blocks.clear();
+  sizes.clear();
   total = 0;
+}
+
+__global__ void checksum_kernel(const uint32_t* __restrict__ p, size_t nwords, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x)
+    acc += (unsigned long long)p[i] * (unsigned long long)((i % 1000003) + 1);
+  atomicAdd(out, acc);
+}
+
+// Debug aid (LDN_DEBUG_HASH=1): order-independent checksum of every activation buffer after each step, so two runs
+// on identical inputs can be diffed to find the first non-deterministic step.
+static void debug_hash(Program& prog, size_t step, cudaStream_t stream) {
+  static unsigned long long* d = nullptr;
+  if (!d) cudaMalloc(&d, 8);
+  cudaMemsetAsync(d, 0, 8, stream);
+  for (size_t b = 0; b < prog.arena->blocks.size(); ++b)
+    checksum_kernel<<<256, 256, 0, stream>>>((const uint32_t*)prog.arena->blocks[b], prog.arena->sizes[b] / 4, d);
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, stream);
+  cudaStreamSynchronize(stream);
+  printf("LDNHASH %zu %s %016llx\n", step, prog.names[step].c_str(), h);
 }
 
 void run_program(Program& prog, bool use_graph, cudaStream_t stream) {
   if (!prog.warmed || !use_graph) {
     static const bool debug_sync = getenv("LDN_DEBUG_SYNC") != nullptr;
+    static const bool debug_hash_on = getenv("LDN_DEBUG_HASH") != nullptr;
     for (size_t i = 0; i < prog.steps.size(); ++i) {
       prog.steps[i](stream);
+      if (debug_hash_on && prog.arena) debug_hash(prog, i, stream);
       if (debug_sync) {
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess)
@@ -176,6 +201,8 @@ int ldn_unet_denoise(ldn_handle h, const float* x, const float* sigma, float* ou
   LDN_API_END
 }
 
+int ldn_unet_last_launches(ldn_handle h) { return h ? ldn::unet_last_launches(h) : 0; }
+
 int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
                  float c1, float c2, const float* noise, float* x_out, float* denoised_out, int64_t n, void* stream) {
   LDN_API_BEGIN
@@ -208,7 +235,7 @@ int ldn_groupnorm_bf16(const void* x0, int C0, const void* x1, int C1, int B, in
   static thread_local int ws_b = 0;
   if (ws_b < B) {
     if (ws) cudaFree(ws);
-    LDN_CUDA(cudaMalloc(&ws, sizeof(double) * 64 * B));
+    LDN_CUDA(cudaMalloc(&ws, groupnorm_ws_bytes(B)));
     ws_b = B;
   }
   launch_groupnorm((const bf16*)x0, C0, (const bf16*)x1, C1, B, HW, groups, eps, gamma, beta, silu != 0, (bf16*)out, ws,

@@ -29,6 +29,7 @@ struct DevTensor {
 typedef std::function<void(cudaStream_t)> Step;
 
 // A fixed launch sequence over fixed buffers for one problem shape; optionally frozen into a CUDA graph.
+struct Arena;
 struct Program {
   std::vector<Step> steps;
   std::vector<std::string> names;  // one label per step (profiling / debugging)
@@ -40,10 +41,12 @@ struct Program {
   float* out = nullptr;
   size_t io_elems = 0;
   int launches = 0;  // kernels launched per run (reported as gpu_launches by bench.py)
+  struct Arena* arena = nullptr;  // activation arena (debug checksums)
 };
 
 struct Arena {
   std::vector<void*> blocks;
+  std::vector<size_t> sizes;
   size_t total = 0;
   void* alloc(size_t bytes, bool zero = false);
   template <typename T>

@@ -281,7 +281,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   GemmParams& p = plan.p;
   memset(&p, 0, sizeof(p));
   LDN_CHECK(a.Wt && a.A0 && (a.out || a.out_f32), "gemm: null operand");
-  LDN_CHECK(a.N % 16 == 0 || a.N % 8 == 0, "gemm: N must be a multiple of 8");
+  LDN_CHECK(a.N % 16 == 0, "gemm: N must be a multiple of 16");
   int BN = a.BN ? a.BN : pick_bn(a.N, a.epi == 1);
   if (a.epi == 1) LDN_CHECK(a.N % BN == 0 && BN % 32 == 0, "geglu: N must be a multiple of BN, BN of 32");
   LDN_CHECK(BN % 16 == 0 && BN >= 16 && BN <= 256, "gemm: bad BN");
@@ -326,7 +326,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
     p.tmA1 = a.A1 ? make_tmap_2d(a.A1, a.M, a.K1, a.lda1, kBM) : p.tmA0;
     plan.grid = dim3((a.N + BN - 1) / BN, (a.M + kBM - 1) / kBM, 1);
   }
-  p.tmB = make_tmap_2d(a.Wt, a.N, K, K, BN);
+  p.tmB = make_tmap_2d(a.Wt, a.wt_rows > 0 ? a.wt_rows : a.N, K, K, BN);  // rows past wt_rows read as zero
   p.epi = a.epi;
   p.out = a.out;
   p.ldo = a.ldo;

@@ -12,24 +12,24 @@
 
 namespace ldn {
 
-// ------------------------------------------------------------------ GroupNorm statistics
-// grid: (splits, B); block: (C/8) * R threads. stats[b][g] = {sum, sumsq} in double (pre-zeroed).
+// ------------------------------------------------------------------ GroupNorm statistics (deterministic: no atomics)
+// Kernel 1, grid (splits, B), block (C/8)*R threads: every thread owns 8 consecutive channels for a strided set of
+// pixels, folds them into at most two (group, sum, sumsq) partials in shared memory, then warp g reduces the partials of
+// group g in a fixed order and writes one double2 per (batch, split, group).
+// Kernel 2, grid B, 1024 threads: warp g sums the split partials in a fixed order -> (mean, rstd).
+#define LDN_GN_MAX_SPLITS 1024
+
 __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
-                                int cpg, int rows_per_block, double* __restrict__ stats) {
+                                int cpg, int rows_per_block, double2* __restrict__ partial) {
   const int C = C0 + C1;
   const int nvec = C >> 3;
   const int R = blockDim.x / nvec;
   const int cv = threadIdx.x % nvec;
   const int prow = threadIdx.x / nvec;
   const int b = blockIdx.y;
-  __shared__ float s_sum[32], s_sq[32];
-  if (threadIdx.x < 32) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
-  if (prow < R) {
-    const int c = cv * 8;
+  __shared__ float s_part[1024][4];  // per thread: {sum_lo, sq_lo, sum_hi, sq_hi} for groups g_lo = c/cpg and g_lo+1
+  const int c = cv * 8;
+  {
     const bf16* src;
     int ld;
     if (c < C0) {
@@ -56,28 +56,72 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16*
         q[2 * i + 1] += bb * bb;
       }
     }
-    // fold the 8 channels into their groups (a vector may straddle two groups)
-    int g_prev = c / cpg;
-    float as = 0.f, aq = 0.f;
+    const int g_lo = c / cpg;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int g = (c + i) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&s_sum[g_prev], as);
-        atomicAdd(&s_sq[g_prev], aq);
-        as = aq = 0.f;
-        g_prev = g;
+      if ((c + i) / cpg == g_lo) {
+        a0 += s[i];
+        a1 += q[i];
+      } else {
+        a2 += s[i];
+        a3 += q[i];
       }
-      as += s[i];
-      aq += q[i];
     }
-    atomicAdd(&s_sum[g_prev], as);
-    atomicAdd(&s_sq[g_prev], aq);
+    s_part[threadIdx.x][0] = a0;
+    s_part[threadIdx.x][1] = a1;
+    s_part[threadIdx.x][2] = a2;
+    s_part[threadIdx.x][3] = a3;
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    atomicAdd(&stats[((size_t)b * 32 + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
-    atomicAdd(&stats[((size_t)b * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < 32; g += nwarps) {
+    // channel vectors that touch group g: cv in [first, last]
+    const int first = (g * cpg) >> 3;
+    const int last = ((g + 1) * cpg - 1) >> 3;
+    const int ncv = last - first + 1;
+    double sum = 0.0, sq = 0.0;
+    for (int idx = lane; idx < ncv * R; idx += 32) {
+      const int v = first + idx % ncv;
+      const int pr = idx / ncv;
+      const int t = pr * nvec + v;
+      const int g_lo = (v * 8) / cpg;
+      if (g_lo == g) {
+        sum += (double)s_part[t][0];
+        sq += (double)s_part[t][1];
+      } else if (g_lo + 1 == g) {
+        sum += (double)s_part[t][2];
+        sq += (double)s_part[t][3];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) partial[((size_t)b * gridDim.x + blockIdx.x) * 32 + g] = make_double2(sum, sq);
+  }
+}
+
+__global__ void gn_finalize_kernel(const double2* __restrict__ partial, int splits, double n, float eps,
+                                   float2* __restrict__ mean_rstd) {
+  const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double sum = 0.0, sq = 0.0;
+  for (int s = lane; s < splits; s += 32) {
+    const double2 v = partial[((size_t)b * splits + s) * 32 + g];
+    sum += v.x;
+    sq += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) {
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0) var = 0;
+    mean_rstd[b * 32 + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
   }
 }
 
@@ -87,25 +131,18 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 // grid: (pixel chunks, B); dynamic smem: 2*C floats (per-channel scale / shift)
 __global__ void gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
                                 int cpg, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                int silu, const double* __restrict__ stats, bf16* __restrict__ out,
+                                int silu, const float2* __restrict__ mean_rstd, bf16* __restrict__ out,
                                 int rows_per_block) {
   extern __shared__ float s_ab[];
   const int C = C0 + C1;
   float* s_a = s_ab;
   float* s_b = s_ab + C;
   const int b = blockIdx.y;
-  const double n = (double)HW * cpg;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double sum = stats[((size_t)b * 32 + g) * 2 + 0];
-    const double sq = stats[((size_t)b * 32 + g) * 2 + 1];
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float a = rstd * gamma[c];
+    const float2 mr = mean_rstd[b * 32 + c / cpg];
+    const float a = mr.y * gamma[c];
     s_a[c] = a;
-    s_b[c] = beta[c] - (float)mean * a;
+    s_b[c] = beta[c] - mr.x * a;
   }
   __syncthreads();
   const int nvec = C >> 3;
@@ -141,8 +178,9 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   LDN_CHECK(C % 32 == 0 && C % 8 == 0 && C0 % 8 == 0, "groupnorm: channel counts must be multiples of 8/32");
   LDN_CHECK(C / 8 <= 1024, "groupnorm: too many channels");
   const int cpg = C / groups;
-  double* stats = reinterpret_cast<double*>(stats_ws);
-  LDN_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * 32 * B, stream));
+  // workspace: [B][splits][32] double2 partials, then [B][32] float2 (mean, rstd)
+  double2* partial = reinterpret_cast<double2*>(stats_ws);
+  float2* mean_rstd = reinterpret_cast<float2*>(partial + (size_t)B * LDN_GN_MAX_SPLITS * 32);
   const int nvec = C / 8;
   int R = 1024 / nvec;
   if (R > 16) R = 16;
@@ -152,12 +190,15 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   int rows_per_block = (HW + splits - 1) / splits;
   if (rows_per_block < R) rows_per_block = R;
   splits = (HW + rows_per_block - 1) / rows_per_block;
-  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, stats);
+  LDN_CHECK(splits <= LDN_GN_MAX_SPLITS, "groupnorm: too many splits");
+  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, partial);
+  LDN_CUDA(cudaGetLastError());
+  gn_finalize_kernel<<<B, 1024, 0, stream>>>(partial, splits, (double)HW * cpg, eps, mean_rstd);
   LDN_CUDA(cudaGetLastError());
   int rpb2 = (HW + splits - 1) / splits;
   const size_t smem = sizeof(float) * 2 * C;
   gn_apply_kernel<<<dim3((HW + rpb2 - 1) / rpb2, B), 512, smem, stream>>>(x0, C0, x1, C1, HW, cpg, eps, gamma, beta,
-                                                                          silu ? 1 : 0, stats, out, rpb2);
+                                                                          silu ? 1 : 0, mean_rstd, out, rpb2);
   LDN_CUDA(cudaGetLastError());
 }
 

@@ -392,8 +392,8 @@ void launch_repack_conv_weight(const void* src, int src_dtype, int O, int I, int
 // denoised = uncond + (cond - uncond) * cfg                     (torch.lerp, src/sample/CFG.py:55-60)
 // mode 0: x' = c0 * x - c1 * denoised                           (dpmpp_2m_cfgpp as executed: samplers.py:952-953,
 //                                                                 c0 = sigma_next/sigma, c1 = expm1(-h))
-// mode 1: d = (x - denoised) * c2 ; x' = x + d * c0 + noise*c1  (euler ancestral: samplers.py:728-732,
-//                                                                 c2 = 1/sigma, c0 = sigma_down - sigma, c1 = sigma_up)
+// mode 1: d = (x - denoised) / c2 ; x' = x + d * c0 + noise*c1  (euler ancestral: samplers.py:728-732,
+//                                                                 c2 = sigma, c0 = sigma_down - sigma, c1 = sigma_up)
 // mode 2: denoised only
 __global__ void cfg_step_kernel(const float* __restrict__ x, const float* __restrict__ du, const float* __restrict__ dc,
                                 float cfg, int mode, float c0, float c1, float c2, const float* __restrict__ noise,
@@ -408,7 +408,7 @@ __global__ void cfg_step_kernel(const float* __restrict__ x, const float* __rest
       x_out[i] = c0 * x[i] - c1 * den;
     } else if (mode == 1) {
       const float xv = x[i];
-      const float d = (xv - den) * c2;
+      const float d = (xv - den) / c2;
       float r = xv + d * c0;
       if (noise) r += noise[i] * c1;
       x_out[i] = r;

@@ -15,6 +15,7 @@
 // forward is a CUDA graph.
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 #include "engine.h"
 
@@ -46,7 +47,7 @@ __global__ void pad_context_kernel(const float* __restrict__ ctx, int rows, int 
 }
 
 // dst[c, b*nk_pad + k] = src[c, b*N + k]  (only used when N % 8 != 0: TMA box starts must be 16-byte aligned)
-__global__ void pad_vt_cols_kernel(const bf16* __restrict__ src, int C, int Bn, int N, int nk_pad,
+__global__ void pad_vt_cols_kernel(const bf16* __restrict__ src, int ld_src, int C, int Bn, int N, int nk_pad,
                                    bf16* __restrict__ dst) {
   const size_t total = (size_t)C * Bn * N;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -54,7 +55,7 @@ __global__ void pad_vt_cols_kernel(const bf16* __restrict__ src, int C, int Bn, 
     const size_t cb = i / N;
     const int b = (int)(cb % Bn);
     const size_t c = cb / Bn;
-    dst[(c * Bn + b) * nk_pad + k] = src[i];
+    dst[(c * Bn + b) * nk_pad + k] = src[c * ld_src + (size_t)b * N + k];
   }
 }
 
@@ -403,6 +404,7 @@ struct Builder {
   // SpatialTransformer (depth 1): x [B,H,W,C] -> new buffer
   bf16* transformer(const STW& s, const bf16* x, int H, int W, int level) {
     const int N = H * W, T = B * N, C = s.C;
+    const int Tld = (T + 15) / 16 * 16;  // leading dimension of V^T (16-byte rows, whole 16-column GEMM chunks)
     const std::string tb = s.prefix + ".transformer_blocks.0";
     bf16* out = A.get<bf16>((size_t)T * C);
     bf16* X = sB;  // token stream
@@ -424,12 +426,12 @@ struct Builder {
       a.out = QK; a.ldo = ldqk; a.head_dim = s.d; a.head_slot = s.slot;
       gemm(tb + ".attn1.qk", a);
       GemmArgs v;
-      v.A0 = e->W(0, tb + ".attn1.to_v.weight").b(); v.lda0 = C; v.K0 = C; v.Wt = sA; v.M = C; v.N = T;
-      v.out = sVt; v.ldo = T;
+      v.A0 = e->W(0, tb + ".attn1.to_v.weight").b(); v.lda0 = C; v.K0 = C; v.Wt = sA; v.M = C; v.N = Tld; v.wt_rows = T;
+      v.out = sVt; v.ldo = Tld;
       gemm(tb + ".attn1.vt", v);
       AttnArgs at;
       at.Q = QK; at.ldq = ldqk; at.K = QK + (size_t)U.heads * s.slot; at.ldk = ldqk;
-      at.Vt = sVt; at.ldvt = T; at.vt_rows = C;
+      at.Vt = sVt; at.ldvt = Tld; at.vt_rows = C;
       at.B = B; at.heads = U.heads; at.Nq = N; at.Nk = N; at.nk_pad = N; at.d = s.d; at.slot = s.slot;
       if (N % 8 != 0) {
         // per-batch key offsets b*N would start TMA boxes at non-16B-aligned addresses: re-lay V^T with padded batches
@@ -439,7 +441,7 @@ struct Builder {
         bf16* dst = sVtPad;
         const int Bn = B;
         add(tb + ".attn1.vt_pad", [=](cudaStream_t st) {
-          pad_vt_cols_kernel<<<64, 256, 0, st>>>(src, C, Bn, N, npad, dst);
+          pad_vt_cols_kernel<<<64, 256, 0, st>>>(src, Tld, C, Bn, N, npad, dst);
           LDN_CUDA(cudaGetLastError());
         });
         at.Vt = sVtPad; at.ldvt = (long long)B * npad;
@@ -503,6 +505,7 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
   std::unique_ptr<Program> prog(new Program());
   U.program_arenas.emplace_back(new Arena());
   Arena& A = *U.program_arenas.back();
+  prog->arena = &A;
   Builder bd{e, U, *prog, A, B, H, W};
   const int nlev = (int)U.channel_mult.size();
   // ---- scratch sizing
@@ -525,6 +528,7 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
   }
   // upsampled tensors: (2h x 2w) x C of the coarser level
   max_act = std::max(max_act, (size_t)B * H * W * (size_t)(U.model_ch * U.channel_mult[std::min(1, nlev - 1)]));
+  max_act += (size_t)16 * 2560;  // slack: V^T rows are padded to 16-column multiples
   bd.sA = A.get<bf16>(max_act);
   bd.sB = A.get<bf16>(max_act);
   bd.sC = A.get<bf16>(max_act);
@@ -551,7 +555,7 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
       bd.sQK[nlev - 1] = A.get<bf16>((size_t)B * h * w * 2 * U.heads * slot_of(c / U.heads), true);
     }
   }
-  bd.gn_ws = reinterpret_cast<float*>(A.get<double>((size_t)64 * B));
+  bd.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B)));
   bd.temb = A.get<float>((size_t)B * U.model_ch);
   bd.emb1 = A.get<float>((size_t)B * U.temb_dim);
   bd.emb = A.get<float>((size_t)B * U.temb_dim);
@@ -693,6 +697,8 @@ void unet_denoise(ldn_engine* e, const float* x, const float* sigma, float* out,
     it = U.programs.emplace(key, std::unique_ptr<Program>(build_unet_program(e, rows, h, w))).first;
   }
   Program& P = *it->second;
+  if (getenv("LDN_DEBUG_HASH") && P.arena)  // identical start state for every run so per-step checksums are comparable
+    for (size_t b = 0; b < P.arena->blocks.size(); ++b) cudaMemsetAsync(P.arena->blocks[b], 0, P.arena->sizes[b], stream);
   LDN_CUDA(cudaMemcpyAsync(P.in_x, x, P.io_elems * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   LDN_CUDA(cudaMemcpyAsync(P.in_sigma, sigma, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   run_program(P, e->cfg.use_graph != 0, stream);

@@ -1,0 +1,151 @@
+"""Sampler loop of the engine — the host-side mirror of the reference's sampling driver for the path that
+BASELINE.json measures.
+
+Public surface mirrors `sampling.KSampler().sample(model, seed, steps, cfg, sampler_name, scheduler, positive,
+negative, latent_image, denoise)` (src/sample/sampling.py:773-887) and the sampler functions
+`sample_dpmpp_2m_cfgpp` / `sample_euler_ancestral_dy_cfg_pp` (src/sample/samplers.py:755-962, 612-740) *as they
+execute* (the CFG++ branches are never taken; fact 9: multiscale is on by default for dpmpp_2m).
+
+Per step the host issues exactly two engine calls — `ldn_unet_denoise` (one CUDA graph: the 2B-row UNet forward with
+EPS scaling) and `ldn_cfg_step` (CFG lerp + solver update) — and never synchronises: solver coefficients are computed
+up front on the CPU in fp32 with the reference's op order.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .engine import Engine
+from .schedule import calculate_sigmas, get_ancestral_step, max_denoise
+
+LATENT_SCALE = 0.18215  # src/Utilities/Latent.py:41-62
+SAMPLERS = ("dpmpp_2m_cfgpp", "euler_ancestral_cfgpp")
+
+
+def prepare_noise(latent: torch.Tensor, seed: int) -> torch.Tensor:
+    """ksampler_util.py:274-295: global CPU generator, one draw for the whole batch (so seeds reproduce)."""
+    g = torch.manual_seed(seed)
+    return torch.randn(latent.size(), dtype=latent.dtype, layout=latent.layout, generator=g, device="cpu")
+
+
+def _multiscale_fullres(step: int, n_steps: int, start: int = 5, end: int = 8, intermittent: bool = True) -> bool:
+    if step < start or step >= n_steps - end:
+        return True
+    if intermittent:
+        return (step - start) % 2 == 0
+    return False
+
+
+class SamplerLoop:
+    """Reusable loop state for one (batch, resolution): device buffers are allocated once."""
+
+    def __init__(self, engine: Engine, batch: int, lat_h: int, lat_w: int):
+        self.e = engine
+        dev = engine.device
+        self.B = batch
+        self.x2 = torch.empty(2 * batch, 4, lat_h, lat_w, device=dev)  # [uncond rows | cond rows] input
+        self.sig2 = torch.empty(2 * batch, device=dev)
+        self.den2 = torch.empty_like(self.x2)
+        self.x_next = torch.empty(batch, 4, lat_h, lat_w, device=dev)
+
+    def denoise_pair(self, x: torch.Tensor, sigma: float) -> Tuple[torch.Tensor, torch.Tensor]:
+        """calc_cond_batch (src/cond/cond.py:150-288): one batched call, rows [uncond.., cond..]."""
+        B = self.B
+        self.x2[:B].copy_(x)
+        self.x2[B:].copy_(x)
+        self.sig2.fill_(sigma)
+        self.e.denoise(self.x2, self.sig2, out=self.den2)
+        return self.den2[:B], self.den2[B:]
+
+
+def sample_dpmpp_2m_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
+                          enable_multiscale: bool = True, multiscale_factor: float = 0.5,
+                          callback: Optional[Callable] = None) -> torch.Tensor:
+    """x <- (sigma_{i+1}/sigma_i) x - expm1(-h_i) * lerp(uncond, cond, cfg)  (first order, as the reference executes)."""
+    B, _, oh, ow = x.shape
+    sh = int(max(8, ((oh * multiscale_factor) // 8) * 8)) if enable_multiscale else oh
+    sw = int(max(8, ((ow * multiscale_factor) // 8) * 8)) if enable_multiscale else ow
+    active = enable_multiscale and (sh != oh or sw != ow)
+    sig = sigmas.float().cpu()
+    t = -torch.log(sig)
+    sigma_steps = torch.exp(-t)
+    ratios = sigma_steps[1:] / sigma_steps[:-1]
+    h = t[1:] - t[:-1]
+    hexp = torch.expm1(-h)
+    n = len(sig) - 1
+    full = SamplerLoop(engine, B, oh, ow)
+    low = SamplerLoop(engine, B, sh, sw) if active else None
+    den = torch.empty_like(x)
+    for i in range(n):
+        if (not active) or _multiscale_fullres(i, n):
+            du, dc = full.denoise_pair(x, float(sig[i]))
+            engine.cfg_step(x, du, dc, cfg, 0, c0=float(ratios[i]), c1=float(hexp[i]), x_out=full.x_next,
+                            denoised_out=den)
+            x, full.x_next = full.x_next, x
+        else:
+            xp = F.interpolate(x, size=(sh, sw), mode="bilinear", align_corners=False)
+            du, dc = low.denoise_pair(xp, float(sig[i]))
+            d_low = torch.empty_like(xp)
+            engine.cfg_step(None, du, dc, cfg, 2, denoised_out=d_low)
+            den = F.interpolate(d_low, size=(oh, ow), mode="bilinear", align_corners=False)
+            x = float(ratios[i]) * x - float(hexp[i]) * den
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sig[i], "denoised": den})
+    return x
+
+
+def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
+                                 noise_sampler: Optional[Callable] = None,
+                                 callback: Optional[Callable] = None) -> torch.Tensor:
+    """d = (x - D)/sigma; x += d (sigma_down - sigma); x += randn_like(x) sigma_up   (eta = 1, s_noise = 1)."""
+    B = x.shape[0]
+    sig = sigmas.float().cpu()
+    n = len(sig) - 1
+    loop = SamplerLoop(engine, B, x.shape[2], x.shape[3])
+    den = torch.empty_like(x)
+    for i in range(n):
+        du, dc = loop.denoise_pair(x, float(sig[i]))
+        sd, su = get_ancestral_step(sig[i], sig[i + 1])
+        noise = None
+        if sig[i + 1] > 0:
+            noise = noise_sampler(x) if noise_sampler is not None else torch.randn_like(x)
+        engine.cfg_step(x, du, dc, cfg, 1, c0=float(sd - sig[i]), c1=float(su), c2=float(sig[i]), noise=noise,
+                        x_out=loop.x_next, denoised_out=den)
+        x, loop.x_next = loop.x_next, x
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sig[i], "denoised": den})
+    return x
+
+
+def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str, scheduler: str,
+           positive: torch.Tensor, negative: torch.Tensor, latent_image: Dict[str, torch.Tensor],
+           denoise: float = 1.0, enable_multiscale: bool = True, noise: Optional[torch.Tensor] = None,
+           callback: Optional[Callable] = None) -> Tuple[Dict[str, torch.Tensor]]:
+    """Drop-in for KSampler.sample on the measured path. positive / negative: [1 or B, 77k, 768] conditioning tensors.
+    Returns ({"samples": latents / 0.18215 on the CPU},) like the reference node."""
+    if sampler_name not in SAMPLERS:
+        raise ValueError(f"sampler {sampler_name!r} is not built (have {SAMPLERS})")
+    if denoise != 1.0:
+        raise NotImplementedError("denoise < 1 (img2img / HiresFix second pass) is not built yet")
+    latent = latent_image["samples"]
+    B = latent.shape[0]
+    dev = engine.device
+    sigmas = calculate_sigmas(engine.schedule, scheduler, steps)
+    if noise is None:
+        noise = prepare_noise(latent, seed)
+    lat = latent * LATENT_SCALE if torch.count_nonzero(latent) > 0 else latent  # CFG.py:266-269
+    if max_denoise(engine.schedule, sigmas):
+        x = noise * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+    else:
+        x = noise * sigmas[0]
+    x = (x + lat).to(dev, torch.float32).contiguous()
+    ctx = torch.cat([negative.expand(B, -1, -1), positive.expand(B, -1, -1)]).to(dev)  # rows: uncond first
+    engine.set_context(ctx)
+    if sampler_name == "dpmpp_2m_cfgpp":
+        x = sample_dpmpp_2m_cfgpp(engine, x, sigmas, cfg, enable_multiscale=enable_multiscale, callback=callback)
+    else:
+        x = sample_euler_ancestral_cfgpp(engine, x, sigmas, cfg, callback=callback)
+    out = (x / LATENT_SCALE).to(torch.float32).cpu()
+    return ({"samples": out},)

@@ -252,6 +252,10 @@ def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, mask: Optional[Tensor
     b, n, c = q.shape
     d = c // heads
     q, k, v = (t.view(b, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    if mask is None and n * k.shape[2] > (1 << 24):
+        # same maths without materialising the N x N matrix (what the reference calls: F.scaled_dot_product_attention,
+        # AttentionMethods.py:130) — only used at benchmark sizes where the explicit form would need > 10 GB
+        return F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
     s = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
     if mask is not None:
         s = s + mask

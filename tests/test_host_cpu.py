@@ -1,0 +1,144 @@
+"""CPU: the C-ABI library loads and exports what include/ldn.h declares; host-side logic (schedules, synthetic weights,
+sampler loop, batch sharding over 2 gloo ranks) matches the oracle / reference goldens.  No GPU compute here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def test_library_exports_every_declared_symbol():
+    from lightdiffusion_next_b200 import _lib
+    lib = _lib.load()
+    assert _lib.MISSING == []
+    header = open(os.path.join(ROOT, "include", "ldn.h")).read()
+    declared = set(re.findall(r"\b(ldn_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ldn.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
+    assert lib.ldn_version() >= 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check of the no-fallback rule")
+def test_create_fails_loudly_without_gpu():
+    from lightdiffusion_next_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.ldn_config(2, 32, 32, 77, 1)
+    h = ctypes.c_void_p()
+    rc = lib.ldn_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc != 0 and lib.ldn_last_error()
+    from lightdiffusion_next_b200.engine import Engine
+    with pytest.raises(_lib.LdnError):
+        Engine()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "lightdiffusion_next_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), fn
+
+
+def test_schedule_matches_reference_tables(golden_unet):
+    from lightdiffusion_next_b200.schedule import DiscreteSchedule, calculate_sigmas
+    ms = DiscreteSchedule()
+    assert torch.equal(ms.sigmas, golden_unet["sigmas"]) and torch.equal(ms.log_sigmas, golden_unet["log_sigmas"])
+    for name, steps in (("karras", 20), ("karras", 30), ("normal", 10), ("normal", 22)):
+        assert torch.equal(calculate_sigmas(ms, name, steps), golden_unet[f"sched_{name}_{steps}"])
+    for hw in (16, 32):
+        assert torch.equal(ms.timestep(golden_unet[f"apply_sigma_{hw}"]).float(), golden_unet[f"apply_t_{hw}"])
+
+
+def test_synth_weights_match_oracle_generator():
+    from lightdiffusion_next_b200 import synth
+    from oracle import sd15_oracle as O
+    a, b = synth.unet_shapes(), O.unet_param_shapes()
+    assert a == b and len(a) == 686
+    assert sum(int(torch.tensor(s).prod()) for s in a.values()) == 859_520_964
+    for k in ("time_embed.0.weight", "out.0.bias", "middle_block.1.transformer_blocks.0.ff.net.2.weight"):
+        assert torch.equal(synth.synth_tensor(k, a[k]), O.synth_state_dict({k: b[k]})[k])
+
+
+@pytest.mark.parametrize("name,sampler,sched,steps", [("euler_a", "euler_ancestral_cfgpp", "karras", 4),
+                                                      ("dpmpp_2m", "dpmpp_2m_cfgpp", "karras", 6),
+                                                      ("dpmpp_2m_ms", "dpmpp_2m_cfgpp", "karras", 15)])
+def test_sampler_loop_host_logic(golden_sample, unet_sd, name, sampler, sched, steps):
+    """The engine's sampler loop (coefficients, CFG row order, noise, multiscale schedule) driven by a CPU fake engine
+    reproduces the reference's final latents."""
+    from lightdiffusion_next_b200 import sampling as S
+    from fake_engine import FakeEngine
+    g = golden_sample
+    eng = FakeEngine(unet_sd)
+    out = S.sample(eng, 42, steps, 7.0, sampler, sched, g["ctx_pos"], g["ctx_neg"], {"samples": torch.zeros(1, 4, 16, 16)})
+    assert rel(out[0]["samples"], g[f"{name}_final"]) < 1e-4
+    assert eng.denoise_calls == steps
+
+
+def test_shard_range_ragged():
+    from lightdiffusion_next_b200.distributed import shard_range
+    for batch in (0, 1, 3, 8, 32, 33):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(batch, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from lightdiffusion_next_b200 import distributed as D, sampling as S
+from lightdiffusion_next_b200.synth import unet_shapes, synth_tensor
+from fake_engine import FakeEngine
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.set_num_threads(4)
+shapes = {{k: v for k, v in unet_shapes().items()}}
+sd = D.broadcast_state_dict(shapes, synth_tensor, "cpu")
+# rank 1 received exactly what rank 0 generated
+chk = synth_tensor("out.2.weight", shapes["out.2.weight"])
+assert torch.equal(sd["out.2.weight"], chk)
+eng = FakeEngine(sd)
+g = torch.Generator().manual_seed(1234)
+pos = torch.randn(1, 77, 768, generator=g); neg = torch.randn(1, 77, 768, generator=g)
+B = 3  # ragged over 2 ranks
+res = D.sample_sharded(eng, 42, 2, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, {{"samples": torch.zeros(B, 4, 16, 16)}})
+if rank == 0:
+    torch.save(res[0]["samples"], {out!r})
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharded_sampling_equals_single_process(tmp_path, unet_sd):
+    """world_size=2 over gloo on CPU: weights broadcast, noise scattered, latents gathered; the sharded batch equals
+    the single-process batch bit-for-bit in structure (same noise rows) and numerically in value."""
+    from lightdiffusion_next_b200 import sampling as S
+    from fake_engine import FakeEngine
+    out = str(tmp_path / "sharded.pt")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, out=out))
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    sharded = torch.load(out)
+    g = torch.Generator().manual_seed(1234)
+    pos = torch.randn(1, 77, 768, generator=g)
+    neg = torch.randn(1, 77, 768, generator=g)
+    single = S.sample(FakeEngine(unet_sd), 42, 2, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg,
+                      {"samples": torch.zeros(3, 4, 16, 16)})[0]["samples"]
+    assert sharded.shape == single.shape
+    assert rel(sharded, single) < 1e-5
