@@ -18,6 +18,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace ldn {
 
 static constexpr int kAttnThreads = 192;
@@ -306,6 +308,13 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   p.kv_stages = stages;
   plan.smem_bytes = fixed + stages * stage_bytes;
   plan.grid = dim3((a.Nq + kTileQ - 1) / kTileQ, a.heads, a.B);
+  p.variant = 1;
+  static const bool force_v1 = getenv("LDN_ATTN_V1") != nullptr;
+  static const int poly_mod = getenv("LDN_ATTN_POLY") ? atoi(getenv("LDN_ATTN_POLY")) : 0;
+  if (dp <= 64 && !force_v1) {
+    p.poly_mod = poly_mod;
+    finish_attn2_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+  }
   return plan;
 }
 
@@ -321,6 +330,7 @@ static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 }
 
 void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
+  if (plan.p.variant == 2) return launch_attn2(plan, stream);
   switch (plan.p.dv) {
     case 48: launch_attn_t<48>(plan, stream); break;
     case 64: launch_attn_t<64>(plan, stream); break;

@@ -112,6 +112,8 @@ struct AttnParams {
   int causal;
   int kv_stages;
   float scale_log2;  // softmax scale * log2(e)
+  int variant;       // 1: attention.cu (one query tile per CTA), 2: attention2.cu (two query tiles, d <= 64)
+  int poly_mod;      // variant 2: every poly_mod-th group of 8 exponentials runs on the FMA pipes (0 = all MUFU)
   bf16* out;         // [B*Nq, heads*d]
   long long ldo;
 };
@@ -136,6 +138,8 @@ struct AttnArgs {
   long long ldo;
 };
 AttnPlan make_attn_plan(const AttnArgs& a);
+void finish_attn2_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
+void launch_attn2(const AttnPlan& plan, cudaStream_t stream);
 void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)
