@@ -24,6 +24,13 @@ void set_last_error(const std::string& s) { g_last_error = s; }
 
 using namespace ldn;
 
+static const size_t kOpWsBytes = (size_t)64 << 20;
+static float* op_splitk_ws() {  // workspace for op-level calls (the engine has its own per program)
+  static float* ws = nullptr;
+  if (!ws) LDN_CUDA(cudaMalloc(&ws, kOpWsBytes));
+  return ws;
+}
+
 extern "C" {
 
 const char* ldn_last_error(void) { return g_last_error.c_str(); }
@@ -42,6 +49,7 @@ int ldn_gemm_bf16(const void* A0, int64_t lda0, int K0, const void* A1, int64_t 
   a.residual = (const bf16*)residual; a.ldr = ldr;
   a.out = (bf16*)out; a.ldo = ldo; a.out_f32 = out_f32;
   a.epi = epi; a.head_dim = head_dim; a.head_slot = head_slot; a.BN = BN;
+  a.splitk_ws = op_splitk_ws(); a.splitk_ws_bytes = kOpWsBytes;
   GemmPlan plan = make_gemm_plan(a);
   launch_gemm(plan, (cudaStream_t)stream);
   LDN_API_END
@@ -57,6 +65,7 @@ int ldn_conv3x3_bf16(const void* x, const void* Wt, int B, int H, int W, int Cin
   a.bias = bias; a.rowbias = rowbias; a.ld_rowbias = ld_rowbias;
   a.residual = (const bf16*)residual; a.ldr = Cout;
   a.out = (bf16*)out; a.ldo = Cout;
+  a.splitk_ws = op_splitk_ws(); a.splitk_ws_bytes = kOpWsBytes;
   GemmPlan plan = make_gemm_plan(a);
   launch_gemm(plan, (cudaStream_t)stream);
   LDN_API_END

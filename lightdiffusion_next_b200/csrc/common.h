@@ -58,6 +58,11 @@ struct GemmParams {
   const bf16* residual;
   long long ldr;
   int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
+  // split-K (small-M problems): grid.z splits, each writes an fp32 partial tile; splitk_reduce_kernel finishes
+  int splits, chunks_per_split;
+  float* ws;
+  long long ws_split_stride;  // elements between consecutive splits (= rows * N)
+  int total_rows;
 };
 
 struct GemmPlan {
@@ -93,6 +98,8 @@ struct GemmArgs {
   int head_dim = 0, head_slot = 0;
   int BN = 0;  // 0 = choose
   int wt_rows = 0;  // valid rows of Wt if fewer than N (the rest are zero-filled by TMA)
+  float* splitk_ws = nullptr;  // optional fp32 workspace enabling split-K for problems with too few tiles
+  size_t splitk_ws_bytes = 0;
 };
 
 GemmPlan make_gemm_plan(const GemmArgs& a);

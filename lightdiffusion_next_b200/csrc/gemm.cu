@@ -83,14 +83,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int nk = p.num_k_chunks;
+  const int kc_begin = blockIdx.z * p.chunks_per_split;
+  const int kc_end = min(p.num_k_chunks, kc_begin + p.chunks_per_split);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % stages;
-        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        const int it = kc - kc_begin;
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
         uint8_t* b_dst = a_dst + a_bytes;
@@ -113,9 +115,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kBM, (uint32_t)BN);
-      for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % stages;
-        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        const int it = kc - kc_begin;
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
         for (int k = 0; k < kBK / 16; ++k) {
           // advance 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
           tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (kc > 0 || k > 0) ? 1u : 0u);
+                      (it > 0 || k > 0) ? 1u : 0u);
         }
         tc_commit(&empty_bar[s]);
       }
@@ -156,7 +159,24 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     }
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
 
-    if (p.epi == 0) {
+    if (p.splits > 1) {
+      // split-K: raw fp32 partial tile; bias / residual are applied by splitk_reduce_kernel
+      float* wbase = p.ws + (long long)blockIdx.z * p.ws_split_stride;
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (out_row >= 0 && n < p.N) {
+          float4* op = reinterpret_cast<float4*>(wbase + out_row * p.N + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            op[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                __uint_as_float(v[4 * i + 3]));
+        }
+        __syncwarp();
+      }
+    } else if (p.epi == 0) {
       for (int c = 0; c < BN; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_lane + (uint32_t)c, v);
@@ -259,6 +279,53 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   }
 }
 
+// out[row, n] = sum_z ws[z][row][n] (fixed order => deterministic) + bias + rowbias + residual, 8 columns per thread
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, int rows, int N,
+                                     const float* __restrict__ bias, const float* __restrict__ rowbias, int ld_rowbias,
+                                     int rows_per_batch, const bf16* __restrict__ residual, long long ldr,
+                                     bf16* __restrict__ out, long long ldo) {
+  const int nv = N >> 3;
+  const long long total = (long long)rows * nv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % nv) * 8;
+    const long long row = idx / nv;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+    for (int z = 0; z < splits; ++z) {
+      const float4* src = reinterpret_cast<const float4*>(ws + z * split_stride + row * N + n);
+      const float4 a = src[0], b = src[1];
+      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+      f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    if (bias) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += bias[n + i];
+    }
+    if (rowbias) {
+      const float* rb = rowbias + (row / rows_per_batch) * ld_rowbias + n;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += rb[i];
+    }
+    if (residual) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(residual + row * ldr + n);
+      const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[2 * i] += bf16_lo(w[i]);
+        f[2 * i + 1] += bf16_hi(w[i]);
+      }
+    }
+    uint4 ov;
+    ov.x = pack_bf16x2(f[0], f[1]);
+    ov.y = pack_bf16x2(f[2], f[3]);
+    ov.z = pack_bf16x2(f[4], f[5]);
+    ov.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + row * ldo + n) = ov;
+  }
+}
+
 // ----------------------------------------------------------------------------------- host side
 
 static int pick_bn(int N, bool geglu) {
@@ -351,6 +418,27 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
   if (stages > p.num_k_chunks) stages = p.num_k_chunks < 1 ? 1 : p.num_k_chunks;
+  // split-K when the tile grid cannot fill the machine and K is long (L2 / L3 / middle-block convs: M = 512..2048)
+  p.splits = 1;
+  p.chunks_per_split = p.num_k_chunks;
+  p.total_rows = p.M;
+  const int tiles = plan.grid.x * plan.grid.y;
+  if (a.splitk_ws && a.epi == 0 && a.head_dim == 0 && !a.out_f32 && tiles < 148 && p.num_k_chunks >= 40) {
+    int splits = (2 * 148 + tiles - 1) / tiles;
+    if (splits > p.num_k_chunks / 8) splits = p.num_k_chunks / 8;
+    if (splits > 16) splits = 16;
+    while (splits > 1 && (size_t)splits * p.M * a.N * sizeof(float) > a.splitk_ws_bytes) --splits;
+    if (splits > 1) {
+      p.chunks_per_split = (p.num_k_chunks + splits - 1) / splits;
+      splits = (p.num_k_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+      p.splits = splits;
+      p.ws = a.splitk_ws;
+      p.ws_split_stride = (long long)p.M * a.N;
+      plan.grid.z = splits;
+      if (p.conv) p.rows_per_batch = a.H * a.W;
+    }
+  }
+  if (stages > p.chunks_per_split) stages = p.chunks_per_split;
   p.stages = stages;
   plan.smem_bytes = stages * stage_bytes + 1024 + 256;
   return plan;
@@ -364,6 +452,16 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   }
   gemm_tc_kernel<<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
   LDN_CUDA(cudaGetLastError());
+  if (plan.p.splits > 1) {
+    const GemmParams& p = plan.p;
+    const long long total = (long long)p.total_rows * (p.N / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, p.ws_split_stride, p.splits, p.total_rows, p.N, p.bias,
+                                                    p.rowbias, p.ld_rowbias, p.rows_per_batch > 0 ? p.rows_per_batch : 1,
+                                                    p.residual, p.ldr, p.out, p.ldo);
+    LDN_CUDA(cudaGetLastError());
+  }
 }
 
 }  // namespace ldn

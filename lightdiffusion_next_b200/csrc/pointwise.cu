@@ -126,9 +126,12 @@ void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const flo
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                const bf16* __restrict__ Wt, const float* __restrict__ bias, int B, int H, int W, int Cin,
                                int Cout, bf16* __restrict__ out) {
-  extern __shared__ float s_w[];  // [Cout][9*Cin]
+  extern __shared__ float s_w[];  // transposed: [9*Cin][Cout] so the 8 output channels of a thread are contiguous
   const int K = 9 * Cin;
-  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) s_w[i] = __bfloat162float(Wt[i]);
+  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) {
+    const int o = i / K, k = i - o * K;
+    s_w[k * Cout + o] = __bfloat162float(Wt[i]);
+  }
   __syncthreads();
   const int groups = Cout / 8;
   const size_t total = (size_t)B * H * W * groups;
@@ -151,9 +154,12 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
         if (xx < 0 || xx >= W) continue;
         for (int c = 0; c < Cin; ++c) {
           const float v = x[(((size_t)b * Cin + c) * H + yy) * W + xx] * scale;
-          const int k = (ky * 3 + kx) * Cin + c;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, s_w[(g * 8 + i) * K + k], acc[i]);
+          const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * Cin + c) * Cout + g * 8);
+          const float4 w0 = wr[0], w1 = wr[1];
+          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
         }
       }
     }

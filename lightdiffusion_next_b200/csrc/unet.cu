@@ -333,6 +333,8 @@ struct Builder {
   bf16* sVtPad = nullptr;  // zero-initialised, only used for levels whose token count is not a multiple of 8
   std::vector<bf16*> sQK;  // per level
   size_t vt_pad_elems = 0;
+  float* splitk_ws = nullptr;
+  size_t splitk_ws_bytes = 0;
   float* gn_ws = nullptr;
   float *temb = nullptr, *emb1 = nullptr, *emb = nullptr, *emb_all = nullptr;
 
@@ -341,7 +343,10 @@ struct Builder {
     P.names.push_back(name);
     P.launches += launches;
   }
-  void gemm(const std::string& name, const GemmArgs& a) {
+  void gemm(const std::string& name, const GemmArgs& a0) {
+    GemmArgs a = a0;
+    a.splitk_ws = splitk_ws;
+    a.splitk_ws_bytes = splitk_ws_bytes;
     GemmPlan plan = make_gemm_plan(a);
     add(name, [plan](cudaStream_t st) { launch_gemm(plan, st); });
   }
@@ -534,6 +539,8 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
   bd.sC = A.get<bf16>(max_act);
   bd.sO = A.get<bf16>(max_act);
   bd.sVt = A.get<bf16>(max_act);
+  bd.splitk_ws_bytes = (size_t)64 << 20;
+  bd.splitk_ws = reinterpret_cast<float*>(A.alloc(bd.splitk_ws_bytes));
   bd.vt_pad_elems = (size_t)1280 * B * 8 * 8;  // only tiny token counts (< 64) can be non-multiples of 8
   bd.sVtPad = A.get<bf16>(bd.vt_pad_elems, true);
   bd.sG = A.get<bf16>(std::max<size_t>(max_geglu, 16));
