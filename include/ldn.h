@@ -89,10 +89,12 @@ int ldn_gemm_bf16(const void* A0, int64_t lda0, int K0, const void* A1, int64_t 
 /* x: NHWC bf16 [B,H,W,Cin]; Wt: [Cout, 3,3, Cin] bf16; out NHWC bf16 [B,H,W,Cout]; stride 1, pad 1. */
 int ldn_conv3x3_bf16(const void* x, const void* Wt, int B, int H, int W, int Cin, int Cout, const float* bias,
                      const float* rowbias, int ld_rowbias, const void* residual, void* out, void* stream);
-/* Q: [B*Nq, heads*slot], K: [B*nk_pad, heads*slot], Vt: [vt_rows, B*nk_pad] (all bf16); out: [B*Nq, heads*d]. */
+/* Q: [B*Nq, heads*slot], K: [B*nk_pad, heads*slot], Vt: [vt_rows, B*nk_pad] (all bf16); out: [B*Nq, heads*d].
+ * vt_head_stride: rows per head in Vt; 0 or d = plain V^T. For d = 40, 48 selects the fastest kernel and requires
+ * row 40 of every head to be all ones (rows 41..47 zero): the softmax row sum is then computed by the tensor core. */
 int ldn_attention_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* Vt, int64_t ldvt,
-                       int64_t vt_rows, int B, int heads, int Nq, int Nk, int nk_pad, int d, int slot, int causal,
-                       float scale, void* out, int64_t ldo, void* stream);
+                       int64_t vt_rows, int vt_head_stride, int B, int heads, int Nq, int Nk, int nk_pad, int d,
+                       int slot, int causal, float scale, void* out, int64_t ldo, void* stream);
 /* GroupNorm (+SiLU) over NHWC bf16, input may be a channel concat of x0 (C0) and x1 (C1, may be NULL/0). */
 int ldn_groupnorm_bf16(const void* x0, int C0, const void* x1, int C1, int B, int HW, int groups, float eps,
                        const float* gamma, const float* beta, int silu, void* out, void* stream);

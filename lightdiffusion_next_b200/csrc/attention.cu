@@ -309,11 +309,15 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   plan.smem_bytes = fixed + stages * stage_bytes;
   plan.grid = dim3((a.Nq + kTileQ - 1) / kTileQ, a.heads, a.B);
   p.variant = 1;
+  p.vt_head_stride = a.vt_head_stride > 0 ? a.vt_head_stride : a.d;
   static const bool force_v1 = getenv("LDN_ATTN_V1") != nullptr;
   static const int poly_mod = getenv("LDN_ATTN_POLY") ? atoi(getenv("LDN_ATTN_POLY")) : 0;
-  if (dp <= 64 && !force_v1) {
-    p.poly_mod = poly_mod;
-    finish_attn2_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+  p.poly_mod = poly_mod;
+  if (a.d == 40 && p.vt_head_stride == 48) {
+    finish_attn3_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // the caller laid V^T out with a ones row: version 3
+  } else {
+    LDN_CHECK(p.vt_head_stride == a.d, "attention: vt_head_stride is only supported as 48 for d = 40");
+    if (dp <= 64 && !force_v1) finish_attn2_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   }
   return plan;
 }
@@ -330,6 +334,7 @@ static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 }
 
 void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
+  if (plan.p.variant == 3) return launch_attn3(plan, stream);
   if (plan.p.variant == 2) return launch_attn2(plan, stream);
   switch (plan.p.dv) {
     case 48: launch_attn_t<48>(plan, stream); break;

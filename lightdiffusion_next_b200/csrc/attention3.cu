@@ -1,0 +1,384 @@
+// Attention kernel, third generation, for head dim 40 (SD1.5 level 0: N = 16384 tokens at 1024^2, 42 % of the step's
+// FLOPs). Same Q / K layout as attention.cu; V^T carries, per head, 48 rows: 40 value rows, one row of ONES and 7 zero rows.
+//
+// What the ncu captures of the first two generations showed (profiles/r1_attention_ncu_full.md): at d = 40 the kernel is
+// bound by the softmax instruction stream, not by the MMAs (384 tensor-clk per 128x128 tile vs 1024 MUFU-clk and about
+// as many FMA/ALU-pipe clk). This version strips the per-element FMA/ALU work to the minimum:
+//   * the softmax ROW SUM is computed by the tensor core: because row 40 of V^T is all ones, column 40 of P*V is
+//     sum_k P[q,k] (of the same bf16-rounded P the numerator uses) -> no FADD per element;
+//   * O (and the row sum) stay RESIDENT in TMEM across key tiles (tcgen05.mma accumulates), so there is no per-tile
+//     TMEM->register read-modify-write of O; the running max is applied lazily: P uses a stale max and O is rescaled
+//     in TMEM (tcgen05.ld / tcgen05.st) only when the true max has grown by more than 2^8 (rare after the first tiles);
+//   * per element what remains is 1 FFMA (scale, subtract max) + 1 ex2 + half a pack; a compile-time subset of the ex2
+//     can run as a polynomial on the FMA pipes to balance MUFU against FMA;
+//   * schedule as in generation 2: two 128-row query tiles per CTA sharing each K / V^T tile, one softmax warpgroup per
+//     tile (one thread per row, S row read from TMEM once into registers), S of the next key tile issued as soon as the
+//     current one is in registers, P double-buffered in shared memory, setmaxnreg 56 / 224.
+#include "common.h"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace ldn {
+
+static constexpr int kA3Threads = 384;
+static constexpr int kQ3 = 128;
+static constexpr int kK3 = 128;
+static constexpr int kDV3 = 48;
+static constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+__device__ __forceinline__ float ex2m(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2p(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float n = t - 12582912.0f;
+  const float f = x - n;
+  float p = fmaf(f, 0.0555041086f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ uint32_t pin3(uint32_t v) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <uint32_t kPolyMask>
+__global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (2 * kQ3);
+  const int stages = p.kv_stages;
+  constexpr uint32_t atom_bytes = 128 * 128;
+  constexpr uint32_t vt_atom_bytes = kDV3 * 128;
+  constexpr uint32_t stage_bytes = atom_bytes + 2 * vt_atom_bytes;
+
+  uint8_t* q_smem = smem;                       // 2 query tiles
+  uint8_t* p_smem = smem + 2 * atom_bytes;      // [tile][parity][2 atoms]
+  const int pb = p.p_bufs;                      // 1: single P buffer per tile (more K/V stages), 2: double buffered
+  uint8_t* kv_smem = p_smem + (size_t)(4 * pb) * atom_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + (size_t)stages * stage_bytes);
+  uint64_t* q_full = bars;         // 1
+  uint64_t* s_full = bars + 1;     // [2]
+  uint64_t* s_free = bars + 3;     // [2] 128 arrivals
+  uint64_t* p_full = bars + 5;     // [2] 128 arrivals
+  uint64_t* pv_done = bars + 7;    // [2] one completion per key tile
+  uint64_t* p_free = bars + 9;     // [2 tiles][2 parities] one completion per use of the P buffer
+  uint64_t* kv_full = bars + 13;
+  uint64_t* kv_empty = kv_full + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + stages);
+  constexpr uint32_t kTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,304) O1 [320,368)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmVt);
+    mbar_init(q_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 128);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_done[t], 1);
+      mbar_init(&p_free[2 * t], 1);
+      mbar_init(&p_free[2 * t + 1], 1);
+    }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = (p.Nk + kK3 - 1) / kK3;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * atom_bytes);
+        tma_load_2d(q_smem, &p.tmQ, q_full, h * p.slot, b * p.Nq + q0);
+        tma_load_2d(q_smem + atom_bytes, &p.tmQ, q_full, h * p.slot, b * p.Nq + q0 + kQ3);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = j % stages;
+          const uint32_t ph = (uint32_t)(j / stages) & 1u;
+          mbar_wait(&kv_empty[s], ph ^ 1u);
+          uint8_t* k_dst = kv_smem + (size_t)s * stage_bytes;
+          uint8_t* v_dst = k_dst + atom_bytes;
+          mbar_arrive_expect_tx(&kv_full[s], stage_bytes);
+          const int key0 = b * p.nk_pad + j * kK3;
+          const int krow0 = b * p.k_batch_stride + j * kK3;
+          tma_load_2d(k_dst, &p.tmK, &kv_full[s], h * p.slot, krow0);
+          tma_load_2d(v_dst, &p.tmVt, &kv_full[s], key0, h * kDV3);
+          tma_load_2d(v_dst + vt_atom_bytes, &p.tmVt, &kv_full[s], key0 + 64, h * kDV3);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc_s = make_idesc_bf16(128, 128);
+        const uint32_t idesc_pv = make_idesc_bf16(128, kDV3);
+        const uint32_t q_addr = smem_u32(q_smem);
+        const uint32_t p_addr = smem_u32(p_smem);
+        const uint32_t kv_addr = smem_u32(kv_smem);
+        auto issue_s = [&](int t, uint32_t k_addr) {
+          const uint64_t a0 = make_smem_desc_sw128(q_addr + (uint32_t)t * atom_bytes);
+          const uint64_t b0 = make_smem_desc_sw128(k_addr);
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks)  // dqk = 48
+            tc_mma_bf16(tmem_base + (uint32_t)t * 128, a0 + (uint64_t)(2 * ks), b0 + (uint64_t)(2 * ks), idesc_s,
+                        ks > 0 ? 1u : 0u);
+          tc_commit(&s_full[t]);
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_s(0, kv_addr);
+        issue_s(1, kv_addr);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = j % stages;
+          const uint32_t v_addr = kv_addr + (uint32_t)s * stage_bytes + atom_bytes;
+          if (j + 1 < n_tiles) {
+            const int s1 = (j + 1) % stages;
+            mbar_wait(&kv_full[s1], (uint32_t)((j + 1) / stages) & 1u);
+            const uint32_t k_next = kv_addr + (uint32_t)s1 * stage_bytes;
+            for (int t = 0; t < 2; ++t) {
+              mbar_wait(&s_free[t], (uint32_t)j & 1u);
+              tc_fence_after();
+              issue_s(t, k_next);
+            }
+          }
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&p_full[t], (uint32_t)j & 1u);
+            tc_fence_after();
+            const uint32_t pa = p_addr + (uint32_t)(t * pb + (pb == 2 ? (j & 1) : 0)) * 2 * atom_bytes;
+#pragma unroll
+            for (int ks = 0; ks < kK3 / 16; ++ks) {
+              const uint64_t adesc =
+                  make_smem_desc_sw128(pa + (uint32_t)(ks >> 2) * atom_bytes) + (uint64_t)(2 * (ks & 3));
+              const uint64_t bdesc =
+                  make_smem_desc_sw128(v_addr + (uint32_t)(ks >> 2) * vt_atom_bytes) + (uint64_t)(2 * (ks & 3));
+              // O (and the row sum in column 40) accumulate across key tiles
+              tc_mma_bf16(tmem_base + 256 + (uint32_t)t * 64, adesc, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+            }
+            tc_commit(&pv_done[t]);
+            tc_commit(&p_free[2 * t + (j & 1)]);
+          }
+          tc_commit(&kv_empty[s]);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = (warp - 4) >> 2;
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const uint32_t tmem_s = tmem_base + (uint32_t)t * 128 + lane_off;
+    const uint32_t tmem_o = tmem_base + 256 + (uint32_t)t * 64 + lane_off;
+    const int q_idx = q0 + t * kQ3 + r;
+    const float sc = p.scale_log2;
+    const uint32_t p_row0 = pin3(smem_u32(p_smem) + (uint32_t)(t * pb) * 2 * atom_bytes + (uint32_t)r * 128);
+    const uint32_t sw16 = (uint32_t)(r & 7) << 4;
+    uint64_t* const my_s_full = &s_full[t];
+    uint64_t* const my_s_free = &s_free[t];
+    uint64_t* const my_p_full = &p_full[t];
+    uint64_t* const my_pv_done = &pv_done[t];
+    float m_used = 0.f;  // exponent offset currently baked into O (scaled log2 units)
+    if (p.pingpong && t == 1 && n_tiles > 0) asm volatile("bar.arrive 1, 256;" ::: "memory");  // tile 0 goes first
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(my_s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t sv[128];
+      tmem_ld32(tmem_s + 0, sv + 0);
+      tmem_ld32(tmem_s + 32, sv + 32);
+      tmem_ld32(tmem_s + 64, sv + 64);
+      tmem_ld32(tmem_s + 96, sv + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(my_s_free);
+
+      const int limit = p.Nk - j * kK3;
+      if (limit < kK3) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= limit) sv[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 8) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        // lazy rescale: only when this row's max outgrew the offset baked into O by more than 2^8
+        const bool need = mx > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(my_pv_done, (uint32_t)(j - 1) & 1u);  // every earlier P*V has landed in O
+          tc_fence_after();
+          const float m_new = need ? mx : m_used;
+          const float f = ex2m(m_used - m_new);  // 1 for rows that do not need it
+          m_used = m_new;
+#pragma unroll
+          for (int c = 0; c < kDV3; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_o + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st16(tmem_o + (uint32_t)c, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // the P buffer of this parity was last read by P*V of key tile j-2
+      uint32_t p_row = p_row0;
+      if (pb == 2) {
+        if (j >= 2) mbar_wait(&p_free[2 * t + (j & 1)], (uint32_t)(((j >> 1) + 1) & 1));
+        p_row += (uint32_t)(j & 1) * 2 * atom_bytes;
+      } else if (j >= 1) {
+        mbar_wait(my_pv_done, (uint32_t)(j - 1) & 1u);  // P*V of the previous key tile has finished reading the buffer
+      }
+      const float m_off = m_used;
+      // MUFU ping-pong: the two softmax warpgroups take turns in the exp phase (named barriers 1 / 2)
+      if (p.pingpong) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      // software-pipelined: the MUFU works on chunk c while the FMA pipe prepares chunk c+1 and the ALU / LSU pack and
+      // store chunk c-1, so no instruction waits on the ~20-clk MUFU latency in program order
+      float x[8], e[8], d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sv[i]), sc, -m_off);
+#pragma unroll
+      for (int c = 0; c <= 16; ++c) {
+        if (c < 16) {
+          if ((kPolyMask >> c) & 1u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = ex2p(x[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = ex2m(x[i]);
+          }
+        }
+        if (c + 1 < 16) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sv[(c + 1) * 8 + i]), sc, -m_off);
+        }
+        if (c > 0) {
+          const int cc = (c - 1) * 8;
+          const uint32_t addr = p_row + (uint32_t)(cc >> 6) * atom_bytes + ((((uint32_t)(cc & 63) >> 3) << 4) ^ sw16);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack_bf16x2(d[0], d[1])),
+                       "r"(pack_bf16x2(d[2], d[3])), "r"(pack_bf16x2(d[4], d[5])), "r"(pack_bf16x2(d[6], d[7]))
+                       : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = e[i];
+      }
+      if (p.pingpong && !(t == 1 && j == n_tiles - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(1 + (t ^ 1)) : "memory");
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(my_p_full);
+    }
+    // epilogue: O[:, 0:40] / O[:, 40]
+    if (n_tiles > 0) {
+      mbar_wait(my_pv_done, (uint32_t)(n_tiles - 1) & 1u);
+      tc_fence_after();
+      uint32_t v[48];
+      tmem_ld16(tmem_o + 0, v + 0);
+      tmem_ld16(tmem_o + 16, v + 16);
+      tmem_ld16(tmem_o + 32, v + 32);
+      tmem_ld_wait();
+      if (q_idx < p.Nq) {
+        const float l = __uint_as_float(v[40]);
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        bf16* orow = p.out + ((long long)b * p.Nq + q_idx) * p.ldo + (long long)h * 40;
+#pragma unroll
+        for (int c = 0; c < 40; c += 8) {
+          uint4 ov;
+          ov.x = pack_bf16x2(__uint_as_float(v[c + 0]) * inv, __uint_as_float(v[c + 1]) * inv);
+          ov.y = pack_bf16x2(__uint_as_float(v[c + 2]) * inv, __uint_as_float(v[c + 3]) * inv);
+          ov.z = pack_bf16x2(__uint_as_float(v[c + 4]) * inv, __uint_as_float(v[c + 5]) * inv);
+          ov.w = pack_bf16x2(__uint_as_float(v[c + 6]) * inv, __uint_as_float(v[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c) = ov;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <uint32_t kPolyMask>
+static void launch_attn3_t(const AttnPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDN_CUDA(cudaFuncSetAttribute(attn3_tc_kernel<kPolyMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  attn3_tc_kernel<kPolyMask><<<plan.grid, kA3Threads, plan.smem_bytes, stream>>>(plan.p);
+  LDN_CUDA(cudaGetLastError());
+}
+
+void launch_attn3(const AttnPlan& plan, cudaStream_t stream) {
+  switch (plan.p.poly_mod) {
+    case 2: return launch_attn3_t<0xAAAAu>(plan, stream);  // 50 % polynomial
+    case 3: return launch_attn3_t<0x9249u>(plan, stream);  // 37.5 %
+    case 4: return launch_attn3_t<0x8888u>(plan, stream);  // 25 %
+    case 8: return launch_attn3_t<0x8080u>(plan, stream);  // 12.5 %
+    default: return launch_attn3_t<0u>(plan, stream);
+  }
+}
+
+void finish_attn3_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B) {
+  AttnParams& p = plan.p;
+  LDN_CHECK(p.d == 40 && p.dv == 48 && p.dqk == 48 && !p.causal, "attention3: d = 40, non-causal only");
+  const int stage_bytes = 16384 + 2 * kDV3 * 128;
+  static const int pbufs = getenv("LDN_ATTN_PBUF") ? atoi(getenv("LDN_ATTN_PBUF")) : 1;
+  p.p_bufs = pbufs == 2 ? 2 : 1;
+  static const int pingpong = getenv("LDN_ATTN_PINGPONG") ? atoi(getenv("LDN_ATTN_PINGPONG")) : 0;
+  p.pingpong = pingpong;
+  const int fixed = 2 * 16384 + 4 * p.p_bufs * 16384 + 1024 + 256;
+  const int n_tiles = (Nk + kK3 - 1) / kK3;
+  int stages = (226 * 1024 - fixed) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages > n_tiles) stages = n_tiles;
+  if (getenv("LDN_ATTN_STAGES")) stages = std::min(stages, atoi(getenv("LDN_ATTN_STAGES")));
+  if (stages < 1) stages = 1;
+  p.kv_stages = stages;
+  p.variant = 3;
+  plan.smem_bytes = fixed + stages * stage_bytes;
+  plan.grid = dim3((Nq + 2 * kQ3 - 1) / (2 * kQ3), heads, B);
+}
+
+}  // namespace ldn

@@ -74,12 +74,12 @@ int ldn_conv3x3_bf16(const void* x, const void* Wt, int B, int H, int W, int Cin
 }  // extern "C"
 
 extern "C" int ldn_attention_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* Vt, int64_t ldvt,
-                                  int64_t vt_rows, int B, int heads, int Nq, int Nk, int nk_pad, int d, int slot,
-                                  int causal, float scale, void* out, int64_t ldo, void* stream) {
+                                  int64_t vt_rows, int vt_head_stride, int B, int heads, int Nq, int Nk, int nk_pad,
+                                  int d, int slot, int causal, float scale, void* out, int64_t ldo, void* stream) {
   LDN_API_BEGIN
   AttnArgs a;
   a.Q = (const bf16*)Q; a.ldq = ldq; a.K = (const bf16*)K; a.ldk = ldk; a.Vt = (const bf16*)Vt; a.ldvt = ldvt;
-  a.vt_rows = vt_rows; a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.nk_pad = nk_pad; a.d = d; a.slot = slot;
+  a.vt_rows = vt_rows; a.vt_head_stride = vt_head_stride; a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.nk_pad = nk_pad; a.d = d; a.slot = slot;
   a.causal = causal; a.scale = scale; a.out = (bf16*)out; a.ldo = ldo;
   AttnPlan plan = make_attn_plan(a);
   launch_attn(plan, (cudaStream_t)stream);

@@ -58,6 +58,7 @@ struct GemmParams {
   const bf16* residual;
   long long ldr;
   int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
+  int row_head_dim, row_head_slot;  // GEMM mode, row_head_dim > 0: output row m -> (m / dim) * slot + m % dim
   // split-K (small-M problems): grid.z splits, each writes an fp32 partial tile; splitk_reduce_kernel finishes
   int splits, chunks_per_split;
   float* ws;
@@ -96,6 +97,7 @@ struct GemmArgs {
   const bf16* residual = nullptr;
   long long ldr = 0;
   int head_dim = 0, head_slot = 0;
+  int row_head_dim = 0, row_head_slot = 0;
   int BN = 0;  // 0 = choose
   int wt_rows = 0;  // valid rows of Wt if fewer than N (the rest are zero-filled by TMA)
   float* splitk_ws = nullptr;  // optional fp32 workspace enabling split-K for problems with too few tiles
@@ -119,7 +121,10 @@ struct AttnParams {
   int causal;
   int kv_stages;
   float scale_log2;  // softmax scale * log2(e)
-  int variant;       // 1: attention.cu (one query tile per CTA), 2: attention2.cu (two query tiles, d <= 64)
+  int vt_head_stride; // rows per head in Vt (d, or 48 when a ones row at index d supplies the softmax row sum)
+  int variant;       // 3: attention3.cu (d = 40, row sums on the tensor core, O resident in TMEM); 1: attention.cu (one query tile per CTA), 2: attention2.cu (two query tiles, d <= 64)
+  int pingpong;      // variant 3: softmax warpgroups alternate on the MUFU
+  int p_bufs;        // variant 3: P buffers per query tile in shared memory (1 or 2)
   int poly_mod;      // variant 2: every poly_mod-th group of 8 exponentials runs on the FMA pipes (0 = all MUFU)
   bf16* out;         // [B*Nq, heads*d]
   long long ldo;
@@ -139,6 +144,7 @@ struct AttnArgs {
   long long vt_rows;
   int B, heads, Nq, Nk, nk_pad, d, slot;
   int kv_batch_stride = 0;  // K rows per batch (0 = nk_pad)
+  int vt_head_stride = 0;   // rows per head in Vt (0 = d). d = 40 with stride 48: row 40 of every head must be all ones
   int causal = 0;
   float scale;
   bf16* out;
@@ -147,6 +153,8 @@ struct AttnArgs {
 AttnPlan make_attn_plan(const AttnArgs& a);
 void finish_attn2_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn2(const AttnPlan& plan, cudaStream_t stream);
+void finish_attn3_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
+void launch_attn3(const AttnPlan& plan, cudaStream_t stream);
 void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     } else {
       const int m = m0 + r;
       out_row = (m < p.M) ? m : -1;
+      if (p.row_head_dim > 0 && out_row >= 0) out_row = (m / p.row_head_dim) * p.row_head_slot + (m % p.row_head_dim);
       batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
     }
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -406,6 +407,8 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.ldr = a.ldr;
   p.head_dim = a.head_dim;
   p.head_slot = a.head_slot;
+  p.row_head_dim = a.row_head_dim;
+  p.row_head_slot = a.row_head_slot;
   if (a.head_dim > 0) LDN_CHECK(a.head_dim % 8 == 0, "gemm: head_dim must be a multiple of 8");
 
   int cols = 32;
@@ -423,7 +426,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.chunks_per_split = p.num_k_chunks;
   p.total_rows = p.M;
   const int tiles = plan.grid.x * plan.grid.y;
-  if (a.splitk_ws && a.epi == 0 && a.head_dim == 0 && !a.out_f32 && tiles < 148 && p.num_k_chunks >= 40) {
+  if (a.splitk_ws && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && !a.out_f32 && tiles < 148 && p.num_k_chunks >= 40) {
     int splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > p.num_k_chunks / 8) splits = p.num_k_chunks / 8;
     if (splits > 16) splits = 16;

@@ -59,6 +59,16 @@ __global__ void pad_vt_cols_kernel(const bf16* __restrict__ src, int ld_src, int
   }
 }
 
+// V^T buffers of head-dim-40 layers carry 48 rows per head; row 40 of every head is all ones (softmax row sums on the
+// tensor core, attention3.cu), rows 41..47 stay zero.
+__global__ void fill_ones_rows_kernel(bf16* __restrict__ vt, int heads, long long ld, int head_stride, int row) {
+  const long long total = (long long)heads * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(i / ld);
+    vt[((long long)h * head_stride + row) * ld + (i % ld)] = __float2bfloat16(1.0f);
+  }
+}
+
 }  // namespace ldn
 
 using namespace ldn;
@@ -273,7 +283,7 @@ void unet_finalize(ldn_engine* e, cudaStream_t stream) {
   U.ctx_pad = U.arena.get<bf16>((size_t)cap_rows * U.ctx_cap_pad * U.ctx_dim);
   for (auto& s : U.sts) {
     U.kctx.push_back(U.arena.get<bf16>((size_t)cap_rows * U.ctx_cap_pad * U.heads * s.slot, true));
-    U.vtctx.push_back(U.arena.get<bf16>((size_t)s.C * cap_rows * U.ctx_cap_pad, true));
+    U.vtctx.push_back(U.arena.get<bf16>((size_t)(s.d == 40 ? U.heads * 48 : s.C) * cap_rows * U.ctx_cap_pad, true));
   }
   LDN_CUDA(cudaStreamSynchronize(stream));
   e->finalized[0] = true;
@@ -288,6 +298,12 @@ void unet_set_context(ldn_engine* e, const float* ctx, int rows, int tokens, cud
     // layout (leading dimensions) changes: zero K buffers so slot padding columns / padded keys are 0
     for (size_t i = 0; i < U.sts.size(); ++i) {
       LDN_CUDA(cudaMemsetAsync(U.kctx[i], 0, (size_t)rows * nk_pad * U.heads * U.sts[i].slot * sizeof(bf16), stream));
+      if (U.sts[i].d == 40) {
+        const long long ld = (long long)rows * nk_pad;
+        LDN_CUDA(cudaMemsetAsync(U.vtctx[i], 0, (size_t)U.heads * 48 * ld * sizeof(bf16), stream));
+        fill_ones_rows_kernel<<<32, 256, 0, stream>>>(U.vtctx[i], U.heads, ld, 48, 40);
+        LDN_CUDA(cudaGetLastError());
+      }
     }
   }
   U.ctx_rows = rows;
@@ -316,6 +332,7 @@ void unet_set_context(ldn_engine* e, const float* ctx, int rows, int tokens, cud
     v.Wt = U.ctx_pad;
     v.M = s.C; v.N = M;
     v.out = U.vtctx[i]; v.ldo = M;
+    if (s.d == 40) { v.row_head_dim = 40; v.row_head_slot = 48; }
     launch_gemm(make_gemm_plan(v), stream);
   }
 }
@@ -332,6 +349,7 @@ struct Builder {
   bf16 *sA = nullptr, *sB = nullptr, *sC = nullptr, *sO = nullptr, *sG = nullptr, *sVt = nullptr, *sCol = nullptr;
   bf16* sVtPad = nullptr;  // zero-initialised, only used for levels whose token count is not a multiple of 8
   std::vector<bf16*> sQK;  // per level
+  std::vector<bf16*> sVt40;  // per level: [heads*48, Tld] V^T with a ones row per head (head dim 40 only)
   size_t vt_pad_elems = 0;
   float* splitk_ws = nullptr;
   size_t splitk_ws_bytes = 0;
@@ -430,15 +448,20 @@ struct Builder {
       a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = s.Wqk; a.M = T; a.N = 2 * C;
       a.out = QK; a.ldo = ldqk; a.head_dim = s.d; a.head_slot = s.slot;
       gemm(tb + ".attn1.qk", a);
+      const bool ones = (s.d == 40);  // attention3: 48 rows per head, row 40 = ones
+      bf16* Vt = ones ? sVt40[level] : sVt;
       GemmArgs v;
       v.A0 = e->W(0, tb + ".attn1.to_v.weight").b(); v.lda0 = C; v.K0 = C; v.Wt = sA; v.M = C; v.N = Tld; v.wt_rows = T;
-      v.out = sVt; v.ldo = Tld;
+      v.out = Vt; v.ldo = Tld;
+      if (ones) { v.row_head_dim = 40; v.row_head_slot = 48; }
       gemm(tb + ".attn1.vt", v);
       AttnArgs at;
       at.Q = QK; at.ldq = ldqk; at.K = QK + (size_t)U.heads * s.slot; at.ldk = ldqk;
-      at.Vt = sVt; at.ldvt = Tld; at.vt_rows = C;
+      at.Vt = Vt; at.ldvt = Tld; at.vt_rows = ones ? U.heads * 48 : C;
+      at.vt_head_stride = ones ? 48 : 0;
       at.B = B; at.heads = U.heads; at.Nq = N; at.Nk = N; at.nk_pad = N; at.d = s.d; at.slot = s.slot;
       if (N % 8 != 0) {
+        LDN_CHECK(!ones, "head-dim-40 level with a token count that is not a multiple of 8");
         // per-batch key offsets b*N would start TMA boxes at non-16B-aligned addresses: re-lay V^T with padded batches
         const int npad = (N + 7) / 8 * 8;
         LDN_CHECK((size_t)C * B * npad <= vt_pad_elems, "V^T pad scratch too small");
@@ -470,7 +493,8 @@ struct Builder {
       gemm(tb + ".attn2.q", a);
       AttnArgs at;
       at.Q = QK; at.ldq = ldqk; at.K = U.kctx[s.index]; at.ldk = (long long)U.heads * s.slot;
-      at.Vt = U.vtctx[s.index]; at.ldvt = (long long)U.ctx_rows * U.nk_pad; at.vt_rows = C;
+      at.Vt = U.vtctx[s.index]; at.ldvt = (long long)U.ctx_rows * U.nk_pad; at.vt_rows = s.d == 40 ? U.heads * 48 : C;
+      at.vt_head_stride = s.d == 40 ? 48 : 0;
       at.B = B; at.heads = U.heads; at.Nq = N; at.Nk = U.ctx_tokens; at.nk_pad = U.nk_pad; at.d = s.d;
       at.slot = s.slot; at.scale = scale; at.out = sO; at.ldo = C;
       AttnPlan plan = make_attn_plan(at);
@@ -551,6 +575,15 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
       const int c = U.model_ch * U.channel_mult[level];
       const int slot = slot_of(c / U.heads);
       bd.sQK.push_back(U.attn_level[level] ? A.get<bf16>((size_t)B * h * w * 2 * U.heads * slot, true) : nullptr);
+      bf16* vt40 = nullptr;
+      if (U.attn_level[level] && c / U.heads == 40) {
+        const long long tld = ((long long)B * h * w + 15) / 16 * 16;
+        vt40 = A.get<bf16>((size_t)U.heads * 48 * tld, true);
+        fill_ones_rows_kernel<<<64, 256>>>(vt40, U.heads, tld, 48, 40);
+        LDN_CUDA(cudaGetLastError());
+        LDN_CUDA(cudaDeviceSynchronize());
+      }
+      bd.sVt40.push_back(vt40);
       if (level != nlev - 1) {
         h /= 2;
         w /= 2;

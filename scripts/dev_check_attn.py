@@ -21,7 +21,7 @@ def attn(B, H, Nq, Nk, d, causal=False, time_it=False):
     out = torch.zeros(B * Nq, H * d, device=dev, dtype=torch.bfloat16)
     scale = d ** -0.5
     def run():
-        L.check(lib.ldn_attention_bf16(Qb.data_ptr(), H * slot, Kb.data_ptr(), H * slot, Vt.data_ptr(), B * nk_pad, H * d,
+        L.check(lib.ldn_attention_bf16(Qb.data_ptr(), H * slot, Kb.data_ptr(), H * slot, Vt.data_ptr(), B * nk_pad, H * d, 0,
                                        B, H, Nq, Nk, nk_pad, d, slot, int(causal), scale, out.data_ptr(), H * d, L.cur_stream()))
     run(); torch.cuda.synchronize()
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float(), is_causal=causal)

@@ -45,7 +45,7 @@ for (B,Hh,Nq,Nk,d) in ((2,8,1024,1024,40),(2,8,256,256,80),(2,8,64,64,160),(2,8,
     Vt=torch.zeros(Hh*d,B*nk_pad,device=dev,dtype=torch.bfloat16); Vt.view(Hh,d,B,nk_pad)[...,:Nk]=torch.randn(Hh,d,B,Nk,device=dev).bfloat16()
     def f():
         out=torch.zeros(B*Nq,Hh*d,device=dev,dtype=torch.bfloat16)
-        L.check(lib.ldn_attention_bf16(Qb.data_ptr(),Hh*slot,Kb.data_ptr(),Hh*slot,Vt.data_ptr(),B*nk_pad,Hh*d,B,Hh,Nq,Nk,nk_pad,d,slot,0,d**-0.5,out.data_ptr(),Hh*d,L.cur_stream()))
+        L.check(lib.ldn_attention_bf16(Qb.data_ptr(),Hh*slot,Kb.data_ptr(),Hh*slot,Vt.data_ptr(),B*nk_pad,Hh*d,0,B,Hh,Nq,Nk,nk_pad,d,slot,0,d**-0.5,out.data_ptr(),Hh*d,L.cur_stream()))
         return out
     rep(f"attn B{B} H{Hh} {Nq}x{Nk} d{d}", f)
 # groupnorm / layernorm

@@ -98,29 +98,40 @@ def test_conv3x3(lib, B, H, W, Cin, Cout):
     assert rel(out.permute(0, 3, 1, 2), ref) < TOL
 
 
-@pytest.mark.parametrize("B,H,Nq,Nk,d,causal", [(1, 1, 128, 128, 64, False), (2, 8, 1024, 1024, 40, False),
-                                                (2, 8, 1024, 77, 40, False), (2, 8, 256, 256, 160, False),
-                                                (2, 8, 1024, 1024, 80, False), (2, 8, 256, 77, 160, False),
-                                                (2, 8, 64, 64, 160, False), (2, 8, 16, 16, 160, False),
-                                                (3, 12, 77, 77, 64, True), (2, 8, 4096, 154, 40, False),
-                                                (1, 8, 4096, 4096, 40, False)])
-def test_attention(lib, B, H, Nq, Nk, d, causal):
+@pytest.mark.parametrize("B,H,Nq,Nk,d,causal,ones", [(1, 1, 128, 128, 64, False, False), (2, 8, 1024, 1024, 40, False, False),
+                                                     (2, 8, 1024, 77, 40, False, False), (2, 8, 256, 256, 160, False, False),
+                                                     (2, 8, 1024, 1024, 80, False, False), (2, 8, 256, 77, 160, False, False),
+                                                     (2, 8, 64, 64, 160, False, False), (2, 8, 16, 16, 160, False, False),
+                                                     (3, 12, 77, 77, 64, True, False), (2, 8, 4096, 154, 40, False, False),
+                                                     (1, 8, 4096, 4096, 40, False, False),
+                                                     # head dim 40 with the ones-row V^T layout (attention3.cu: row sums on the
+                                                     # tensor core, O resident in TMEM, lazy rescale)
+                                                     (2, 8, 1024, 1024, 40, False, True), (2, 8, 1024, 77, 40, False, True),
+                                                     (1, 8, 4096, 4096, 40, False, True), (2, 8, 64, 64, 40, False, True),
+                                                     (2, 8, 4096, 154, 40, False, True), (1, 2, 200, 1000, 40, False, True)])
+def test_attention(lib, B, H, Nq, Nk, d, causal, ones):
     L, l = lib
     torch.manual_seed(Nq + Nk + d)
     slot = (d + 63) // 64 * 64
     nk_pad = (Nk + 127) // 128 * 128 if Nk % 8 else Nk
+    hs = 48 if ones else d
     q = torch.randn(B, H, Nq, d, device="cuda").bfloat16()
     k = torch.randn(B, H, Nk, d, device="cuda").bfloat16()
     v = torch.randn(B, H, Nk, d, device="cuda").bfloat16()
+    if ones:  # make the running max grow along the keys so the lazy-rescale path is exercised
+        k = (k.float() * torch.linspace(0.2, 3.0, Nk, device="cuda")[None, None, :, None]).bfloat16()
     Qb = torch.zeros(B * Nq, H * slot, device="cuda", dtype=torch.bfloat16)
     Kb = torch.zeros(B * nk_pad, H * slot, device="cuda", dtype=torch.bfloat16)
     Qb.view(B, Nq, H, slot)[..., :d] = q.permute(0, 2, 1, 3)
     Kb.view(B, nk_pad, H, slot)[:, :Nk, :, :d] = k.permute(0, 2, 1, 3)
-    Vt = torch.zeros(H * d, B * nk_pad, device="cuda", dtype=torch.bfloat16)
-    Vt.view(H, d, B, nk_pad)[..., :Nk] = v.permute(1, 3, 0, 2)
+    Vt = torch.zeros(H * hs, B * nk_pad, device="cuda", dtype=torch.bfloat16)
+    Vt.view(H, hs, B, nk_pad)[:, :d, :, :Nk] = v.permute(1, 3, 0, 2)
+    if ones:
+        Vt.view(H, hs, B, nk_pad)[:, d] = 1.0
     out = torch.zeros(B * Nq, H * d, device="cuda", dtype=torch.bfloat16)
-    L.check(l.ldn_attention_bf16(Qb.data_ptr(), H * slot, Kb.data_ptr(), H * slot, Vt.data_ptr(), B * nk_pad, H * d, B, H,
-                                 Nq, Nk, nk_pad, d, slot, int(causal), d ** -0.5, out.data_ptr(), H * d, L.cur_stream()))
+    L.check(l.ldn_attention_bf16(Qb.data_ptr(), H * slot, Kb.data_ptr(), H * slot, Vt.data_ptr(), B * nk_pad, H * hs,
+                                 hs if ones else 0, B, H, Nq, Nk, nk_pad, d, slot, int(causal), d ** -0.5, out.data_ptr(),
+                                 H * d, L.cur_stream()))
     ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), is_causal=causal)
     ref = ref.permute(0, 2, 1, 3).reshape(B * Nq, H * d)
     assert rel(out, ref) < TOL
