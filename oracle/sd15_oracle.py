@@ -439,3 +439,135 @@ def ksample(sd, seed: int, steps: int, cfg: float, sampler: str, scheduler: str,
     else:
         raise ValueError(sampler)
     return x / LATENT_SCALE
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# VAE decoder  (AutoencodingEngine.decode / Decoder.forward, src/AutoEncoders/VariationalAE.py:130-145, 532-567;
+# ResnetBlock src/AutoEncoders/ResBlock.py:383-406; AttnBlock src/Attention/Attention.py:159-178; Upsample
+# VariationalAE.py:192-221; VAE.decode output mapping :602-604, 690-722)
+# ----------------------------------------------------------------------------------------------------------------
+VAE_CFG = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4, out_ch=3)
+
+
+def vae_decoder_param_shapes(cfg=VAE_CFG) -> Dict[str, Tuple[int, ...]]:
+    """Decoder-side state-dict keys (without the 'first_stage_model.' prefix) -> shapes."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(p, o, i, k):
+        s[p + ".weight"] = (o, i, k, k)
+        s[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        s[p + ".weight"] = (c,)
+        s[p + ".bias"] = (c,)
+
+    def res(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cout, cin, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".nin_shortcut", cout, cin, 1)
+
+    ch, mult, nres = cfg["ch"], cfg["ch_mult"], cfg["num_res_blocks"]
+    conv("post_quant_conv", cfg["z_channels"], cfg["z_channels"], 1)
+    block_in = ch * mult[-1]
+    conv("decoder.conv_in", block_in, cfg["z_channels"], 3)
+    res("decoder.mid.block_1", block_in, block_in)
+    norm("decoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"decoder.mid.attn_1.{n}", block_in, block_in, 1)
+    res("decoder.mid.block_2", block_in, block_in)
+    for lvl in reversed(range(len(mult))):
+        block_out = ch * mult[lvl]
+        for i in range(nres + 1):
+            res(f"decoder.up.{lvl}.block.{i}", block_in, block_out)
+            block_in = block_out
+        if lvl != 0:
+            conv(f"decoder.up.{lvl}.upsample.conv", block_in, block_in, 3)
+    norm("decoder.norm_out", block_in)
+    conv("decoder.conv_out", cfg["out_ch"], block_in, 3)
+    return s
+
+
+def _vae_res(sd, p, x):
+    h = _conv(sd, p + ".conv1", F.silu(_gn(sd, p + ".norm1", x, 1e-6)))
+    h = _conv(sd, p + ".conv2", F.silu(_gn(sd, p + ".norm2", h, 1e-6)))
+    if (p + ".nin_shortcut.weight") in sd:
+        x = _conv(sd, p + ".nin_shortcut", x, padding=0)
+    return x + h
+
+
+def vae_decode(sd: Dict[str, Tensor], z: Tensor, cfg=VAE_CFG) -> Tensor:
+    """z [B,4,h,w] fp32 -> image [B,8h,8w,3] fp32 in [0,1] (what VAEDecode returns)."""
+    mult, nres = cfg["ch_mult"], cfg["num_res_blocks"]
+    h = _conv(sd, "post_quant_conv", z.float(), padding=0)
+    h = _conv(sd, "decoder.conv_in", h)
+    h = _vae_res(sd, "decoder.mid.block_1", h)
+    # AttnBlock: single head over all pixels, d = C
+    p = "decoder.mid.attn_1"
+    n = _gn(sd, p + ".norm", h, 1e-6)
+    q, k, v = (_conv(sd, f"{p}.{t}", n, padding=0) for t in ("q", "k", "v"))
+    b, c, hh, ww = q.shape
+    q, k, v = (t.reshape(b, c, hh * ww).transpose(1, 2) for t in (q, k, v))
+    a = attention(q, k, v, heads=1).transpose(1, 2).reshape(b, c, hh, ww)
+    h = h + _conv(sd, p + ".proj_out", a, padding=0)
+    h = _vae_res(sd, "decoder.mid.block_2", h)
+    for lvl in reversed(range(len(mult))):
+        for i in range(nres + 1):
+            h = _vae_res(sd, f"decoder.up.{lvl}.block.{i}", h)
+        if lvl != 0:
+            h = _conv(sd, f"decoder.up.{lvl}.upsample.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"))
+    h = _conv(sd, "decoder.conv_out", F.silu(_gn(sd, "decoder.norm_out", h, 1e-6)))
+    return torch.clamp((h + 1.0) / 2.0, min=0.0, max=1.0).movedim(1, -1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CLIP-L text encoder  (CLIPTextModel_.forward src/clip/CLIPTextModel.py:51-107; CLIPLayer / CLIPAttention / CLIPMLP
+# src/clip/Clip.py:14-180; config include/clip/sd1_clip_config.json: 12 layers, 768 wide, 12 heads, quick_gelu)
+# ----------------------------------------------------------------------------------------------------------------
+CLIP_CFG = dict(layers=12, width=768, heads=12, mlp=3072, vocab=49408, positions=77)
+
+
+def clip_param_shapes(cfg=CLIP_CFG) -> Dict[str, Tuple[int, ...]]:
+    """Keys below 'text_model.' -> shapes."""
+    w, m = cfg["width"], cfg["mlp"]
+    s: Dict[str, Tuple[int, ...]] = {"embeddings.token_embedding.weight": (cfg["vocab"], w),
+                                     "embeddings.position_embedding.weight": (cfg["positions"], w)}
+    for i in range(cfg["layers"]):
+        p = f"encoder.layers.{i}"
+        for n in ("layer_norm1", "layer_norm2"):
+            s[f"{p}.{n}.weight"] = (w,)
+            s[f"{p}.{n}.bias"] = (w,)
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            s[f"{p}.self_attn.{n}.weight"] = (w, w)
+            s[f"{p}.self_attn.{n}.bias"] = (w,)
+        s[f"{p}.mlp.fc1.weight"] = (m, w)
+        s[f"{p}.mlp.fc1.bias"] = (m,)
+        s[f"{p}.mlp.fc2.weight"] = (w, m)
+        s[f"{p}.mlp.fc2.bias"] = (w,)
+    s["final_layer_norm.weight"] = (w,)
+    s["final_layer_norm.bias"] = (w,)
+    return s
+
+
+def clip_encode(sd: Dict[str, Tensor], ids: Tensor, cfg=CLIP_CFG) -> Tuple[Tensor, Tensor]:
+    """ids [S,77] int64 -> (final_LN(layer -2 output), final_LN(last layer output)), both [S,77,768] fp32.
+    SD1.5 conditions on the first (CLIPSetLastLayer(-2), src/clip/Clip.py:592-608)."""
+    heads = cfg["heads"]
+    x = sd["embeddings.token_embedding.weight"].float()[ids] + sd["embeddings.position_embedding.weight"].float()
+    n = x.shape[1]
+    mask = torch.full((n, n), float("-inf")).triu_(1)
+    inter = None
+    for i in range(cfg["layers"]):
+        p = f"encoder.layers.{i}"
+        h = _ln(sd, p + ".layer_norm1", x)
+        q = _linear(sd, p + ".self_attn.q_proj", h)
+        k = _linear(sd, p + ".self_attn.k_proj", h)
+        v = _linear(sd, p + ".self_attn.v_proj", h)
+        x = x + _linear(sd, p + ".self_attn.out_proj", attention(q, k, v, heads, mask))
+        h = _linear(sd, p + ".mlp.fc1", _ln(sd, p + ".layer_norm2", x))
+        x = x + _linear(sd, p + ".mlp.fc2", h * torch.sigmoid(1.702 * h))
+        if i == cfg["layers"] - 2:
+            inter = x.clone()
+    return _ln(sd, "final_layer_norm", inter), _ln(sd, "final_layer_norm", x)

@@ -122,3 +122,62 @@ if "sample" in what:
         print(name, float(res[0]["samples"].std()), flush=True)
     torch.save(out, os.path.join(HERE, "sample_small.pt"))
     print("wrote sample_small.pt")
+
+if "vae" in what:
+    from src.AutoEncoders import VariationalAE as V
+    shapes = O.vae_decoder_param_shapes()
+    sd = {k: v.float() for k, v in O.synth_state_dict(shapes, seed=4321).items()}
+    # the reference VAE also needs encoder-side keys to construct; give it its own (unused here) random ones
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    eng = V.AutoencodingEngine(V.Encoder(**dd), V.Decoder(**dd), V.DiagonalGaussianRegularizer())
+    full = eng.state_dict()
+    ref_dec = {k: tuple(v.shape) for k, v in full.items() if k.startswith("decoder.") or k.startswith("post_quant_conv")}
+    assert ref_dec == shapes, (set(ref_dec) ^ set(shapes))
+    g = torch.Generator().manual_seed(99)
+    for k in full:
+        full[k] = sd[k] if k in sd else torch.randn(full[k].shape, generator=g) * 0.02
+    vae = V.VAE(sd=full)
+    out = {}
+    for hw in (8, 16):
+        z = torch.randn(2, 4, hw, hw, generator=g)
+        img = V.VAEDecode().decode(vae, {"samples": z})[0]
+        out[f"z_{hw}"] = z
+        out[f"img_{hw}"] = img.float().clone()
+        print("vae", hw, tuple(img.shape), float(img.mean()), float(img.std()), flush=True)
+    torch.save(out, os.path.join(HERE, "vae_small.pt"))
+    print("wrote vae_small.pt")
+
+if "clip" in what:
+    from src.SD15 import SDClip, SDToken
+    shapes = O.clip_param_shapes()
+    sd = O.synth_state_dict(shapes, seed=777)
+    tok = SDToken.SD1Tokenizer(tokenizer=lambda embedding_directory=None: SDToken.SDTokenizer(
+        tokenizer_path=os.path.join(REF, "include", "sd1_tokenizer/"), embedding_directory=embedding_directory))
+    m = SDClip.SD1ClipModel(device="cpu", dtype=torch.float16)
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    pref = "clip_l.transformer.text_model."
+    mine = {pref + k: v for k, v in shapes.items()}
+    missing = set(mine) - set(ref_shapes)
+    assert not missing, missing
+    extra = {k for k in ref_shapes if k not in mine}
+    print("reference-only CLIP keys:", sorted(extra))
+    full = m.state_dict()
+    for k, v in sd.items():
+        assert tuple(full[pref + k].shape) == tuple(v.shape), k
+        full[pref + k] = v
+    m.load_state_dict(full)
+    m.set_clip_options({"layer": -2})
+    out = {}
+    for name, text in (("plain", "a photograph of an astronaut riding a horse"), ("empty", ""),
+                       ("weighted", "a (red:1.3) cube on a (blue:0.7) sphere")):
+        tokens = tok.tokenize_with_weights(text)
+        cond, pooled = m.encode_token_weights(tokens)
+        ids = torch.tensor([[t for t, _ in row] for row in tokens["l"]], dtype=torch.int64)
+        wts = torch.tensor([[w for _, w in row] for row in tokens["l"]], dtype=torch.float32)
+        out[f"{name}_ids"] = ids
+        out[f"{name}_weights"] = wts
+        out[f"{name}_cond"] = cond.float().clone()
+        print("clip", name, tuple(ids.shape), tuple(cond.shape), float(cond.std()), flush=True)
+    torch.save(out, os.path.join(HERE, "clip_small.pt"))
+    print("wrote clip_small.pt")

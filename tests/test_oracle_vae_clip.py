@@ -1,0 +1,39 @@
+"""CPU: pins the oracle's VAE decoder and CLIP-L encoder against fixtures produced by the reference itself
+(tests/golden/make_golden.py vae clip)."""
+import os
+
+import torch
+
+from oracle import sd15_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def test_vae_decode_matches_reference():
+    g = torch.load(os.path.join(GOLDEN, "vae_small.pt"))
+    sd = O.synth_state_dict(O.vae_decoder_param_shapes(), seed=4321)  # fp16-rounded, like the fixture
+    for hw in (8, 16):
+        img = O.vae_decode(sd, g[f"z_{hw}"])
+        assert img.shape == g[f"img_{hw}"].shape == (2, 8 * hw, 8 * hw, 3)
+        assert rel(img, g[f"img_{hw}"]) < 1e-5
+        assert float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+
+
+def test_clip_encode_matches_reference():
+    g = torch.load(os.path.join(GOLDEN, "clip_small.pt"))
+    sd = O.synth_state_dict(O.clip_param_shapes(), seed=777)
+    pen_empty, _ = O.clip_encode(sd, g["empty_ids"])
+    for name in ("plain", "empty"):
+        pen, last = O.clip_encode(sd, g[f"{name}_ids"])
+        assert rel(pen, g[f"{name}_cond"]) < 2e-5, name      # SD1.5 conditions on layer -2 (+ final LN)
+        assert rel(last, g[f"{name}_cond"]) > 1e-2
+    # prompt weighting (ClipTokenWeightEncoder, src/SD15/SDClip.py:54-76): z = (z - z_empty) * w + z_empty per token
+    pen, _ = O.clip_encode(sd, g["weighted_ids"])
+    w = g["weighted_weights"][0][:, None]
+    z = (pen[0] - pen_empty[0]) * w + pen_empty[0]
+    assert rel(z[None], g["weighted_cond"]) < 2e-5
+    assert float((g["weighted_weights"] != 1).sum()) >= 2
