@@ -58,6 +58,7 @@ struct GemmParams {
   const bf16* residual;
   long long ldr;
   int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
+  int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77)
   int row_head_dim, row_head_slot;  // GEMM mode, row_head_dim > 0: output row m -> (m / dim) * slot + m % dim
   // split-K (small-M problems): grid.z splits, each writes an fp32 partial tile; splitk_reduce_kernel finishes
   int splits, chunks_per_split;
@@ -98,7 +99,9 @@ struct GemmArgs {
   long long ldr = 0;
   int head_dim = 0, head_slot = 0;
   int row_head_dim = 0, row_head_slot = 0;
+  int act = 0;
   int BN = 0;  // 0 = choose
+  long long wt_ld = 0;  // leading dimension of Wt in elements (0 = K)
   int wt_rows = 0;  // valid rows of Wt if fewer than N (the rest are zero-filled by TMA)
   float* splitk_ws = nullptr;  // optional fp32 workspace enabling split-K for problems with too few tiles
   size_t splitk_ws_bytes = 0;
@@ -165,7 +168,7 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
                       const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws,
                       cudaStream_t stream);
 void launch_layernorm(const bf16* x, int rows, int C, float eps, const float* gamma, const float* beta, bf16* out,
-                      cudaStream_t stream);
+                      cudaStream_t stream, float* out_f32 = nullptr);
 // out[b, n] = act_in(x[b, :]) . W[n, :] + bias[n]   (tiny-M linear; W bf16 [N, K], x fp32 [Bn, K])
 void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
                          bool silu_out, float* out, cudaStream_t stream);
@@ -184,6 +187,8 @@ void launch_conv_out(const bf16* h, const bf16* Wt, const float* bias, const flo
 void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);
 // stride-2 3x3 pad-1 im2col gather: [B,H,W,C] -> [B*(H/2)*(W/2), 9*C]
 void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);
+// dst[c, b*nk_pad + k] = src[c, b*N + k]: V^T re-laid with 16-byte aligned per-batch column offsets
+void launch_pad_vt_cols(const bf16* src, int ld_src, int C, int Bn, int N, int nk_pad, bf16* dst, cudaStream_t stream);
 void launch_fill_bf16(bf16* p, size_t n, float v, cudaStream_t stream);
 // weight ingest: src is fp32 or fp16 (src_dtype 0 = f32, 1 = f16, 2 = bf16)
 void launch_convert_to_bf16(const void* src, int src_dtype, size_t n, bf16* dst, cudaStream_t stream);
@@ -195,6 +200,15 @@ void launch_repack_conv_weight(const void* src, int src_dtype, int O, int I, int
 void launch_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
                      float c1, float c2, const float* noise, float* x_out, float* denoised_out, size_t n,
                      cudaStream_t stream);
+// rgb[B,H,W,3] fp32 = clamp((conv3x3(h) + 1) / 2, 0, 1)   (VAE conv_out + VAE.process_output)
+void launch_conv_out_rgb(const bf16* h, const bf16* Wt, const float* bias, int B, int H, int W, int Cin, float* rgb,
+                         cudaStream_t stream);
+// y[b,o,p] = sum_c W[o,c] x[b,c,p] + bias[o] on fp32 NCHW (VAE post_quant_conv, 4 -> 4 channels)
+void launch_conv1x1_f32(const float* x, const float* W, const float* bias, int B, int Cin, int Cout, int HW, float* y,
+                        cudaStream_t stream);
+// out[r, :] = tok_emb[ids[r], :] + pos_emb[r % T, :]  -> bf16
+void launch_clip_embed(const long long* ids, const float* tok_emb, const float* pos_emb, int rows, int T, int C, bf16* out,
+                       cudaStream_t stream);
 void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
                          cudaStream_t stream);
 

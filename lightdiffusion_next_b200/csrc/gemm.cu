@@ -202,6 +202,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
             f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
           }
         }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = f[i] / (1.0f + __expf(-1.702f * f[i]));
+        }
         if (p.residual) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + n);
 #pragma unroll
@@ -394,7 +398,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
     p.tmA1 = a.A1 ? make_tmap_2d(a.A1, a.M, a.K1, a.lda1, kBM) : p.tmA0;
     plan.grid = dim3((a.N + BN - 1) / BN, (a.M + kBM - 1) / kBM, 1);
   }
-  p.tmB = make_tmap_2d(a.Wt, a.wt_rows > 0 ? a.wt_rows : a.N, K, K, BN);  // rows past wt_rows read as zero
+  p.tmB = make_tmap_2d(a.Wt, a.wt_rows > 0 ? a.wt_rows : a.N, K, a.wt_ld > 0 ? a.wt_ld : K, BN);  // rows past wt_rows read as zero
   p.epi = a.epi;
   p.out = a.out;
   p.ldo = a.ldo;
@@ -407,6 +411,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.ldr = a.ldr;
   p.head_dim = a.head_dim;
   p.head_slot = a.head_slot;
+  p.act = a.act;
   p.row_head_dim = a.row_head_dim;
   p.row_head_slot = a.row_head_slot;
   if (a.head_dim > 0) LDN_CHECK(a.head_dim % 8 == 0, "gemm: head_dim must be a multiple of 8");
@@ -426,7 +431,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.chunks_per_split = p.num_k_chunks;
   p.total_rows = p.M;
   const int tiles = plan.grid.x * plan.grid.y;
-  if (a.splitk_ws && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && !a.out_f32 && tiles < 148 && p.num_k_chunks >= 40) {
+  if (a.splitk_ws && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && a.act == 0 && !a.out_f32 && tiles < 148 && p.num_k_chunks >= 40) {
     int splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > p.num_k_chunks / 8) splits = p.num_k_chunks / 8;
     if (splits > 16) splits = 16;

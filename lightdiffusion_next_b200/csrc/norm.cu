@@ -205,7 +205,7 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
 // ------------------------------------------------------------------ LayerNorm: one warp per row, row held in registers
 template <int MAXV>
 __global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int C, float eps, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, bf16* __restrict__ out) {
+                                 const float* __restrict__ beta, bf16* __restrict__ out, float* __restrict__ out_f32) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -257,28 +257,33 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int C, fl
       const float4 b1 = *reinterpret_cast<const float4*>(beta + c + 4);
       const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      uint32_t o[4];
+      if (out_f32) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        o[i] = pack_bf16x2((v[k][2 * i] - mean) * rstd * g[2 * i] + bb[2 * i],
-                           (v[k][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bb[2 * i + 1]);
-      *reinterpret_cast<uint4*>(dst + c) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < 8; ++i) out_f32[(size_t)warp * C + c + i] = (v[k][i] - mean) * rstd * g[i] + bb[i];
+      } else {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          o[i] = pack_bf16x2((v[k][2 * i] - mean) * rstd * g[2 * i] + bb[2 * i],
+                             (v[k][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bb[2 * i + 1]);
+        *reinterpret_cast<uint4*>(dst + c) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }
 
 void launch_layernorm(const bf16* x, int rows, int C, float eps, const float* gamma, const float* beta, bf16* out,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, float* out_f32) {
   LDN_CHECK(C % 8 == 0 && C <= 8 * 32 * 6, "layernorm: C must be a multiple of 8 and <= 1536");
   const int threads = 256;
   const int blocks = (rows * 32 + threads - 1) / threads;
   const int nvec = C / 8;
   if (nvec <= 64)
-    layernorm_kernel<2><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
+    layernorm_kernel<2><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out, out_f32);
   else if (nvec <= 96)
-    layernorm_kernel<3><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
+    layernorm_kernel<3><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out, out_f32);
   else
-    layernorm_kernel<6><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out);
+    layernorm_kernel<6><<<blocks, threads, 0, stream>>>(x, rows, C, eps, gamma, beta, out, out_f32);
   LDN_CUDA(cudaGetLastError());
 }
 

@@ -465,3 +465,105 @@ void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long l
 }
 
 }  // namespace ldn
+
+namespace ldn {
+
+// ------------------------------------------------------------------ VAE conv_out (Cin -> 3) with the image mapping fused
+__global__ void conv_out_rgb_kernel(const bf16* __restrict__ h, const bf16* __restrict__ Wt, const float* __restrict__ bias,
+                                    int B, int H, int W, int Cin, float* __restrict__ rgb) {
+  extern __shared__ float s_wrgb[];  // [3][9*Cin]
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_wrgb[i] = __bfloat162float(Wt[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const size_t npix = (size_t)B * H * W;
+  const int nvec = Cin >> 3;
+  for (size_t pix = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += (size_t)gridDim.x * wpb) {
+    const int xw = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int b = (int)(pix / ((size_t)W * H));
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = xw + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const bf16* src = h + (((size_t)b * H + yy) * W + xx) * Cin;
+        const int kbase = (ky * 3 + kx) * Cin;
+        for (int v = lane; v < nvec; v += 32) {
+          const uint4 u = *reinterpret_cast<const uint4*>(src + v * 8);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float f0 = bf16_lo(w[i]), f1 = bf16_hi(w[i]);
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              const float* wr = s_wrgb + o * K + kbase + v * 8 + 2 * i;
+              acc[o] = fmaf(f0, wr[0], fmaf(f1, wr[1], acc[o]));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o)
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const float e = acc[o] + (bias ? bias[o] : 0.f);
+        rgb[pix * 3 + o] = fminf(fmaxf((e + 1.0f) * 0.5f, 0.f), 1.f);
+      }
+    }
+  }
+}
+void launch_conv_out_rgb(const bf16* h, const bf16* Wt, const float* bias, int B, int H, int W, int Cin, float* rgb,
+                         cudaStream_t stream) {
+  LDN_CHECK(Cin % 8 == 0, "conv_out_rgb: Cin must be a multiple of 8");
+  const size_t smem = sizeof(float) * 3 * 9 * Cin;
+  conv_out_rgb_kernel<<<148 * 4, 512, smem, stream>>>(h, Wt, bias, B, H, W, Cin, rgb);
+  LDN_CUDA(cudaGetLastError());
+}
+
+__global__ void conv1x1_f32_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                                   int B, int Cin, int Cout, int HW, float* __restrict__ y) {
+  const size_t total = (size_t)B * Cout * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int o = (int)((i / HW) % Cout);
+    const int b = (int)(i / ((size_t)HW * Cout));
+    float acc = bias ? bias[o] : 0.f;
+    for (int c = 0; c < Cin; ++c) acc = fmaf(W[o * Cin + c], x[((size_t)b * Cin + c) * HW + p], acc);
+    y[i] = acc;
+  }
+}
+void launch_conv1x1_f32(const float* x, const float* W, const float* bias, int B, int Cin, int Cout, int HW, float* y,
+                        cudaStream_t stream) {
+  const size_t total = (size_t)B * Cout * HW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv1x1_f32_kernel<<<blocks, 256, 0, stream>>>(x, W, bias, B, Cin, Cout, HW, y);
+  LDN_CUDA(cudaGetLastError());
+}
+
+__global__ void clip_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                  int rows, int T, int C, bf16* __restrict__ out) {
+  const size_t total = (size_t)rows * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int r = (int)(i / C);
+    out[i] = __float2bfloat16(tok[(size_t)ids[r] * C + c] + pos[(size_t)(r % T) * C + c]);
+  }
+}
+void launch_clip_embed(const long long* ids, const float* tok_emb, const float* pos_emb, int rows, int T, int C, bf16* out,
+                       cudaStream_t stream) {
+  const size_t total = (size_t)rows * C;
+  int blocks = (int)((total + 255) / 256);
+  clip_embed_kernel<<<blocks, 256, 0, stream>>>(ids, tok_emb, pos_emb, rows, T, C, out);
+  LDN_CUDA(cudaGetLastError());
+}
+
+}  // namespace ldn

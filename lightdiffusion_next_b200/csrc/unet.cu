@@ -59,6 +59,11 @@ __global__ void pad_vt_cols_kernel(const bf16* __restrict__ src, int ld_src, int
   }
 }
 
+void launch_pad_vt_cols(const bf16* src, int ld_src, int C, int Bn, int N, int nk_pad, bf16* dst, cudaStream_t stream) {
+  pad_vt_cols_kernel<<<64, 256, 0, stream>>>(src, ld_src, C, Bn, N, nk_pad, dst);
+  LDN_CUDA(cudaGetLastError());
+}
+
 // V^T buffers of head-dim-40 layers carry 48 rows per head; row 40 of every head is all ones (softmax row sums on the
 // tensor core, attention3.cu), rows 41..47 stay zero.
 __global__ void fill_ones_rows_kernel(bf16* __restrict__ vt, int heads, long long ld, int head_stride, int row) {
