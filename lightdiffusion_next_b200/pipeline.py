@@ -1,0 +1,59 @@
+"""pipe(prompt, ...) / sample() / decode() surface of the engine — the host-side mirror of `pipeline()`
+(src/user/pipeline.py:31-518) for the SD1.5 txt2img path: CLIP encode -> KSampler -> VAE decode.
+
+Tokenisation stays with the caller (the reference's SD1Tokenizer, src/SD15/SDToken.py:292-396, is host Python that runs in
+microseconds and needs its vocabulary files): `tokens` is what `tokenize_with_weights` returns, i.e. a list of 77-long
+lists of (token_id, weight).  Everything after that runs on the B200 engine.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import sampling as S
+from .engine import Engine
+
+EMPTY_TOKENS = [49406] + [49407] * 76  # <|startoftext|>, <|endoftext|> padding: what the SD1 tokenizer emits for ""
+
+
+class Pipeline:
+    def __init__(self, engine: Engine):
+        self.e = engine
+
+    # ---------------------------------------------------------------- CLIPTextEncode (src/clip/Clip.py:574-589)
+    def encode(self, tokens: Sequence[Sequence[Tuple[int, float]]]) -> torch.Tensor:
+        """tokens: k chunks of 77 (id, weight) pairs -> conditioning [1, 77*k, 768] (layer -2 + final LN).
+        Prompt weights: per-token lerp against the empty-prompt encoding (ClipTokenWeightEncoder, SDClip.py:54-76)."""
+        ids = torch.tensor([[t for t, _ in row] for row in tokens], dtype=torch.int64)
+        wts = torch.tensor([[w for _, w in row] for row in tokens], dtype=torch.float32)
+        has_w = bool((wts != 1.0).any())
+        if has_w:
+            ids = torch.cat([ids, torch.tensor([EMPTY_TOKENS], dtype=torch.int64)])
+        pen, _ = self.e.clip_encode(ids)
+        if has_w:
+            z_empty = pen[-1]
+            pen = pen[:-1]
+            w = wts.to(pen.device)[:, :, None]
+            pen = (pen - z_empty) * w + z_empty
+        return pen.reshape(1, -1, pen.shape[-1])
+
+    # ---------------------------------------------------------------- KSampler (src/sample/sampling.py:773-887)
+    def sample(self, positive: torch.Tensor, negative: torch.Tensor, width: int, height: int, batch: int = 1,
+               seed: int = 0, steps: int = 20, cfg: float = 7.0, sampler_name: str = "dpmpp_2m_cfgpp",
+               scheduler: str = "karras", enable_multiscale: bool = True) -> torch.Tensor:
+        latent = {"samples": torch.zeros(batch, 4, height // 8, width // 8)}  # EmptyLatentImage (Latent.py:174-190)
+        return S.sample(self.e, seed, steps, cfg, sampler_name, scheduler, positive, negative, latent,
+                        enable_multiscale=enable_multiscale)[0]["samples"]
+
+    # ---------------------------------------------------------------- VAEDecode (VariationalAE.py:771-784)
+    def decode(self, samples: torch.Tensor) -> torch.Tensor:
+        """latents (already divided by 0.18215, as KSampler returns them) -> [B,H,W,3] fp32 in [0,1] on the CPU."""
+        return self.e.vae_decode(samples).cpu()
+
+    def __call__(self, tokens, negative_tokens=None, width: int = 512, height: int = 512, batch: int = 1, seed: int = 0,
+                 steps: int = 20, cfg: float = 7.0, sampler_name: str = "dpmpp_2m_cfgpp", scheduler: str = "karras"):
+        pos = self.encode(tokens)
+        neg = self.encode(negative_tokens if negative_tokens is not None else [[(t, 1.0) for t in EMPTY_TOKENS]])
+        lat = self.sample(pos, neg, width, height, batch, seed, steps, cfg, sampler_name, scheduler)
+        return self.decode(lat)
