@@ -337,7 +337,7 @@ def main():
                          "ms_per_launch": attn_ms, "launches_per_step": 5},
         }
         if step_tflop is not None:
-            whole = its / world / bs * step_tflop
+            whole = its / world * step_tflop  # `its` counts image-iterations; each is one CFG step of step_tflop
             line["step_roofline"] = {"bound": "tensor", "achieved": whole, "peak": peaks["bf16_sus"], "unit": "TFLOP/s",
                                      "frac": whole / peaks["bf16_sus"], "tflop_per_step": step_tflop,
                                      "peak_source": peaks["source"] + " (sustained)"}

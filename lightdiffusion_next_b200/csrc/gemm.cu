@@ -17,7 +17,7 @@
 //               GEMM mode: A may be a virtual concat of two matrices along K (skip-connection concat).
 //   warp 1      allocates TMEM; lane 0 issues tcgen05.mma (M=128, N=BN, K=16) x 4 per stage, fp32 accum in TMEM,
 //               tcgen05.commit releases the smem stage / publishes the accumulator.
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns, fused bias / time-embedding row bias / residual /
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, alternate 16-column chunks): tcgen05.ld 32 lanes x 16 columns, fused bias / time-embedding row bias / residual /
 //               GEGLU (value * gelu_erf(gate)), bf16 (or fp32) store.
 #include "common.h"
 #include "ptx.cuh"
@@ -26,7 +26,7 @@ namespace ldn {
 
 static constexpr int kBM = 128;
 static constexpr int kBK = 64;
-static constexpr int kGemmThreads = 192;
+static constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int ehalf = (warp - 2) >> 2;  // the two warps of a quarter take alternate 16-column chunks
     const int r = q * 32 + lane;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     if (p.splits > 1) {
       // split-K: raw fp32 partial tile; bias / residual are applied by splitk_reduce_kernel
       float* wbase = p.ws + (long long)blockIdx.z * p.ws_split_stride;
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = ehalf * 16; c < BN; c += 32) {
         uint32_t v[16];
         tmem_ld16(t_lane + (uint32_t)c, v);
         tmem_ld_wait();
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
         __syncwarp();
       }
     } else if (p.epi == 0) {
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = ehalf * 16; c < BN; c += 32) {
         uint32_t v[16];
         tmem_ld16(t_lane + (uint32_t)c, v);
         tmem_ld_wait();
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       // by the BN/2 matching gate columns (Activation.py:30-31: x, gate = proj(x).chunk(2); x * gelu(gate)).
       const int half = BN / 2;
       const int o0 = n0 / 2;
-      for (int c = 0; c < half; c += 16) {
+      for (int c = ehalf * 16; c < half; c += 32) {
         uint32_t va[16], vg[16];
         tmem_ld16(t_lane + (uint32_t)c, va);
         tmem_ld16(t_lane + (uint32_t)(half + c), vg);
