@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
       if (p.causal) limit = min(limit, q_idx - kbase + 1);
       const bool need_mask = limit < kTileK;
       // pass 1: row max
-      float mx = -INFINITY;
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
 #pragma unroll
       for (int c = 0; c < kTileK; c += 32) {
         uint32_t v[32];
@@ -181,16 +181,17 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
         if (need_mask) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c + i < limit) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (c + i < limit) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v[i]));
         }
       }
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       const float m_new = fmaxf(m_run, mx * sc);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = fast_exp2(m_run - m_use);   // m_run = -inf -> 0
-      float rs = 0.f;
+      float rsa[4] = {0.f, 0.f, 0.f, 0.f};
       // pass 2: p = exp2(s*sc - m), write bf16 P tile (K-major, 128B swizzle)
 #pragma unroll
       for (int c = 0; c < kTileK; c += 32) {
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
             if (c + i >= limit) p0 = 0.f;
             if (c + i + 1 >= limit) p1 = 0.f;
           }
-          rs += p0 + p1;
+          rsa[(i >> 1) & 3] += p0 + p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
         // 32 keys = 4 x 16B chunks; chunk index within the 64-key atom row: (c/8 + t) & 7, atom = c / 64
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
                        : "memory");
         }
       }
-      l_run = l_run * alpha + rs;
+      l_run = l_run * alpha + ((rsa[0] + rsa[1]) + (rsa[2] + rsa[3]));
       m_run = m_new;
       fence_proxy_async_smem();
       tc_fence_before();

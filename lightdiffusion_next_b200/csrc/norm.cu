@@ -44,7 +44,25 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16*
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
     const int p_begin = blockIdx.x * rows_per_block;
     const int p_end = min(HW, p_begin + rows_per_block);
-    for (int pix = p_begin + prow; pix < p_end; pix += R) {
+    int pix = p_begin + prow;
+    for (; pix + 3 * R < p_end; pix += 4 * R) {  // four independent 16-byte loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(pix + u * R) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = bf16_lo(w[i]), bb = bf16_hi(w[i]);
+          s[2 * i] += a;
+          q[2 * i] += a * a;
+          s[2 * i + 1] += bb;
+          q[2 * i + 1] += bb * bb;
+        }
+      }
+    }
+    for (; pix < p_end; pix += R) {
       const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)pix * ld);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -149,6 +167,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16*
   const int p_begin = blockIdx.x * rows_per_block;
   const int p_end = min(HW, p_begin + rows_per_block);
   const int total = (p_end - p_begin) * nvec;
+#pragma unroll 2
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int pix = p_begin + idx / nvec;
     const int c = (idx % nvec) * 8;
