@@ -264,41 +264,53 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
       if (pb == 2) {
         if (j >= 2) mbar_wait(&p_free[2 * t + (j & 1)], (uint32_t)(((j >> 1) + 1) & 1));
         p_row += (uint32_t)(j & 1) * 2 * atom_bytes;
-      } else if (j >= 1) {
-        mbar_wait(my_pv_done, (uint32_t)(j - 1) & 1u);  // P*V of the previous key tile has finished reading the buffer
       }
       const float m_off = m_used;
       // MUFU ping-pong: the two softmax warpgroups take turns in the exp phase (named barriers 1 / 2)
       if (p.pingpong) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-      // software-pipelined: the MUFU works on chunk c while the FMA pipe prepares chunk c+1 and the ALU / LSU pack and
-      // store chunk c-1, so no instruction waits on the ~20-clk MUFU latency in program order
-      float x[8], e[8], d[8];
+      // Exp phase. With a single P buffer the previous tile's P*V may still be reading it when this tile's first
+      // probabilities are ready (MMA issue + execution + commit take ~600 clk after p_full), so the first half of the
+      // row is exponentiated and packed into registers only; the buffer is waited for at the midpoint -- by then the
+      // MMA has long finished -- and the deferred stores go out together with the second half.
+      uint32_t pk[8][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sv[i]), sc, -m_off);
+      for (int c = 0; c < 8; ++c) {
+        float e[8];
 #pragma unroll
-      for (int c = 0; c <= 16; ++c) {
-        if (c < 16) {
+        for (int i = 0; i < 8; ++i) e[i] = fmaf(__uint_as_float(sv[c * 8 + i]), sc, -m_off);
+        if ((kPolyMask >> c) & 1u) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = ex2p(e[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = ex2m(e[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[c][i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+      }
+      if (pb == 1 && j >= 1) mbar_wait(my_pv_done, (uint32_t)(j - 1) & 1u);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        uint32_t w0, w1, w2, w3;
+        if (c < 8) {
+          w0 = pk[c][0]; w1 = pk[c][1]; w2 = pk[c][2]; w3 = pk[c][3];
+        } else {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = fmaf(__uint_as_float(sv[c * 8 + i]), sc, -m_off);
           if ((kPolyMask >> c) & 1u) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = ex2p(x[i]);
+            for (int i = 0; i < 8; ++i) e[i] = ex2p(e[i]);
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = ex2m(x[i]);
+            for (int i = 0; i < 8; ++i) e[i] = ex2m(e[i]);
           }
+          w0 = pack_bf16x2(e[0], e[1]); w1 = pack_bf16x2(e[2], e[3]);
+          w2 = pack_bf16x2(e[4], e[5]); w3 = pack_bf16x2(e[6], e[7]);
         }
-        if (c + 1 < 16) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = fmaf(__uint_as_float(sv[(c + 1) * 8 + i]), sc, -m_off);
-        }
-        if (c > 0) {
-          const int cc = (c - 1) * 8;
-          const uint32_t addr = p_row + (uint32_t)(cc >> 6) * atom_bytes + ((((uint32_t)(cc & 63) >> 3) << 4) ^ sw16);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack_bf16x2(d[0], d[1])),
-                       "r"(pack_bf16x2(d[2], d[3])), "r"(pack_bf16x2(d[4], d[5])), "r"(pack_bf16x2(d[6], d[7]))
-                       : "memory");
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = e[i];
+        const int cc = c * 8;
+        const uint32_t addr = p_row + (uint32_t)(cc >> 6) * atom_bytes + ((((uint32_t)(cc & 63) >> 3) << 4) ^ sw16);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
       }
       if (p.pingpong && !(t == 1 && j == n_tiles - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(1 + (t ^ 1)) : "memory");
       fence_proxy_async_smem();
