@@ -312,7 +312,7 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   p.variant = 1;
   p.vt_head_stride = a.vt_head_stride > 0 ? a.vt_head_stride : a.d;
   static const bool force_v1 = getenv("LDN_ATTN_V1") != nullptr;
-  static const int poly_mod = getenv("LDN_ATTN_POLY") ? atoi(getenv("LDN_ATTN_POLY")) : 0;
+  static const int poly_mod = getenv("LDN_ATTN_POLY") ? atoi(getenv("LDN_ATTN_POLY")) : 3;  // 37.5 % of the ex2 on the FMA pipes (measured best)
   p.poly_mod = poly_mod;
   if (a.d == 40 && p.vt_head_stride == 48) {
     // ones-row V^T: generation 3 (default). Generation 4 (two threads per row, 16 softmax warps) measured slower

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
     }
     for (int s = 0; s < stages; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], 2);
     }
     fence_barrier_init();
   }
@@ -135,57 +135,65 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
           tma_load_2d(v_dst + vt_atom_bytes, &p.tmVt, &kv_full[s], key0 + 64, h * kDV3);
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
+      // One MMA-issuing thread PER QUERY TILE (warp 1 -> tile 0, warp 2 -> tile 1). A resource-binding experiment
+      // (exponentials removed: same run time) showed that a single issuing thread was the bottleneck of generations
+      // 1-3: at d = 40 the MMAs are tiny (N = 48: 24 tensor-clk each), so descriptor arithmetic + issue latency of 22 MMAs
+      // per key tile on ONE thread cost more than the softmax. All descriptors that do not depend on the ring stage
+      // are built once, the per-stage ones with a single 32-bit add.
       if (lane == 0) {
+        const int t = warp - 1;
         const uint32_t idesc_s = make_idesc_bf16(128, 128);
         const uint32_t idesc_pv = make_idesc_bf16(128, kDV3);
-        const uint32_t q_addr = smem_u32(q_smem);
-        const uint32_t p_addr = smem_u32(p_smem);
         const uint32_t kv_addr = smem_u32(kv_smem);
-        auto issue_s = [&](int t, uint32_t k_addr) {
-          const uint64_t a0 = make_smem_desc_sw128(q_addr + (uint32_t)t * atom_bytes);
-          const uint64_t b0 = make_smem_desc_sw128(k_addr);
-#pragma unroll
-          for (int ks = 0; ks < 3; ++ks)  // dqk = 48
-            tc_mma_bf16(tmem_base + (uint32_t)t * 128, a0 + (uint64_t)(2 * ks), b0 + (uint64_t)(2 * ks), idesc_s,
-                        ks > 0 ? 1u : 0u);
-          tc_commit(&s_full[t]);
-        };
+        const uint32_t tm_s = tmem_base + (uint32_t)t * 128;
+        const uint32_t tm_o = tmem_base + 256 + (uint32_t)t * 64;
+        const uint64_t qd0 = make_smem_desc_sw128(smem_u32(q_smem) + (uint32_t)t * atom_bytes);
+        const uint64_t pd0 = make_smem_desc_sw128(smem_u32(p_smem) + (uint32_t)(t * pb) * 2 * atom_bytes);
+        const uint64_t pd1 = pd0 + (uint64_t)(atom_bytes >> 4);
+        const uint64_t kv0 = make_smem_desc_sw128(kv_addr);  // descriptor of stage 0's K tile; stages / V^T are offsets
+        uint64_t* const my_s_full = &s_full[t];
+        uint64_t* const my_s_free = &s_free[t];
+        uint64_t* const my_p_full = &p_full[t];
         mbar_wait(q_full, 0);
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        issue_s(0, kv_addr);
-        issue_s(1, kv_addr);
+        tc_mma_bf16(tm_s, qd0, kv0, idesc_s, 0u);
+        tc_mma_bf16(tm_s, qd0 + 2, kv0 + 2, idesc_s, 1u);
+        tc_mma_bf16(tm_s, qd0 + 4, kv0 + 4, idesc_s, 1u);
+        tc_commit(my_s_full);
+        int s = 0;
         for (int j = 0; j < n_tiles; ++j) {
-          const int s = j % stages;
-          const uint32_t v_addr = kv_addr + (uint32_t)s * stage_bytes + atom_bytes;
+          const uint64_t kd = kv0 + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+          const uint64_t vd0 = kd + (uint64_t)(atom_bytes >> 4);
+          const uint64_t vd1 = vd0 + (uint64_t)(vt_atom_bytes >> 4);
           if (j + 1 < n_tiles) {
-            const int s1 = (j + 1) % stages;
+            const int s1 = (s + 1 == stages) ? 0 : s + 1;
             mbar_wait(&kv_full[s1], (uint32_t)((j + 1) / stages) & 1u);
-            const uint32_t k_next = kv_addr + (uint32_t)s1 * stage_bytes;
-            for (int t = 0; t < 2; ++t) {
-              mbar_wait(&s_free[t], (uint32_t)j & 1u);
-              tc_fence_after();
-              issue_s(t, k_next);
-            }
-          }
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&p_full[t], (uint32_t)j & 1u);
+            const uint64_t kn = kv0 + (uint64_t)(((uint32_t)s1 * stage_bytes) >> 4);
+            mbar_wait(my_s_free, (uint32_t)j & 1u);
             tc_fence_after();
-            const uint32_t pa = p_addr + (uint32_t)(t * pb + (pb == 2 ? (j & 1) : 0)) * 2 * atom_bytes;
-#pragma unroll
-            for (int ks = 0; ks < kK3 / 16; ++ks) {
-              const uint64_t adesc =
-                  make_smem_desc_sw128(pa + (uint32_t)(ks >> 2) * atom_bytes) + (uint64_t)(2 * (ks & 3));
-              const uint64_t bdesc =
-                  make_smem_desc_sw128(v_addr + (uint32_t)(ks >> 2) * vt_atom_bytes) + (uint64_t)(2 * (ks & 3));
-              // O (and the row sum in column 40) accumulate across key tiles
-              tc_mma_bf16(tmem_base + 256 + (uint32_t)t * 64, adesc, bdesc, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
-            }
-            tc_commit(&pv_done[t]);
-            tc_commit(&p_free[2 * t + (j & 1)]);
+            tc_mma_bf16(tm_s, qd0, kn, idesc_s, 0u);
+            tc_mma_bf16(tm_s, qd0 + 2, kn + 2, idesc_s, 1u);
+            tc_mma_bf16(tm_s, qd0 + 4, kn + 4, idesc_s, 1u);
+            tc_commit(my_s_full);
           }
-          tc_commit(&kv_empty[s]);
+          const uint64_t pa = pd0 + (pb == 2 && (j & 1) ? (uint64_t)((2 * atom_bytes) >> 4) : 0ull);
+          const uint64_t pbb = pd1 + (pb == 2 && (j & 1) ? (uint64_t)((2 * atom_bytes) >> 4) : 0ull);
+          mbar_wait(my_p_full, (uint32_t)j & 1u);
+          tc_fence_after();
+          tc_mma_bf16(tm_o, pa, vd0, idesc_pv, j > 0 ? 1u : 0u);
+          tc_mma_bf16(tm_o, pa + 2, vd0 + 2, idesc_pv, 1u);
+          tc_mma_bf16(tm_o, pa + 4, vd0 + 4, idesc_pv, 1u);
+          tc_mma_bf16(tm_o, pa + 6, vd0 + 6, idesc_pv, 1u);
+          tc_mma_bf16(tm_o, pbb, vd1, idesc_pv, 1u);
+          tc_mma_bf16(tm_o, pbb + 2, vd1 + 2, idesc_pv, 1u);
+          tc_mma_bf16(tm_o, pbb + 4, vd1 + 4, idesc_pv, 1u);
+          tc_mma_bf16(tm_o, pbb + 6, vd1 + 6, idesc_pv, 1u);
+          tc_commit(&pv_done[t]);
+          if (pb == 2) tc_commit(&p_free[2 * t + (j & 1)]);
+          tc_commit(&kv_empty[s]);  // 2 arrivals per stage: one from each tile's issuing thread
+          s = (s + 1 == stages) ? 0 : s + 1;
         }
       }
     }
@@ -278,7 +286,10 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
         float e[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) e[i] = fmaf(__uint_as_float(sv[c * 8 + i]), sc, -m_off);
-        if ((kPolyMask >> c) & 1u) {
+        if (kPolyMask == 0x10000u) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = e[i] * 0.001f;  // EXPERIMENT ONLY: no exponential
+        } else if ((kPolyMask >> c) & 1u) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = ex2p(e[i]);
         } else {
@@ -298,7 +309,10 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = fmaf(__uint_as_float(sv[c * 8 + i]), sc, -m_off);
-          if ((kPolyMask >> c) & 1u) {
+          if (kPolyMask == 0x10000u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = e[i] * 0.001f;  // EXPERIMENT ONLY
+          } else if ((kPolyMask >> c) & 1u) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) e[i] = ex2p(e[i]);
           } else {
@@ -368,6 +382,7 @@ void launch_attn3(const AttnPlan& plan, cudaStream_t stream) {
     case 3: return launch_attn3_t<0x9249u>(plan, stream);  // 37.5 %
     case 4: return launch_attn3_t<0x8888u>(plan, stream);  // 25 %
     case 8: return launch_attn3_t<0x8080u>(plan, stream);  // 12.5 %
+    case 99: return launch_attn3_t<0x10000u>(plan, stream);  // experiment: no exponential (wrong results)
     default: return launch_attn3_t<0u>(plan, stream);
   }
 }
