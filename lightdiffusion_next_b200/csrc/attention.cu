@@ -318,8 +318,11 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
     // ones-row V^T: generation 3 (default). Generation 4 (two threads per row, 16 softmax warps) measured slower
     // (2.21 ms vs 1.92 ms at N = 16384) and is kept only as a documented experiment (LDN_ATTN_V4=1).
     static const bool use_v4 = getenv("LDN_ATTN_V4") != nullptr;
+    static const bool use_v3 = getenv("LDN_ATTN_V3") != nullptr;
+    // default: generation 5 (generation 3 + P kept in tensor memory, TS-form P*V)
     if (use_v4) finish_attn4_plan(plan, a.Nq, a.Nk, a.heads, a.B);
-    else finish_attn3_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+    else if (use_v3) finish_attn3_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+    else finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   } else {
     LDN_CHECK(p.vt_head_stride == a.d, "attention: vt_head_stride is only supported as 48 for d = 40");
     if (dp <= 64 && !force_v1) finish_attn2_plan(plan, a.Nq, a.Nk, a.heads, a.B);
@@ -339,6 +342,7 @@ static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 }
 
 void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
+  if (plan.p.variant == 5) return launch_attn5(plan, stream);
   if (plan.p.variant == 4) return launch_attn4(plan, stream);
   if (plan.p.variant == 3) return launch_attn3(plan, stream);
   if (plan.p.variant == 2) return launch_attn2(plan, stream);

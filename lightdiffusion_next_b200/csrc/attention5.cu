@@ -1,19 +1,10 @@
-// Attention kernel, third generation, for head dim 40 (SD1.5 level 0: N = 16384 tokens at 1024^2, 42 % of the step's
-// FLOPs). Same Q / K layout as attention.cu; V^T carries, per head, 48 rows: 40 value rows, one row of ONES and 7 zero rows.
-//
-// What the ncu captures of the first two generations showed (profiles/r1_attention_ncu_full.md): at d = 40 the kernel is
-// bound by the softmax instruction stream, not by the MMAs (384 tensor-clk per 128x128 tile vs 1024 MUFU-clk and about
-// as many FMA/ALU-pipe clk). This version strips the per-element FMA/ALU work to the minimum:
-//   * the softmax ROW SUM is computed by the tensor core: because row 40 of V^T is all ones, column 40 of P*V is
-//     sum_k P[q,k] (of the same bf16-rounded P the numerator uses) -> no FADD per element;
-//   * O (and the row sum) stay RESIDENT in TMEM across key tiles (tcgen05.mma accumulates), so there is no per-tile
-//     TMEM->register read-modify-write of O; the running max is applied lazily: P uses a stale max and O is rescaled
-//     in TMEM (tcgen05.ld / tcgen05.st) only when the true max has grown by more than 2^8 (rare after the first tiles);
-//   * per element what remains is 1 FFMA (scale, subtract max) + 1 ex2 + half a pack; a compile-time subset of the ex2
-//     can run as a polynomial on the FMA pipes to balance MUFU against FMA;
-//   * schedule as in generation 2: two 128-row query tiles per CTA sharing each K / V^T tile, one softmax warpgroup per
-//     tile (one thread per row, S row read from TMEM once into registers), S of the next key tile issued as soon as the
-//     current one is in registers, P double-buffered in shared memory, setmaxnreg 56 / 224.
+// Attention kernel, fifth generation, head dim 40: generation 3 (attention3.cu) with the probabilities P kept in
+// TENSOR MEMORY instead of shared memory. After the MMA-issue fix, generation 3 without exponentials still needed
+// 2330 clk per key tile against 1781 clk of pure shared-memory traffic (228 KB per tile pair at 128 B/clk: P written by the
+// softmax threads, P re-read as the A operand of P*V, K / V^T tiles, TMA fills) -- it sat on the shared-memory roofline.
+// Here the softmax threads write bf16 P with tcgen05.st into TMEM columns [384, 512) (64 columns per query tile, two keys
+// per 32-bit cell) and P*V is issued in the TS form (A operand from TMEM), which removes 128 KB of the 228 KB and the
+// generic->async proxy fence; the freed 64 KB of shared memory deepen the K / V^T ring.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -21,6 +12,7 @@
 #include <cstdlib>
 
 namespace ldn {
+namespace a5 {
 
 static constexpr int kA3Threads = 384;
 static constexpr int kQ3 = 128;
@@ -57,7 +49,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <uint32_t kPolyMask>
-__global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kA3Threads, 1) attn5_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -70,9 +62,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
   constexpr uint32_t stage_bytes = atom_bytes + 2 * vt_atom_bytes;
 
   uint8_t* q_smem = smem;                       // 2 query tiles
-  uint8_t* p_smem = smem + 2 * atom_bytes;      // [tile][parity][2 atoms]
-  const int pb = p.p_bufs;                      // 1: single P buffer per tile (more K/V stages), 2: double buffered
-  uint8_t* kv_smem = p_smem + (size_t)(4 * pb) * atom_bytes;
+  uint8_t* kv_smem = smem + 2 * atom_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + (size_t)stages * stage_bytes);
   uint64_t* q_full = bars;         // 1
   uint64_t* s_full = bars + 1;     // [2]
@@ -83,7 +73,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
   uint64_t* kv_full = bars + 13;
   uint64_t* kv_empty = kv_full + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + stages);
-  constexpr uint32_t kTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,304) O1 [320,368)
+  constexpr uint32_t kTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,304) O1 [320,368) P0 [384,448) P1 [448,512)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -150,8 +140,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
         const uint32_t tm_s = tmem_base + (uint32_t)t * 128;
         const uint32_t tm_o = tmem_base + 256 + (uint32_t)t * 64;
         const uint64_t qd0 = make_smem_desc_sw128(smem_u32(q_smem) + (uint32_t)t * atom_bytes);
-        const uint64_t pd0 = make_smem_desc_sw128(smem_u32(p_smem) + (uint32_t)(t * pb) * 2 * atom_bytes);
-        const uint64_t pd1 = pd0 + (uint64_t)(atom_bytes >> 4);
+        const uint32_t tm_p = tmem_base + 384 + (uint32_t)t * 64;
         const uint64_t kv0 = make_smem_desc_sw128(kv_addr);  // descriptor of stage 0's K tile; stages / V^T are offsets
         uint64_t* const my_s_full = &s_full[t];
         uint64_t* const my_s_free = &s_free[t];
@@ -185,21 +174,19 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
             }
             __syncwarp();
           }
-          const uint64_t pa = pd0 + (pb == 2 && (j & 1) ? (uint64_t)((2 * atom_bytes) >> 4) : 0ull);
-          const uint64_t pbb = pd1 + (pb == 2 && (j & 1) ? (uint64_t)((2 * atom_bytes) >> 4) : 0ull);
           mbar_wait(my_p_full, (uint32_t)j & 1u);
           tc_fence_after();
           if (elect_one()) {
-          tc_mma_bf16(tm_o, pa, vd0, idesc_pv, j > 0 ? 1u : 0u);
-          tc_mma_bf16(tm_o, pa + 2, vd0 + 2, idesc_pv, 1u);
-          tc_mma_bf16(tm_o, pa + 4, vd0 + 4, idesc_pv, 1u);
-          tc_mma_bf16(tm_o, pa + 6, vd0 + 6, idesc_pv, 1u);
-          tc_mma_bf16(tm_o, pbb, vd1, idesc_pv, 1u);
-          tc_mma_bf16(tm_o, pbb + 2, vd1 + 2, idesc_pv, 1u);
-          tc_mma_bf16(tm_o, pbb + 4, vd1 + 4, idesc_pv, 1u);
-          tc_mma_bf16(tm_o, pbb + 6, vd1 + 6, idesc_pv, 1u);
+          // A = P from TMEM: k-step ks covers keys [16 ks, 16 ks + 16) = 8 packed columns
+          tc_mma_bf16_ts(tm_o, tm_p + 0, vd0, idesc_pv, j > 0 ? 1u : 0u);
+          tc_mma_bf16_ts(tm_o, tm_p + 8, vd0 + 2, idesc_pv, 1u);
+          tc_mma_bf16_ts(tm_o, tm_p + 16, vd0 + 4, idesc_pv, 1u);
+          tc_mma_bf16_ts(tm_o, tm_p + 24, vd0 + 6, idesc_pv, 1u);
+          tc_mma_bf16_ts(tm_o, tm_p + 32, vd1, idesc_pv, 1u);
+          tc_mma_bf16_ts(tm_o, tm_p + 40, vd1 + 2, idesc_pv, 1u);
+          tc_mma_bf16_ts(tm_o, tm_p + 48, vd1 + 4, idesc_pv, 1u);
+          tc_mma_bf16_ts(tm_o, tm_p + 56, vd1 + 6, idesc_pv, 1u);
           tc_commit(&pv_done[t]);
-          if (pb == 2) tc_commit(&p_free[2 * t + (j & 1)]);
           tc_commit(&kv_empty[s]);  // 2 arrivals per stage: one from each tile's issuing thread
           }
           __syncwarp();
@@ -218,8 +205,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
     const uint32_t tmem_o = tmem_base + 256 + (uint32_t)t * 64 + lane_off;
     const int q_idx = q0 + t * kQ3 + r;
     const float sc = p.scale_log2;
-    const uint32_t p_row0 = pin3(smem_u32(p_smem) + (uint32_t)(t * pb) * 2 * atom_bytes + (uint32_t)r * 128);
-    const uint32_t sw16 = (uint32_t)(r & 7) << 4;
+    const uint32_t tmem_p = tmem_base + 384 + (uint32_t)t * 64 + lane_off;
     uint64_t* const my_s_full = &s_full[t];
     uint64_t* const my_s_free = &s_free[t];
     uint64_t* const my_p_full = &p_full[t];
@@ -278,11 +264,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
         }
       }
       // the P buffer of this parity was last read by P*V of key tile j-2
-      uint32_t p_row = p_row0;
-      if (pb == 2) {
-        if (j >= 2) mbar_wait(&p_free[2 * t + (j & 1)], (uint32_t)(((j >> 1) + 1) & 1));
-        p_row += (uint32_t)(j & 1) * 2 * atom_bytes;
-      }
+
       const float m_off = m_used;
       // MUFU ping-pong: the two softmax warpgroups take turns in the exp phase (named barriers 1 / 2)
       if (p.pingpong) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
@@ -309,7 +291,7 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i) pk[c][i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
       }
-      if (pb == 1 && j >= 1) mbar_wait(my_pv_done, (uint32_t)(j - 1) & 1u);
+      if (j >= 1) mbar_wait(my_pv_done, (uint32_t)(j - 1) & 1u);  // P*V of the previous tile has consumed P
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         uint32_t w0, w1, w2, w3;
@@ -332,12 +314,12 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
           w0 = pack_bf16x2(e[0], e[1]); w1 = pack_bf16x2(e[2], e[3]);
           w2 = pack_bf16x2(e[4], e[5]); w3 = pack_bf16x2(e[6], e[7]);
         }
-        const int cc = c * 8;
-        const uint32_t addr = p_row + (uint32_t)(cc >> 6) * atom_bytes + ((((uint32_t)(cc & 63) >> 3) << 4) ^ sw16);
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tmem_p + (uint32_t)(c * 4)), "r"(w0),
+                     "r"(w1), "r"(w2), "r"(w3)
+                     : "memory");
       }
       if (p.pingpong && !(t == 1 && j == n_tiles - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(1 + (t ^ 1)) : "memory");
-      fence_proxy_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(my_p_full);
     }
@@ -375,45 +357,48 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn3_tc_kernel(const __grid_co
   }
 }
 
+}  // namespace a5
+using namespace a5;
+
 template <uint32_t kPolyMask>
-static void launch_attn3_t(const AttnPlan& plan, cudaStream_t stream) {
+static void launch_attn5_t(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDN_CUDA(cudaFuncSetAttribute(attn3_tc_kernel<kPolyMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(attn5_tc_kernel<kPolyMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  attn3_tc_kernel<kPolyMask><<<plan.grid, kA3Threads, plan.smem_bytes, stream>>>(plan.p);
+  attn5_tc_kernel<kPolyMask><<<plan.grid, kA3Threads, plan.smem_bytes, stream>>>(plan.p);
   LDN_CUDA(cudaGetLastError());
 }
 
-void launch_attn3(const AttnPlan& plan, cudaStream_t stream) {
+void launch_attn5(const AttnPlan& plan, cudaStream_t stream) {
   switch (plan.p.poly_mod) {
-    case 2: return launch_attn3_t<0xAAAAu>(plan, stream);  // 50 % polynomial
-    case 3: return launch_attn3_t<0x9249u>(plan, stream);  // 37.5 %
-    case 4: return launch_attn3_t<0x8888u>(plan, stream);  // 25 %
-    case 8: return launch_attn3_t<0x8080u>(plan, stream);  // 12.5 %
-    case 99: return launch_attn3_t<0x10000u>(plan, stream);  // experiment: no exponential (wrong results)
-    default: return launch_attn3_t<0u>(plan, stream);
+    case 2: return launch_attn5_t<0xAAAAu>(plan, stream);  // 50 % polynomial
+    case 3: return launch_attn5_t<0x9249u>(plan, stream);  // 37.5 %
+    case 4: return launch_attn5_t<0x8888u>(plan, stream);  // 25 %
+    case 8: return launch_attn5_t<0x8080u>(plan, stream);  // 12.5 %
+    case 99: return launch_attn5_t<0x10000u>(plan, stream);  // experiment: no exponential (wrong results)
+    default: return launch_attn5_t<0u>(plan, stream);
   }
 }
 
-void finish_attn3_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B) {
+void finish_attn5_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B) {
   AttnParams& p = plan.p;
-  LDN_CHECK(p.d == 40 && p.dv == 48 && p.dqk == 48 && !p.causal, "attention3: d = 40, non-causal only");
+  LDN_CHECK(p.d == 40 && p.dv == 48 && p.dqk == 48 && !p.causal, "attention5: d = 40, non-causal only");
   const int stage_bytes = 16384 + 2 * kDV3 * 128;
-  static const int pbufs = getenv("LDN_ATTN_PBUF") ? atoi(getenv("LDN_ATTN_PBUF")) : 1;
-  p.p_bufs = pbufs == 2 ? 2 : 1;
-  static const int pingpong = getenv("LDN_ATTN_PINGPONG") ? atoi(getenv("LDN_ATTN_PINGPONG")) : 0;
-  p.pingpong = pingpong;
-  const int fixed = 2 * 16384 + 4 * p.p_bufs * 16384 + 1024 + 256;
+  const int fixed = 2 * 16384 + 1024 + 512;
   const int n_tiles = (Nk + kK3 - 1) / kK3;
   int stages = (226 * 1024 - fixed) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages > n_tiles) stages = n_tiles;
   if (getenv("LDN_ATTN_STAGES")) stages = std::min(stages, atoi(getenv("LDN_ATTN_STAGES")));
+  if (stages < 2 && n_tiles >= 2) stages = 2;
   if (stages < 1) stages = 1;
   p.kv_stages = stages;
-  p.variant = 3;
+  p.variant = 5;
+  p.p_bufs = 1;
+  static const int pingpong = getenv("LDN_ATTN_PINGPONG") ? atoi(getenv("LDN_ATTN_PINGPONG")) : 0;
+  p.pingpong = pingpong;
   plan.smem_bytes = fixed + stages * stage_bytes;
   plan.grid = dim3((Nq + 2 * kQ3 - 1) / (2 * kQ3), heads, B);
 }

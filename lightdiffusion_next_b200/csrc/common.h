@@ -158,6 +158,8 @@ void finish_attn2_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn2(const AttnPlan& plan, cudaStream_t stream);
 void finish_attn3_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn3(const AttnPlan& plan, cudaStream_t stream);
+void finish_attn5_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
+void launch_attn5(const AttnPlan& plan, cudaStream_t stream);
 void finish_attn4_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn4(const AttnPlan& plan, cudaStream_t stream);
 void launch_attn(const AttnPlan& plan, cudaStream_t stream);

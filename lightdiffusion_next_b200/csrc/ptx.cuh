@@ -140,6 +140,19 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// Same with the A operand in tensor memory (TS form): A is 128 lanes x K/2 32-bit columns, two bf16 per cell.
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, dense.
 // Bit layout follows the sm_100 UMMA instruction descriptor: c_format[4,6) a_format[7,10)
 // b_format[10,13) a_major[15] b_major[16] n>>3 [17,23) m>>4 [24,29).
