@@ -115,38 +115,48 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp walks the loop (warp-uniform descriptors in uniform registers); one elected lane issues
+    {
       const uint32_t idesc_s = make_idesc_bf16(128, 128);
       const uint32_t idesc_pv = make_idesc_bf16(128, DV);
-      const uint32_t q_addr = smem_u32(q_smem);
-      const uint32_t p_addr = smem_u32(p_smem);
+      const uint64_t qd = make_smem_desc_sw128(smem_u32(q_smem));
+      const uint64_t pd = make_smem_desc_sw128(smem_u32(p_smem));
+      const uint64_t kv0 = make_smem_desc_sw128(smem_u32(kv_smem));
       mbar_wait(q_full, 0);
+      int s = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % stages;
-        const uint32_t ph = (uint32_t)(j / stages) & 1u;
         mbar_wait(&kv_full[s], ph);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(kv_smem + (size_t)s * stage_bytes);
-        const uint32_t v_addr = k_addr + k_bytes;
-        // S = Q K^T
-        for (int ks = 0; ks < nqk_ksteps; ++ks) {
-          const uint32_t off = (uint32_t)(ks >> 2) * atom_bytes;
-          const uint64_t adesc = make_smem_desc_sw128(q_addr + off) + (uint64_t)(2 * (ks & 3));
-          const uint64_t bdesc = make_smem_desc_sw128(k_addr + off) + (uint64_t)(2 * (ks & 3));
-          tc_mma_bf16(tmem_s, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+        const uint64_t kd = kv0 + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+        const uint64_t vd = kd + (uint64_t)(k_bytes >> 4);
+        if (elect_one()) {
+          // S = Q K^T
+          for (int ks = 0; ks < nqk_ksteps; ++ks) {
+            const uint64_t off = (uint64_t)(((uint32_t)(ks >> 2) * atom_bytes) >> 4) + (uint64_t)(2 * (ks & 3));
+            tc_mma_bf16(tmem_s, qd + off, kd + off, idesc_s, ks > 0 ? 1u : 0u);
+          }
+          tc_commit(s_full);
         }
-        tc_commit(s_full);
+        __syncwarp();
         // wait for P (also implies S and the previous PV were consumed)
         mbar_wait(p_full, (uint32_t)j & 1u);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kTileK / 16; ++ks) {
-          const uint64_t adesc = make_smem_desc_sw128(p_addr + (uint32_t)(ks >> 2) * atom_bytes) + (uint64_t)(2 * (ks & 3));
-          const uint64_t bdesc = make_smem_desc_sw128(v_addr + (uint32_t)(ks >> 2) * vt_atom_bytes) + (uint64_t)(2 * (ks & 3));
-          tc_mma_bf16(tmem_pv, adesc, bdesc, idesc_pv, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < kTileK / 16; ++ks) {
+            const uint64_t aoff = (uint64_t)(((uint32_t)(ks >> 2) * atom_bytes) >> 4) + (uint64_t)(2 * (ks & 3));
+            const uint64_t boff = (uint64_t)(((uint32_t)(ks >> 2) * vt_atom_bytes) >> 4) + (uint64_t)(2 * (ks & 3));
+            tc_mma_bf16(tmem_pv, pd + aoff, vd + boff, idesc_pv, ks > 0 ? 1u : 0u);
+          }
+          tc_commit(&kv_empty[s]);
+          tc_commit(pv_full);
         }
-        tc_commit(&kv_empty[s]);
-        tc_commit(pv_full);
+        __syncwarp();
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else {

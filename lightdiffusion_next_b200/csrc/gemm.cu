@@ -129,27 +129,34 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop so that addresses / descriptors are warp-uniform (uniform registers); one elected
+    // lane issues the MMAs and the commits.
+    {
       const uint32_t idesc = make_idesc_bf16(kBM, (uint32_t)BN);
+      const uint32_t smem_base = smem_u32(smem);
+      int s = 0;
+      uint32_t ph = 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
-        const int it = kc - kc_begin;
-        const int s = it % stages;
-        const uint32_t ph = (uint32_t)(it / stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
         const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-        const uint64_t b_desc = make_smem_desc_sw128(b_addr);
-#pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
+        const uint64_t b_desc = make_smem_desc_sw128(a_addr + a_bytes);
+        if (elect_one()) {
           // advance 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-          tc_mma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (it > 0 || k > 0) ? 1u : 0u);
+          tc_mma_bf16(tmem_base, a_desc, b_desc, idesc, kc > kc_begin ? 1u : 0u);
+          tc_mma_bf16(tmem_base, a_desc + 2, b_desc + 2, idesc, 1u);
+          tc_mma_bf16(tmem_base, a_desc + 4, b_desc + 4, idesc, 1u);
+          tc_mma_bf16(tmem_base, a_desc + 6, b_desc + 6, idesc, 1u);
+          tc_commit(&empty_bar[s]);
+          if (kc + 1 == kc_end) tc_commit(acc_bar);
         }
-        tc_commit(&empty_bar[s]);
+        __syncwarp();
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-      tc_commit(acc_bar);
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
