@@ -62,6 +62,7 @@ struct GemmParams {
   int row_head_dim, row_head_slot;  // GEMM mode, row_head_dim > 0: output row m -> (m / dim) * slot + m % dim
   // split-K (small-M problems): grid.z splits, each writes an fp32 partial tile; splitk_reduce_kernel finishes
   int splits, chunks_per_split;
+  int grid_n, grid_m;  // tile grid (persistent kernel walks it)
   float* ws;
   long long ws_split_stride;  // elements between consecutive splits (= rows * N)
   int total_rows;
@@ -71,6 +72,8 @@ struct GemmPlan {
   GemmParams p;
   dim3 grid;
   int smem_bytes;
+  bool persistent = false;
+  int pgrid = 0;  // CTAs of the persistent kernel (<= SM count)
 };
 
 struct GemmArgs {

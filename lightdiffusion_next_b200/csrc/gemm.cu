@@ -22,6 +22,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace ldn {
 
 static constexpr int kBM = 128;
@@ -44,6 +46,128 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float erf_abs = fmaf(-p, e, 1.0f);  // erf(|x| / sqrt(2))
   const float phi = 0.5f * (1.0f + copysignf(erf_abs, x));
   return x * phi;
+}
+
+// Drains one 128 x BN fp32 accumulator tile from TMEM (columns starting at t_lane) through the fused epilogue.
+// Executed by the 8 epilogue warps; `ehalf` selects which alternate 16-column chunks this warp handles.
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const int BN, const int n0, const long long out_row,
+                                                   const int batch, const uint32_t t_lane, const int ehalf,
+                                                   const int split_z) {
+
+    if (p.splits > 1) {
+      // split-K: raw fp32 partial tile; bias / residual are applied by splitk_reduce_kernel
+      float* wbase = p.ws + (long long)split_z * p.ws_split_stride;
+      for (int c = ehalf * 16; c < BN; c += 32) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (out_row >= 0 && n < p.N) {
+          float4* op = reinterpret_cast<float4*>(wbase + out_row * p.N + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            op[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                __uint_as_float(v[4 * i + 3]));
+        }
+        __syncwarp();
+      }
+    } else if (p.epi == 0) {
+      for (int c = ehalf * 16; c < BN; c += 32) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (out_row >= 0 && n < p.N) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(p.bias + n + i);
+            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+          }
+        }
+        if (p.rowbias) {
+          const float* rb = p.rowbias + (long long)batch * p.ld_rowbias + n;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(rb + i);
+            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = f[i] / (1.0f + __expf(-1.702f * f[i]));
+        }
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + n);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 rv = rp[h];
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[h * 8 + 2 * i] += bf16_lo(w[i]);
+              f[h * 8 + 2 * i + 1] += bf16_hi(w[i]);
+            }
+          }
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldo + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            int col = n + h * 8;
+            if (p.head_dim > 0) col = (col / p.head_dim) * p.head_slot + (col % p.head_dim);
+            uint4 ov;
+            ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
+            ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
+            ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
+            ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
+            *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + col) = ov;
+          }
+        }
+        }
+        __syncwarp();
+      }
+    } else {
+      // GEGLU: weight rows were interleaved at load time so that this tile holds BN/2 value columns followed
+      // by the BN/2 matching gate columns (Activation.py:30-31: x, gate = proj(x).chunk(2); x * gelu(gate)).
+      const int half = BN / 2;
+      const int o0 = n0 / 2;
+      for (int c = ehalf * 16; c < half; c += 32) {
+        uint32_t va[16], vg[16];
+        tmem_ld16(t_lane + (uint32_t)c, va);
+        tmem_ld16(t_lane + (uint32_t)(half + c), vg);
+        tmem_ld_wait();
+        if (out_row >= 0 && (n0 + c) < p.N) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = __uint_as_float(va[i]);
+          float g = __uint_as_float(vg[i]);
+          if (p.bias) {
+            a += p.bias[n0 + c + i];
+            g += p.bias[n0 + half + c + i];
+          }
+          f[i] = a * gelu_erf(g);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 ov;
+          ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
+          ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
+          ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
+          ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
+          *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + o0 + c + h * 8) = ov;
+        }
+        }
+        __syncwarp();
+      }
+    }
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -183,120 +307,188 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
     }
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, (int)blockIdx.z);
+  }
 
-    if (p.splits > 1) {
-      // split-K: raw fp32 partial tile; bias / residual are applied by splitk_reduce_kernel
-      float* wbase = p.ws + (long long)blockIdx.z * p.ws_split_stride;
-      for (int c = ehalf * 16; c < BN; c += 32) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + (uint32_t)c, v);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        if (out_row >= 0 && n < p.N) {
-          float4* op = reinterpret_cast<float4*>(wbase + out_row * p.N + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            op[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                __uint_as_float(v[4 * i + 3]));
-        }
-        __syncwarp();
-      }
-    } else if (p.epi == 0) {
-      for (int c = ehalf * 16; c < BN; c += 32) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + (uint32_t)c, v);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        if (out_row >= 0 && n < p.N) {
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(p.bias + n + i);
-            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-          }
-        }
-        if (p.rowbias) {
-          const float* rb = p.rowbias + (long long)batch * p.ld_rowbias + n;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(rb + i);
-            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-          }
-        }
-        if (p.act == 1) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = f[i] / (1.0f + __expf(-1.702f * f[i]));
-        }
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + n);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 rv = rp[h];
-            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f[h * 8 + 2 * i] += bf16_lo(w[i]);
-              f[h * 8 + 2 * i + 1] += bf16_hi(w[i]);
-            }
-          }
-        }
-        if (p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldo + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------------- persistent variant
+// One CTA per SM walks a static list of (split, m-tile, n-tile) work items: barrier init, TMEM allocation and descriptor
+// prefetch happen once per SM instead of once per tile; the TMA producer runs ahead into the next tile's K chunks while
+// the epilogue warps drain the previous accumulator (two accumulator stages in TMEM: tmem_full / tmem_empty), and the
+// shared-memory ring is as deep as the whole SM allows. Short-K GEMMs (1x1 projections, K = 320) were dominated by the
+// per-CTA prologue + pipeline ramp of the one-tile-per-CTA kernel.
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_persist_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  const uint32_t a_bytes = kBM * kBK * 2;
+  const uint32_t b_bytes = (uint32_t)BN * kBK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tfull_bar = empty_bar + stages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained (8 arrivals: one per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const uint32_t acc_stride = (uint32_t)p.tmem_cols / 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmB);
+    if (!p.conv && p.a0_chunks < p.num_k_chunks) tma_prefetch_desc(&p.tmA1);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = p.grid_n, mn_tiles = p.grid_n * p.grid_m, total = mn_tiles * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int z = w / mn_tiles, rem = w - z * mn_tiles;
+        const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+        const int n0 = nt * BN;
+        int m0 = 0, x0 = 0, y0 = 0, b0 = 0;
+        if (p.conv) {
+          int t = mt;
+          const int tx = t % p.tiles_x;
+          t /= p.tiles_x;
+          const int ty = t % p.tiles_y;
+          x0 = tx * p.BW;
+          y0 = ty * p.BH;
+          b0 = (t / p.tiles_y) * p.BB;
         } else {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            int col = n + h * 8;
-            if (p.head_dim > 0) col = (col / p.head_dim) * p.head_slot + (col % p.head_dim);
-            uint4 ov;
-            ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
-            ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
-            ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
-            ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
-            *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + col) = ov;
+          m0 = mt * kBM;
+        }
+        const int kc_begin = z * p.chunks_per_split;
+        const int kc_end = min(p.num_k_chunks, kc_begin + p.chunks_per_split);
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+          uint8_t* b_dst = a_dst + a_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          if (p.conv) {
+            const int tap = kc / p.cin_chunks;
+            const int cc = kc - tap * p.cin_chunks;
+            const int dy = tap / 3 - 1;
+            const int dx = tap - (tap / 3) * 3 - 1;
+            tma_load_4d(a_dst, &p.tmA0, &full_bar[s], cc * kBK, x0 + dx, y0 + dy, b0);
+          } else if (kc < p.a0_chunks) {
+            tma_load_2d(a_dst, &p.tmA0, &full_bar[s], kc * kBK, m0);
+          } else {
+            tma_load_2d(a_dst, &p.tmA1, &full_bar[s], (kc - p.a0_chunks) * kBK, m0);
+          }
+          tma_load_2d(b_dst, &p.tmB, &full_bar[s], kc * kBK, n0);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+    const uint32_t idesc = make_idesc_bf16(kBM, (uint32_t)BN);
+    const uint32_t smem_base = smem_u32(smem);
+    int s = 0;
+    uint32_t ph = 0;
+    int tl = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
+      const int z = w / mn_tiles;
+      const int kc_begin = z * p.chunks_per_split;
+      const int kc_end = min(p.num_k_chunks, kc_begin + p.chunks_per_split);
+      const int acc = tl & 1;
+      mbar_wait(&tempty_bar[acc], (((uint32_t)tl >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+        const uint64_t b_desc = make_smem_desc_sw128(a_addr + a_bytes);
+        if (elect_one()) {
+          tc_mma_bf16(d_tmem, a_desc, b_desc, idesc, kc > kc_begin ? 1u : 0u);
+          tc_mma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+          tc_mma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+          tc_mma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+          tc_commit(&empty_bar[s]);
+          if (kc + 1 == kc_end) tc_commit(&tfull_bar[acc]);
         }
         __syncwarp();
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-    } else {
-      // GEGLU: weight rows were interleaved at load time so that this tile holds BN/2 value columns followed
-      // by the BN/2 matching gate columns (Activation.py:30-31: x, gate = proj(x).chunk(2); x * gelu(gate)).
-      const int half = BN / 2;
-      const int o0 = n0 / 2;
-      for (int c = ehalf * 16; c < half; c += 32) {
-        uint32_t va[16], vg[16];
-        tmem_ld16(t_lane + (uint32_t)c, va);
-        tmem_ld16(t_lane + (uint32_t)(half + c), vg);
-        tmem_ld_wait();
-        if (out_row >= 0 && (n0 + c) < p.N) {
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a = __uint_as_float(va[i]);
-          float g = __uint_as_float(vg[i]);
-          if (p.bias) {
-            a += p.bias[n0 + c + i];
-            g += p.bias[n0 + half + c + i];
-          }
-          f[i] = a * gelu_erf(g);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 ov;
-          ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
-          ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
-          ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
-          ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
-          *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + o0 + c + h * 8) = ov;
-        }
-        }
-        __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;
+    const int ehalf = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    int tl = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
+      const int z = w / mn_tiles, rem = w - z * mn_tiles;
+      const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+      const int n0 = nt * BN;
+      long long out_row;
+      int batch;
+      if (p.conv) {
+        int t = mt;
+        const int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int tb = t / p.tiles_y;
+        const int bx = r % p.BW;
+        const int by = (r / p.BW) % p.BH;
+        const int bb = r / (p.BW * p.BH);
+        const int x = tx * p.BW + bx, y = ty * p.BH + by, b = tb * p.BB + bb;
+        const bool ok = (x < p.W) && (y < p.H) && (b < p.B);
+        out_row = ok ? ((long long)(b * p.H + y) * p.W + x) : -1;
+        batch = b;
+      } else {
+        const int m = mt * kBM + r;
+        out_row = (m < p.M) ? m : -1;
+        if (p.row_head_dim > 0 && out_row >= 0)
+          out_row = (m / p.row_head_dim) * p.row_head_slot + (m % p.row_head_dim);
+        batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
       }
+      const int acc = tl & 1;
+      mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
 
@@ -473,6 +665,27 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   if (stages > p.chunks_per_split) stages = p.chunks_per_split;
   p.stages = stages;
   plan.smem_bytes = stages * stage_bytes + 1024 + 256;
+  // persistent variant: one CTA per SM, two accumulator stages in TMEM, ring as deep as shared memory allows
+  p.grid_n = plan.grid.x;
+  p.grid_m = plan.grid.y;
+  static const bool force_v1 = getenv("LDN_GEMM_V1") != nullptr;
+  // persistent (1 CTA / SM, single MMA stream) wins when K is short (per-CTA prologue + pipeline ramp dominate); for
+  // long-K problems (3x3 convs) two independent CTAs per SM keep the tensor pipe busier (measured 1018 vs 796 TFLOP/s)
+  static const int persist_max_chunks = getenv("LDN_GEMM_PERSIST_MAX") ? atoi(getenv("LDN_GEMM_PERSIST_MAX")) : 20;
+  plan.persistent = !force_v1 && p.chunks_per_split <= persist_max_chunks;
+  if (plan.persistent) {
+    int acc_stride = 32;
+    while (acc_stride < BN) acc_stride <<= 1;
+    p.tmem_cols = 2 * acc_stride;  // <= 512
+    int pst = (225 * 1024 - 2048) / stage_bytes;
+    if (pst > 8) pst = 8;
+    const int total_chunks = p.chunks_per_split;
+    (void)total_chunks;
+    p.stages = pst;
+    plan.smem_bytes = pst * stage_bytes + 1024 + 512;
+    const int total = (int)(plan.grid.x * plan.grid.y * plan.grid.z);
+    plan.pgrid = total < 148 ? total : 148;
+  }
   return plan;
 }
 
@@ -482,7 +695,16 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  gemm_tc_kernel<<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+  if (plan.persistent) {
+    static bool attr2 = false;
+    if (!attr2) {
+      LDN_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr2 = true;
+    }
+    gemm_tc_persist_kernel<<<plan.pgrid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+  } else {
+    gemm_tc_kernel<<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+  }
   LDN_CUDA(cudaGetLastError());
   if (plan.p.splits > 1) {
     const GemmParams& p = plan.p;
