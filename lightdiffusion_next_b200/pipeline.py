@@ -57,3 +57,14 @@ class Pipeline:
         neg = self.encode(negative_tokens if negative_tokens is not None else [[(t, 1.0) for t in EMPTY_TOKENS]])
         lat = self.sample(pos, neg, width, height, batch, seed, steps, cfg, sampler_name, scheduler)
         return self.decode(lat)
+
+
+def hires_fix(pipe: "Pipeline", samples: torch.Tensor, positive: torch.Tensor, negative: torch.Tensor, width: int,
+              height: int, seed: int = 0, steps: int = 10, cfg: float = 8.0, denoise: float = 0.45,
+              sampler_name: str = "euler_ancestral_cfgpp", scheduler: str = "normal") -> torch.Tensor:
+    """The HiresFix branch of pipeline() (src/user/pipeline.py:346-366): bislerp-upscale the latent to 2x the pixel size,
+    then a second KSampler pass with partial denoise.  `samples`: latents as returned by Pipeline.sample."""
+    from .latent import latent_upscale
+
+    up = latent_upscale({"samples": samples}, width * 2, height * 2)
+    return S.sample(pipe.e, seed, steps, cfg, sampler_name, scheduler, positive, negative, up, denoise=denoise)[0]["samples"]

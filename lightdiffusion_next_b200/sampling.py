@@ -127,12 +127,16 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
     Returns ({"samples": latents / 0.18215 on the CPU},) like the reference node."""
     if sampler_name not in SAMPLERS:
         raise ValueError(f"sampler {sampler_name!r} is not built (have {SAMPLERS})")
-    if denoise != 1.0:
-        raise NotImplementedError("denoise < 1 (img2img / HiresFix second pass) is not built yet")
     latent = latent_image["samples"]
     B = latent.shape[0]
     dev = engine.device
-    sigmas = calculate_sigmas(engine.schedule, scheduler, steps)
+    if denoise is None or denoise > 0.9999:
+        sigmas = calculate_sigmas(engine.schedule, scheduler, steps)
+    else:
+        # KSampler1.set_steps (sampling.py:655-675): the tail of a longer schedule (HiresFix second pass, img2img)
+        if denoise <= 0.0:
+            return ({"samples": latent.clone()},)
+        sigmas = calculate_sigmas(engine.schedule, scheduler, int(steps / denoise))[-(steps + 1):]
     if noise is None:
         noise = prepare_noise(latent, seed)
     lat = latent * LATENT_SCALE if torch.count_nonzero(latent) > 0 else latent  # CFG.py:266-269
@@ -141,6 +145,13 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
     else:
         x = noise * sigmas[0]
     x = (x + lat).to(dev, torch.float32).contiguous()
+    # contexts of unequal token length are tiled to their least common multiple before batching (cond.py:100-126)
+    tn, tp = negative.shape[1], positive.shape[1]
+    if tn != tp:
+        import math
+        lcm = tn * tp // math.gcd(tn, tp)
+        negative = negative.repeat(1, lcm // tn, 1)
+        positive = positive.repeat(1, lcm // tp, 1)
     ctx = torch.cat([negative.expand(B, -1, -1), positive.expand(B, -1, -1)]).to(dev)  # rows: uncond first
     engine.set_context(ctx)
     if sampler_name == "dpmpp_2m_cfgpp":
