@@ -21,7 +21,7 @@ from .engine import Engine
 from .schedule import calculate_sigmas, get_ancestral_step, max_denoise
 
 LATENT_SCALE = 0.18215  # src/Utilities/Latent.py:41-62
-SAMPLERS = ("dpmpp_2m_cfgpp", "euler_ancestral_cfgpp")
+SAMPLERS = ("dpmpp_2m_cfgpp", "euler_ancestral_cfgpp", "dpmpp_sde_cfgpp")
 
 
 def prepare_noise(latent: torch.Tensor, seed: int) -> torch.Tensor:
@@ -119,10 +119,88 @@ def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.
     return x
 
 
+class BrownianIntervalNoise:
+    """Default noise source of dpmpp_sde when none is injected: increments of one Brownian path W over sigma
+    ("time" = sigma, as BrownianTreeNoiseSampler uses it, src/sample/sampling_util.py:239-287), normalised by
+    sqrt(|interval|).  The two queries of a step, (sigma_i, sigma_s) and (sigma_i, sigma_{i+1}), overlap; their
+    increments are built from the same two independent pieces so they are correlated as on a true path.  Drawn on the
+    device; statistically equivalent to the reference's CPU Brownian tree, not sample-identical (inject `noise_sampler`
+    for that)."""
+
+    def __init__(self, x: torch.Tensor, seed: Optional[int] = None):
+        self.shape, self.device = x.shape, x.device
+        self.gen = torch.Generator(device=x.device)
+        self.gen.manual_seed(0 if seed is None else int(seed))
+        self._left = None   # (sigma_hi, sigma_mid, increment over [mid, hi])
+
+    def _draw(self, var: float) -> torch.Tensor:
+        return torch.randn(self.shape, generator=self.gen, device=self.device) * (var ** 0.5)
+
+    def __call__(self, sigma, sigma_next) -> torch.Tensor:
+        hi, lo = float(sigma), float(sigma_next)
+        if self._left is not None and abs(self._left[0] - hi) < 1e-12 and lo < self._left[1]:
+            inc = self._left[2] + self._draw(self._left[1] - lo)   # extend the path from sigma_s down to sigma_{i+1}
+            self._left = None
+        else:
+            inc = self._draw(hi - lo)
+            self._left = (hi, lo, inc)
+        return inc / ((hi - lo) ** 0.5)
+
+
+def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
+                           noise_sampler: Optional[Callable] = None, seed: Optional[int] = None, eta: float = 1.0,
+                           r: float = 0.5, enable_multiscale: bool = False, multiscale_factor: float = 0.5,
+                           callback: Optional[Callable] = None) -> torch.Tensor:
+    """DPM-Solver++ (SDE) as the reference executes it (samplers.py:966-1254): two CFG-batched UNet evaluations per
+    step (at sigma_i and at the midpoint in log-sigma), ancestral noise from `noise_sampler(sigma, sigma_next)`."""
+    B, _, oh, ow = x.shape
+    sh = int(max(8, ((oh * multiscale_factor) // 8) * 8)) if enable_multiscale else oh
+    sw = int(max(8, ((ow * multiscale_factor) // 8) * 8)) if enable_multiscale else ow
+    active = enable_multiscale and (sh != oh or sw != ow)
+    sig = sigmas.float().cpu()
+    n = len(sig) - 1
+    if noise_sampler is None:
+        noise_sampler = BrownianIntervalNoise(x, seed)
+    full = SamplerLoop(engine, B, oh, ow)
+    low = SamplerLoop(engine, B, sh, sw) if active else None
+    sigma_fn = lambda t: t.neg().exp()
+    t_fn = lambda s: s.log().neg()
+
+    def denoised_at(xx: torch.Tensor, sigma: float, fullres: bool) -> torch.Tensor:
+        loop = full if fullres else low
+        xin = xx if fullres else F.interpolate(xx, size=(sh, sw), mode="bilinear", align_corners=False)
+        du, dc = loop.denoise_pair(xin, sigma)
+        d = torch.empty_like(xin)
+        engine.cfg_step(None, du, dc, cfg, 2, denoised_out=d)
+        return d if fullres else F.interpolate(d, size=(oh, ow), mode="bilinear", align_corners=False)
+
+    for i in range(n):
+        fullres = (not active) or (i < 5 or i >= n - 8)  # sampler defaults: start 5, end 8, not intermittent
+        den = denoised_at(x, float(sig[i]), fullres)
+        if sig[i + 1] == 0:
+            x = x + (x - den) / float(sig[i]) * float(sig[i + 1] - sig[i])
+        else:
+            t, t_next = t_fn(sig[i]), t_fn(sig[i + 1])
+            s = t + (t_next - t) * r
+            sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(s), eta)
+            s_ = t_fn(sd)
+            n1 = noise_sampler(sigma_fn(t), sigma_fn(s)).to(x.device)
+            x_2 = float(sigma_fn(s_) / sigma_fn(t)) * x - float((t - s_).expm1()) * den + n1 * float(su)
+            den_2 = denoised_at(x_2, float(sigma_fn(s)), fullres)
+            sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(t_next), eta)
+            t_next_ = t_fn(sd)
+            d_mix = (1 - 1 / (2 * r)) * den + (1 / (2 * r)) * den_2
+            n2 = noise_sampler(sigma_fn(t), sigma_fn(t_next)).to(x.device)
+            x = float(sigma_fn(t_next_) / sigma_fn(t)) * x - float((t - t_next_).expm1()) * d_mix + n2 * float(su)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sig[i], "denoised": den})
+    return x
+
+
 def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str, scheduler: str,
            positive: torch.Tensor, negative: torch.Tensor, latent_image: Dict[str, torch.Tensor],
            denoise: float = 1.0, enable_multiscale: bool = True, noise: Optional[torch.Tensor] = None,
-           callback: Optional[Callable] = None) -> Tuple[Dict[str, torch.Tensor]]:
+           callback: Optional[Callable] = None, noise_sampler: Optional[Callable] = None) -> Tuple[Dict[str, torch.Tensor]]:
     """Drop-in for KSampler.sample on the measured path. positive / negative: [1 or B, 77k, 768] conditioning tensors.
     Returns ({"samples": latents / 0.18215 on the CPU},) like the reference node."""
     if sampler_name not in SAMPLERS:
@@ -156,7 +234,10 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
     engine.set_context(ctx)
     if sampler_name == "dpmpp_2m_cfgpp":
         x = sample_dpmpp_2m_cfgpp(engine, x, sigmas, cfg, enable_multiscale=enable_multiscale, callback=callback)
+    elif sampler_name == "dpmpp_sde_cfgpp":
+        x = sample_dpmpp_sde_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, seed=seed,
+                                   enable_multiscale=enable_multiscale, callback=callback)
     else:
-        x = sample_euler_ancestral_cfgpp(engine, x, sigmas, cfg, callback=callback)
+        x = sample_euler_ancestral_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, callback=callback)
     out = (x / LATENT_SCALE).to(torch.float32).cpu()
     return ({"samples": out},)
