@@ -325,13 +325,11 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   static const int poly_mod = getenv("LDN_ATTN_POLY") ? atoi(getenv("LDN_ATTN_POLY")) : 3;  // 37.5 % of the ex2 on the FMA pipes (measured best)
   p.poly_mod = poly_mod;
   if (a.d == 40 && p.vt_head_stride == 48) {
-    // ones-row V^T: generation 3 (default). Generation 4 (two threads per row, 16 softmax warps) measured slower
-    // (2.21 ms vs 1.92 ms at N = 16384) and is kept only as a documented experiment (LDN_ATTN_V4=1).
-    static const bool use_v4 = getenv("LDN_ATTN_V4") != nullptr;
+    // ones-row V^T. (An experiment with two softmax threads per row / 16 softmax warps measured slower -- 2.21 ms vs
+    // 1.92 ms at N = 16384 -- and was dropped: the limiter was MMA issue, not softmax latency.)
     static const bool use_v3 = getenv("LDN_ATTN_V3") != nullptr;
     // default: generation 5 (generation 3 + P kept in tensor memory, TS-form P*V)
-    if (use_v4) finish_attn4_plan(plan, a.Nq, a.Nk, a.heads, a.B);
-    else if (use_v3) finish_attn3_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+    if (use_v3) finish_attn3_plan(plan, a.Nq, a.Nk, a.heads, a.B);
     else finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   } else {
     LDN_CHECK(p.vt_head_stride == a.d, "attention: vt_head_stride is only supported as 48 for d = 40");
@@ -353,7 +351,6 @@ static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 
 void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
   if (plan.p.variant == 5) return launch_attn5(plan, stream);
-  if (plan.p.variant == 4) return launch_attn4(plan, stream);
   if (plan.p.variant == 3) return launch_attn3(plan, stream);
   if (plan.p.variant == 2) return launch_attn2(plan, stream);
   switch (plan.p.dv) {

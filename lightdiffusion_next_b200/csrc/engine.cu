@@ -236,6 +236,7 @@ int ldn_groupnorm_bf16(const void* x0, int C0, const void* x1, int C1, int B, in
   if (ws_b < B) {
     if (ws) cudaFree(ws);
     LDN_CUDA(cudaMalloc(&ws, groupnorm_ws_bytes(B)));
+    LDN_CUDA(cudaMemset(ws, 0, groupnorm_ws_bytes(B)));
     ws_b = B;
   }
   launch_groupnorm((const bf16*)x0, C0, (const bf16*)x1, C1, B, HW, groups, eps, gamma, beta, silu != 0, (bf16*)out, ws,

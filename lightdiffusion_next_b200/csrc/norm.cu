@@ -16,11 +16,12 @@ namespace ldn {
 // Kernel 1, grid (splits, B), block (C/8)*R threads: every thread owns 8 consecutive channels for a strided set of
 // pixels, folds them into at most two (group, sum, sumsq) partials in shared memory, then warp g reduces the partials of
 // group g in a fixed order and writes one double2 per (batch, split, group).
-// Kernel 2, grid B, 1024 threads: warp g sums the split partials in a fixed order -> (mean, rstd).
+// The last block to arrive for a batch row (arrival counter) sums the split partials in a fixed order -> (mean, rstd).
 #define LDN_GN_MAX_SPLITS 1024
 
 __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
-                                int cpg, int rows_per_block, double2* __restrict__ partial) {
+                                int cpg, int rows_per_block, double2* __restrict__ partial, unsigned int* __restrict__ counters,
+                                float eps, float2* __restrict__ mean_rstd) {
   const int C = C0 + C1;
   const int nvec = C >> 3;
   const int R = blockDim.x / nvec;
@@ -119,27 +120,37 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16*
     }
     if (lane == 0) partial[((size_t)b * gridDim.x + blockIdx.x) * 32 + g] = make_double2(sum, sq);
   }
-}
-
-__global__ void gn_finalize_kernel(const double2* __restrict__ partial, int splits, double n, float eps,
-                                   float2* __restrict__ mean_rstd) {
-  const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double sum = 0.0, sq = 0.0;
-  for (int s = lane; s < splits; s += 32) {
-    const double2 v = partial[((size_t)b * splits + s) * 32 + g];
-    sum += v.x;
-    sq += v.y;
-  }
+  // The last block to finish for this batch row folds the split partials into (mean, rstd) -- in a fixed order, so the
+  // result does not depend on which block happens to be last (deterministic) -- and re-arms the counter.
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[b], 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int splits = gridDim.x;
+    const double n = (double)HW * cpg;
+    for (int g = warp; g < 32; g += nwarps) {
+      double sum = 0.0, sq = 0.0;
+      for (int sp = lane; sp < splits; sp += 32) {
+        const double2 v = __ldcg(&partial[((size_t)b * splits + sp) * 32 + g]);
+        sum += v.x;
+        sq += v.y;
+      }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  }
-  if (lane == 0) {
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;
-    if (var < 0) var = 0;
-    mean_rstd[b * 32 + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+      for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      if (lane == 0) {
+        const double mean = sum / n;
+        double var = sq / n - mean * mean;
+        if (var < 0) var = 0;
+        mean_rstd[b * 32 + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+      }
+    }
+    if (threadIdx.x == 0) counters[b] = 0;
   }
 }
 
@@ -200,6 +211,7 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   // workspace: [B][splits][32] double2 partials, then [B][32] float2 (mean, rstd)
   double2* partial = reinterpret_cast<double2*>(stats_ws);
   float2* mean_rstd = reinterpret_cast<float2*>(partial + (size_t)B * LDN_GN_MAX_SPLITS * 32);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(mean_rstd + (size_t)B * 32);  // zero-initialised workspace
   const int nvec = C / 8;
   int R = 1024 / nvec;
   if (R > 16) R = 16;
@@ -210,9 +222,8 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   if (rows_per_block < R) rows_per_block = R;
   splits = (HW + rows_per_block - 1) / rows_per_block;
   LDN_CHECK(splits <= LDN_GN_MAX_SPLITS, "groupnorm: too many splits");
-  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, partial);
-  LDN_CUDA(cudaGetLastError());
-  gn_finalize_kernel<<<B, 1024, 0, stream>>>(partial, splits, (double)HW * cpg, eps, mean_rstd);
+  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, partial, counters,
+                                                           eps, mean_rstd);
   LDN_CUDA(cudaGetLastError());
   int rpb2 = (HW + splits - 1) / splits;
   const size_t smem = sizeof(float) * 2 * C;

@@ -600,7 +600,7 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
       bd.sQK[nlev - 1] = A.get<bf16>((size_t)B * h * w * 2 * U.heads * slot_of(c / U.heads), true);
     }
   }
-  bd.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B)));
+  bd.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B), true));
   bd.temb = A.get<float>((size_t)B * U.model_ch);
   bd.emb1 = A.get<float>((size_t)B * U.temb_dim);
   bd.emb = A.get<float>((size_t)B * U.temb_dim);

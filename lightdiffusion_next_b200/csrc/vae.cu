@@ -125,7 +125,7 @@ static Program* build_vae_program(ldn_engine* e, int B, int h, int w) {
   vb.sA = A.get<bf16>(max_act);
   vb.sB = A.get<bf16>(max_act);
   vb.sC = A.get<bf16>(max_act);
-  vb.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B)));
+  vb.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B), true));
   prog->io_elems = (size_t)B * V.zc * h * w;
   prog->in_x = A.get<float>(prog->io_elems);
   float* zq = A.get<float>(prog->io_elems);
