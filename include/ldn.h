@@ -90,8 +90,9 @@ int ldn_gemm_bf16(const void* A0, int64_t lda0, int K0, const void* A1, int64_t 
 int ldn_conv3x3_bf16(const void* x, const void* Wt, int B, int H, int W, int Cin, int Cout, const float* bias,
                      const float* rowbias, int ld_rowbias, const void* residual, void* out, void* stream);
 /* Q: [B*Nq, heads*slot], K: [B*nk_pad, heads*slot], Vt: [vt_rows, B*nk_pad] (all bf16); out: [B*Nq, heads*d].
- * vt_head_stride: rows per head in Vt; 0 or d = plain V^T. For d = 40, 48 selects the fastest kernel and requires
- * row 40 of every head to be all ones (rows 41..47 zero): the softmax row sum is then computed by the tensor core. */
+ * vt_head_stride: rows per head in Vt; 0 or d = plain V^T. For d = 40 (stride 48) and d = 80 (stride 96) the padded
+ * layout selects the fastest kernels and requires row d of every head to be all ones (remaining pad rows zero): the
+ * softmax row sum is then computed by the tensor core. */
 int ldn_attention_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* Vt, int64_t ldvt,
                        int64_t vt_rows, int vt_head_stride, int B, int heads, int Nq, int Nk, int nk_pad, int d,
                        int slot, int causal, float scale, void* out, int64_t ldo, void* stream);

@@ -301,7 +301,7 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   p.ldo = a.ldo;
   p.tmQ = make_tmap_2d(a.Q, (uint64_t)a.B * a.Nq, (uint64_t)a.heads * a.slot, a.ldq, 128);
   p.tmK = make_tmap_2d(a.K, (uint64_t)a.B * p.k_batch_stride, (uint64_t)a.heads * a.slot, a.ldk, 128);
-  p.tmVt = make_tmap_2d(a.Vt, (uint64_t)a.vt_rows, (uint64_t)a.B * a.nk_pad, a.ldvt, dp);
+  p.tmVt = make_tmap_2d(a.Vt, (uint64_t)a.vt_rows, (uint64_t)a.B * a.nk_pad, a.ldvt, a.vt_head_stride > 0 ? a.vt_head_stride : dp);
   const int nqk_atoms = (dp + 63) / 64;
   const int q_bytes = nqk_atoms * 16384;
   const int stage_bytes = q_bytes + 2 * dp * 128;
@@ -331,8 +331,10 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
     // default: generation 5 (generation 3 + P kept in tensor memory, TS-form P*V)
     if (use_v3) finish_attn3_plan(plan, a.Nq, a.Nk, a.heads, a.B);
     else finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+  } else if (a.d == 80 && p.vt_head_stride == 96 && !a.causal) {
+    finish_attn6_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // generation 6: ones-row V^T, P aliased over S in TMEM
   } else {
-    LDN_CHECK(p.vt_head_stride == a.d, "attention: vt_head_stride is only supported as 48 for d = 40");
+    LDN_CHECK(p.vt_head_stride == a.d, "attention: vt_head_stride is only supported as 48 (d = 40) or 96 (d = 80)");
     if (dp <= 64 && !force_v1) finish_attn2_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   }
   return plan;
@@ -350,6 +352,7 @@ static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 }
 
 void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
+  if (plan.p.variant == 6) return launch_attn6(plan, stream);
   if (plan.p.variant == 5) return launch_attn5(plan, stream);
   if (plan.p.variant == 3) return launch_attn3(plan, stream);
   if (plan.p.variant == 2) return launch_attn2(plan, stream);

@@ -7,6 +7,7 @@
 // generic->async proxy fence; the freed 64 KB of shared memory deepen the K / V^T ring.
 #include "common.h"
 #include "ptx.cuh"
+#include "attn_softmax.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -20,33 +21,7 @@ static constexpr int kK3 = 128;
 static constexpr int kDV3 = 48;
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
-__device__ __forceinline__ float ex2m(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2p(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;
-  const float n = t - 12582912.0f;
-  const float f = x - n;
-  float p = fmaf(f, 0.0555041086f, 0.2402265070f);
-  p = fmaf(p, f, 0.6931471806f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-__device__ __forceinline__ uint32_t pin3(uint32_t v) {
-  asm volatile("mov.u32 %0, %0;" : "+r"(v));
-  return v;
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+using namespace asm_sm;
 
 template <uint32_t kPolyMask>
 __global__ void __launch_bounds__(kA3Threads, 1) attn5_tc_kernel(const __grid_constant__ AttnParams p) {
@@ -274,48 +249,19 @@ __global__ void __launch_bounds__(kA3Threads, 1) attn5_tc_kernel(const __grid_co
       // MMA has long finished -- and the deferred stores go out together with the second half.
       uint32_t pk[8][4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = fmaf(__uint_as_float(sv[c * 8 + i]), sc, -m_off);
-        if (kPolyMask == 0x10000u) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = e[i] * 0.001f;  // EXPERIMENT ONLY: no exponential
-        } else if ((kPolyMask >> c) & 1u) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2p(e[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2m(e[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pk[c][i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-      }
+      for (int c = 0; c < 8; ++c)
+        exp8_pack(sv + c * 8, sc, -m_off, kPolyMask == 0x10000u ? 2 : (int)((kPolyMask >> c) & 1u), pk[c]);
       if (j >= 1) mbar_wait(my_pv_done, (uint32_t)(j - 1) & 1u);  // P*V of the previous tile has consumed P
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        uint32_t w0, w1, w2, w3;
+        uint32_t w[4];
         if (c < 8) {
-          w0 = pk[c][0]; w1 = pk[c][1]; w2 = pk[c][2]; w3 = pk[c][3];
+          w[0] = pk[c][0]; w[1] = pk[c][1]; w[2] = pk[c][2]; w[3] = pk[c][3];
         } else {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = fmaf(__uint_as_float(sv[c * 8 + i]), sc, -m_off);
-          if (kPolyMask == 0x10000u) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = e[i] * 0.001f;  // EXPERIMENT ONLY
-          } else if ((kPolyMask >> c) & 1u) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = ex2p(e[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = ex2m(e[i]);
-          }
-          w0 = pack_bf16x2(e[0], e[1]); w1 = pack_bf16x2(e[2], e[3]);
-          w2 = pack_bf16x2(e[4], e[5]); w3 = pack_bf16x2(e[6], e[7]);
+          exp8_pack(sv + c * 8, sc, -m_off, kPolyMask == 0x10000u ? 2 : (int)((kPolyMask >> c) & 1u), w);
         }
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tmem_p + (uint32_t)(c * 4)), "r"(w0),
-                     "r"(w1), "r"(w2), "r"(w3)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tmem_p + (uint32_t)(c * 4)), "r"(w[0]),
+                     "r"(w[1]), "r"(w[2]), "r"(w[3])
                      : "memory");
       }
       if (p.pingpong && !(t == 1 && j == n_tiles - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(1 + (t ^ 1)) : "memory");

@@ -150,7 +150,7 @@ struct AttnArgs {
   long long vt_rows;
   int B, heads, Nq, Nk, nk_pad, d, slot;
   int kv_batch_stride = 0;  // K rows per batch (0 = nk_pad)
-  int vt_head_stride = 0;   // rows per head in Vt (0 = d). d = 40 with stride 48: row 40 of every head must be all ones
+  int vt_head_stride = 0;   // rows per head in Vt (0 = d). d = 40 with stride 48 / d = 80 with stride 96: row d of every head must be all ones
   int causal = 0;
   float scale;
   bf16* out;
@@ -163,6 +163,8 @@ void finish_attn3_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn3(const AttnPlan& plan, cudaStream_t stream);
 void finish_attn5_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn5(const AttnPlan& plan, cudaStream_t stream);
+void finish_attn6_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
+void launch_attn6(const AttnPlan& plan, cudaStream_t stream);
 void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)

@@ -50,6 +50,26 @@ void run_program(Program& prog, bool use_graph, cudaStream_t stream) {
   if (!prog.warmed || !use_graph) {
     static const bool debug_sync = getenv("LDN_DEBUG_SYNC") != nullptr;
     static const bool debug_hash_on = getenv("LDN_DEBUG_HASH") != nullptr;
+    static const bool profile_on = getenv("LDN_PROFILE") != nullptr;
+    if (profile_on && prog.warmed) {
+      // Per-step device timing (eager mode only): one CUDA event pair per step, printed as "LDNPROF idx ms name".
+      std::vector<cudaEvent_t> ev(prog.steps.size() + 1);
+      for (auto& e : ev) cudaEventCreate(&e);
+      cudaEventRecord(ev[0], stream);
+      for (size_t i = 0; i < prog.steps.size(); ++i) {
+        prog.steps[i](stream);
+        cudaEventRecord(ev[i + 1], stream);
+      }
+      LDN_CUDA(cudaStreamSynchronize(stream));
+      for (size_t i = 0; i < prog.steps.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        printf("LDNPROF %zu %.4f %s\n", i, ms, prog.names[i].c_str());
+      }
+      fflush(stdout);
+      for (auto& e : ev) cudaEventDestroy(e);
+      return;
+    }
     for (size_t i = 0; i < prog.steps.size(); ++i) {
       prog.steps[i](stream);
       if (debug_hash_on && prog.arena) debug_hash(prog, i, stream);

@@ -354,7 +354,7 @@ struct Builder {
   bf16 *sA = nullptr, *sB = nullptr, *sC = nullptr, *sO = nullptr, *sG = nullptr, *sVt = nullptr, *sCol = nullptr;
   bf16* sVtPad = nullptr;  // zero-initialised, only used for levels whose token count is not a multiple of 8
   std::vector<bf16*> sQK;  // per level
-  std::vector<bf16*> sVt40;  // per level: [heads*48, Tld] V^T with a ones row per head (head dim 40 only)
+  std::vector<bf16*> sVt40;  // per level: [heads*48|96, Tld] V^T with a ones row per head (head dims 40 / 80)
   size_t vt_pad_elems = 0;
   float* splitk_ws = nullptr;
   size_t splitk_ws_bytes = 0;
@@ -371,7 +371,10 @@ struct Builder {
     a.splitk_ws = splitk_ws;
     a.splitk_ws_bytes = splitk_ws_bytes;
     GemmPlan plan = make_gemm_plan(a);
-    add(name, [plan](cudaStream_t st) { launch_gemm(plan, st); });
+    const long long Mm = a.conv ? (long long)a.B * a.H * a.W : a.M;
+    const long long Kk = a.conv ? 9LL * a.Cin : (long long)a.K0 + a.K1;
+    add(name + " [M=" + std::to_string(Mm) + " N=" + std::to_string(a.N) + " K=" + std::to_string(Kk) + "]",
+        [plan](cudaStream_t st) { launch_gemm(plan, st); });
   }
   void groupnorm(const std::string& name, const bf16* x0, int C0, const bf16* x1, int C1, int HW, float eps,
                  const std::string& wprefix, bool silu, bf16* out) {
@@ -453,17 +456,18 @@ struct Builder {
       a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = s.Wqk; a.M = T; a.N = 2 * C;
       a.out = QK; a.ldo = ldqk; a.head_dim = s.d; a.head_slot = s.slot;
       gemm(tb + ".attn1.qk", a);
-      const bool ones = (s.d == 40);  // attention3: 48 rows per head, row 40 = ones
+      const bool ones = sVt40[level] != nullptr;  // V^T with a ones row per head: 48 (d = 40) / 96 (d = 80) rows
+      const int hs = s.d == 40 ? 48 : 96;
       bf16* Vt = ones ? sVt40[level] : sVt;
       GemmArgs v;
       v.A0 = e->W(0, tb + ".attn1.to_v.weight").b(); v.lda0 = C; v.K0 = C; v.Wt = sA; v.M = C; v.N = Tld; v.wt_rows = T;
       v.out = Vt; v.ldo = Tld;
-      if (ones) { v.row_head_dim = 40; v.row_head_slot = 48; }
+      if (ones) { v.row_head_dim = s.d; v.row_head_slot = hs; }
       gemm(tb + ".attn1.vt", v);
       AttnArgs at;
       at.Q = QK; at.ldq = ldqk; at.K = QK + (size_t)U.heads * s.slot; at.ldk = ldqk;
-      at.Vt = Vt; at.ldvt = Tld; at.vt_rows = ones ? U.heads * 48 : C;
-      at.vt_head_stride = ones ? 48 : 0;
+      at.Vt = Vt; at.ldvt = Tld; at.vt_rows = ones ? U.heads * hs : C;
+      at.vt_head_stride = ones ? hs : 0;
       at.B = B; at.heads = U.heads; at.Nq = N; at.Nk = N; at.nk_pad = N; at.d = s.d; at.slot = s.slot;
       if (N % 8 != 0) {
         LDN_CHECK(!ones, "head-dim-40 level with a token count that is not a multiple of 8");
@@ -581,10 +585,12 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
       const int slot = slot_of(c / U.heads);
       bd.sQK.push_back(U.attn_level[level] ? A.get<bf16>((size_t)B * h * w * 2 * U.heads * slot, true) : nullptr);
       bf16* vt40 = nullptr;
-      if (U.attn_level[level] && c / U.heads == 40) {
+      const int dh = c / U.heads;
+      if (U.attn_level[level] && (dh == 40 || dh == 80) && (h * w) % 8 == 0) {
+        const int hs = dh == 40 ? 48 : 96;
         const long long tld = ((long long)B * h * w + 15) / 16 * 16;
-        vt40 = A.get<bf16>((size_t)U.heads * 48 * tld, true);
-        fill_ones_rows_kernel<<<64, 256>>>(vt40, U.heads, tld, 48, 40);
+        vt40 = A.get<bf16>((size_t)U.heads * hs * tld, true);
+        fill_ones_rows_kernel<<<64, 256>>>(vt40, U.heads, tld, hs, dh);
         LDN_CUDA(cudaGetLastError());
         LDN_CUDA(cudaDeviceSynchronize());
       }

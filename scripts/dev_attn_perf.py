@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lightdiffusion_next_b200 import _lib as L
 lib = L.load(); torch.manual_seed(0); dev = "cuda"
 def attn(B, H, Nq, Nk, d, causal=False, ones=False):
-    hs = 48 if ones else d
+    hs = {40: 48, 80: 96}[d] if ones else d
     slot = (d + 63) // 64 * 64
     nk_pad = (Nk + 127) // 128 * 128 if Nk % 8 else Nk
     q = torch.randn(B, H, Nq, d, device=dev).bfloat16(); k = torch.randn(B, H, Nk, d, device=dev).bfloat16(); v = torch.randn(B, H, Nk, d, device=dev).bfloat16()
@@ -25,6 +25,11 @@ def attn(B, H, Nq, Nk, d, causal=False, ones=False):
     ms = e0.elapsed_time(e1) / 10
     print(f"attn ones={ones} B={B} H={H} Nq={Nq} Nk={Nk} d={d} causal={causal}: rel={rel:.3e}  {ms:.3f} ms {4*B*H*Nq*Nk*d/ms/1e9:.1f} TFLOP/s", flush=True)
 print("env", {k: v for k, v in os.environ.items() if k.startswith("LDN_")})
+attn(2, 8, 4096, 4096, 80, ones=True)
+attn(2, 8, 4096, 4096, 80)
+attn(2, 8, 1000, 1000, 80, ones=True)
+attn(2, 8, 16384, 16384, 80, ones=True)
+attn(1, 3, 300, 77, 80, ones=True)
 attn(2, 8, 16384, 16384, 40, ones=True)
 attn(2, 8, 4096, 4096, 40, ones=True)
 attn(2, 8, 16384, 77, 40, ones=True)

@@ -108,13 +108,17 @@ def test_conv3x3(lib, B, H, W, Cin, Cout):
                                                      # tensor core, O resident in TMEM, lazy rescale)
                                                      (2, 8, 1024, 1024, 40, False, True), (2, 8, 1024, 77, 40, False, True),
                                                      (1, 8, 4096, 4096, 40, False, True), (2, 8, 64, 64, 40, False, True),
-                                                     (2, 8, 4096, 154, 40, False, True), (1, 2, 200, 1000, 40, False, True)])
+                                                     (2, 8, 4096, 154, 40, False, True), (1, 2, 200, 1000, 40, False, True),
+                                                     # head dim 80, ones-row V^T with 96 rows per head (attention6.cu: P aliased over S in TMEM)
+                                                     (2, 8, 1024, 1024, 80, False, True), (1, 8, 4096, 4096, 80, False, True),
+                                                     (2, 8, 256, 77, 80, False, True), (1, 2, 200, 1000, 80, False, True),
+                                                     (2, 3, 64, 64, 80, False, True)])
 def test_attention(lib, B, H, Nq, Nk, d, causal, ones):
     L, l = lib
     torch.manual_seed(Nq + Nk + d)
     slot = (d + 63) // 64 * 64
     nk_pad = (Nk + 127) // 128 * 128 if Nk % 8 else Nk
-    hs = 48 if ones else d
+    hs = {40: 48, 80: 96}[d] if ones else d
     q = torch.randn(B, H, Nq, d, device="cuda").bfloat16()
     k = torch.randn(B, H, Nk, d, device="cuda").bfloat16()
     v = torch.randn(B, H, Nk, d, device="cuda").bfloat16()
