@@ -189,6 +189,8 @@ void launch_scale_in(const float* x, const float* sigma, int B, int C, int H, in
 void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const float* bias, int B, int H, int W,
                     int Cin, int Cout, bf16* out, cudaStream_t stream);
 // conv_out: 3x3 Cin -> 4 on NHWC bf16 input; writes denoised = x - eps*sigma (NCHW fp32) and optionally eps
+void launch_conv_out_finish(const float* acc16, const float* bias, const float* x, const float* sigma, int B, int HW,
+                            int cout, float* denoised, cudaStream_t stream);
 void launch_conv_out(const bf16* h, const bf16* Wt, const float* bias, const float* x, const float* sigma, int B,
                      int H, int W, int Cin, int Cout, float* denoised, float* eps_out, cudaStream_t stream);
 void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);

@@ -63,49 +63,75 @@ void launch_timestep_embed(const float* sigma, int Bn, const float* log_sigmas, 
   LDN_CUDA(cudaGetLastError());
 }
 
-// ------------------------------------------------------------------ tiny-M linear: one warp per output feature
+// ------------------------------------------------------------------ tiny-M linear (time-embedding MLP, the 22 emb_layers)
+// HBM-bound on the weight matrix: the (optionally SiLU'd) activations are staged once per block in shared memory and every
+// warp streams whole weight rows with all of a row's 16-byte loads in flight before the first use.
+template <int KV>  // 16-byte weight vectors per lane and row: K <= 256 * KV
 __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, const bf16* __restrict__ W,
                                     const float* __restrict__ bias, int N, int silu_in, int silu_out,
                                     float* __restrict__ out) {
-  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  extern __shared__ float s_x[];  // [8][K]
   const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  const bf16* w = W + (size_t)n * K;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
   for (int b0 = 0; b0 < Bn; b0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-    for (int k = lane * 8; k < K; k += 256) {
-      const uint4 u = *reinterpret_cast<const uint4*>(w + k);
-      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-      float wf[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        wf[2 * i] = bf16_lo(ww[i]);
-        wf[2 * i + 1] = bf16_hi(ww[i]);
+    const int nb = min(8, Bn - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+      const int r = i / K;
+      float v = 0.f;
+      if (r < nb) {
+        v = x[(size_t)(b0 + r) * K + (i - r * K)];
+        if (silu_in) v = silu_p(v);
       }
+      s_x[i] = v;
+    }
+    __syncthreads();
+    for (int n = blockIdx.x * warps + warp; n < N; n += gridDim.x * warps) {
+      const bf16* w = W + (size_t)n * K;
+      uint4 u[KV];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (b0 + r < Bn) {
-          const float* xr = x + (size_t)(b0 + r) * K + k;
+      for (int j = 0; j < KV; ++j) {
+        const int k = lane * 8 + j * 256;
+        u[j] = (k < K) ? __ldg(reinterpret_cast<const uint4*>(w + k)) : make_uint4(0, 0, 0, 0);
+      }
+      float acc[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float xv = xr[i];
-            if (silu_in) xv = silu_p(xv);
-            acc[r] = fmaf(xv, wf[i], acc[r]);
+      for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll
+      for (int j = 0; j < KV; ++j) {
+        const int k = lane * 8 + j * 256;
+        if (k < K) {
+          const uint32_t ww[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+          float wf[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            wf[2 * i] = bf16_lo(ww[i]);
+            wf[2 * i + 1] = bf16_hi(ww[i]);
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (r < nb) {
+              const float4 x0 = *reinterpret_cast<const float4*>(s_x + r * K + k);
+              const float4 x1 = *reinterpret_cast<const float4*>(s_x + r * K + k + 4);
+              acc[r] = fmaf(x0.x, wf[0], acc[r]); acc[r] = fmaf(x0.y, wf[1], acc[r]);
+              acc[r] = fmaf(x0.z, wf[2], acc[r]); acc[r] = fmaf(x0.w, wf[3], acc[r]);
+              acc[r] = fmaf(x1.x, wf[4], acc[r]); acc[r] = fmaf(x1.y, wf[5], acc[r]);
+              acc[r] = fmaf(x1.z, wf[6], acc[r]); acc[r] = fmaf(x1.w, wf[7], acc[r]);
+            }
           }
         }
       }
-    }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float v = acc[r];
+      for (int r = 0; r < 8; ++r) {
+        float v = acc[r];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && b0 + r < Bn) {
-        v += bias ? bias[n] : 0.f;
-        if (silu_out) v = silu_p(v);
-        out[(size_t)(b0 + r) * N + n] = v;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && r < nb) {
+          v += bias ? bias[n] : 0.f;
+          if (silu_out) v = silu_p(v);
+          out[(size_t)(b0 + r) * N + n] = v;
+        }
       }
     }
   }
@@ -113,62 +139,94 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, 
 
 void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
                          bool silu_out, float* out, cudaStream_t stream) {
-  LDN_CHECK(K % 8 == 0, "small_linear: K must be a multiple of 8");
-  const int threads = 256;
-  const int blocks = (N * 32 + threads - 1) / threads;
-  small_linear_kernel<<<blocks, threads, 0, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out);
+  LDN_CHECK(K % 8 == 0 && K <= 2048, "small_linear: K must be a multiple of 8 and at most 2048");
+  const int threads = 256, warps = threads / 32;
+  int blocks = (N + warps - 1) / warps;
+  if (blocks > 148 * 5) blocks = 148 * 5;
+  const size_t smem = sizeof(float) * 8 * K;
+  static bool attr = false;
+  if (!attr) {
+    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  if (K <= 512)
+    small_linear_kernel<2><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out);
+  else if (K <= 1280)
+    small_linear_kernel<5><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out);
+  else
+    small_linear_kernel<8><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out);
   LDN_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------ conv_in: 3x3, tiny Cin, NCHW fp32 -> NHWC bf16
 // Fuses BaseModel.apply_model's input scaling x / sqrt(sigma^2 + 1) (src/sample/sampling.py:29-40).
-// Wt: [Cout, 3, 3, Cin] bf16. thread = (pixel, 8 output channels).
+// Wt: [Cout, 3, 3, Cin] bf16. thread = (4 consecutive pixels of a row, 8 output channels): every weight vector fetched
+// from shared memory feeds 32 FMAs (the one-pixel version sat on the shared-memory bandwidth).
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                const bf16* __restrict__ Wt, const float* __restrict__ bias, int B, int H, int W, int Cin,
                                int Cout, bf16* __restrict__ out) {
   extern __shared__ float s_w[];  // transposed: [9*Cin][Cout] so the 8 output channels of a thread are contiguous
   const int K = 9 * Cin;
-  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) {
-    const int o = i / K, k = i - o * K;
-    s_w[k * Cout + o] = __bfloat162float(Wt[i]);
+  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) {  // consecutive threads -> consecutive o: conflict-free
+    const int k = i / Cout, o = i - k * Cout;
+    s_w[i] = __bfloat162float(Wt[(size_t)o * K + k]);
   }
   __syncthreads();
   const int groups = Cout / 8;
-  const size_t total = (size_t)B * H * W * groups;
+  const int wq = (W + 3) / 4;  // pixel quads per row
+  const size_t total = (size_t)B * H * wq * groups;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int g = (int)(idx % groups);
-    const size_t pix = idx / groups;
-    const int xw = (int)(pix % W);
-    const int y = (int)((pix / W) % H);
-    const int b = (int)(pix / ((size_t)W * H));
+    const size_t quad = idx / groups;
+    const int x0 = (int)(quad % wq) * 4;
+    const int y = (int)((quad / wq) % H);
+    const int b = (int)(quad / ((size_t)wq * H));
     const float sg = sigma ? sigma[b] : 0.f;
     const float scale = sigma ? rsqrtf(sg * sg + 1.f) : 1.f;
-    float acc[8];
+    float acc[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = bias ? bias[g * 8 + i] : 0.f;
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[px][i] = bias ? bias[g * 8 + i] : 0.f;
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = y + ky - 1;
       if (yy < 0 || yy >= H) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = xw + kx - 1;
-        if (xx < 0 || xx >= W) continue;
-        for (int c = 0; c < Cin; ++c) {
-          const float v = x[(((size_t)b * Cin + c) * H + yy) * W + xx] * scale;
+      for (int c = 0; c < Cin; ++c) {
+        const float* row = x + (((size_t)b * Cin + c) * H + yy) * W;
+        float in[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int xx = x0 + i - 1;
+          in[i] = (xx >= 0 && xx < W) ? row[xx] * scale : 0.f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
           const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * Cin + c) * Cout + g * 8);
           const float4 w0 = wr[0], w1 = wr[1];
-          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const float v = in[px + kx];
+            acc[px][0] = fmaf(v, w0.x, acc[px][0]); acc[px][1] = fmaf(v, w0.y, acc[px][1]);
+            acc[px][2] = fmaf(v, w0.z, acc[px][2]); acc[px][3] = fmaf(v, w0.w, acc[px][3]);
+            acc[px][4] = fmaf(v, w1.x, acc[px][4]); acc[px][5] = fmaf(v, w1.y, acc[px][5]);
+            acc[px][6] = fmaf(v, w1.z, acc[px][6]); acc[px][7] = fmaf(v, w1.w, acc[px][7]);
+          }
         }
       }
     }
-    uint4 ov;
-    ov.x = pack_bf16x2(acc[0], acc[1]);
-    ov.y = pack_bf16x2(acc[2], acc[3]);
-    ov.z = pack_bf16x2(acc[4], acc[5]);
-    ov.w = pack_bf16x2(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(out + pix * Cout + g * 8) = ov;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      if (x0 + px < W) {
+        uint4 ov;
+        ov.x = pack_bf16x2(acc[px][0], acc[px][1]);
+        ov.y = pack_bf16x2(acc[px][2], acc[px][3]);
+        ov.z = pack_bf16x2(acc[px][4], acc[px][5]);
+        ov.w = pack_bf16x2(acc[px][6], acc[px][7]);
+        *reinterpret_cast<uint4*>(out + (((size_t)b * H + y) * W + x0 + px) * Cout + g * 8) = ov;
+      }
+    }
   }
 }
 
@@ -182,9 +240,9 @@ void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const fl
     LDN_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  const size_t total = (size_t)B * H * W * (Cout / 8);
+  const size_t total = (size_t)B * H * ((W + 3) / 4) * (Cout / 8);
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;
   conv_in_kernel<<<blocks, 256, smem, stream>>>(x, sigma, Wt, bias, B, H, W, Cin, Cout, out);
   LDN_CUDA(cudaGetLastError());
 }
@@ -278,6 +336,30 @@ void launch_conv_out(const bf16* h, const bf16* Wt, const float* bias, const flo
   } else {
     LDN_CHECK(false, "conv_out: only Cout 3 or 4");
   }
+  LDN_CUDA(cudaGetLastError());
+}
+
+// Second half of the UNet output head when the 3x3 conv itself runs on the tensor cores (implicit GEMM, Cout padded to 16
+// columns, fp32 [pixels, 16] scratch): eps = acc + bias; denoised = x - eps * sigma (EPS.calculate_denoised,
+// src/sample/sampling.py:42-56), written as NCHW fp32.
+__global__ void conv_out_finish_kernel(const float* __restrict__ acc16, const float* __restrict__ bias,
+                                       const float* __restrict__ x, const float* __restrict__ sigma, int B, int HW,
+                                       int cout, float* __restrict__ denoised) {
+  const size_t total = (size_t)B * cout * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const int o = (int)((i / HW) % cout);
+    const int b = (int)(i / ((size_t)HW * cout));
+    const float e = acc16[((size_t)b * HW + pix) * 16 + o] + (bias ? bias[o] : 0.f);
+    denoised[i] = x[i] - e * sigma[b];
+  }
+}
+void launch_conv_out_finish(const float* acc16, const float* bias, const float* x, const float* sigma, int B, int HW,
+                            int cout, float* denoised, cudaStream_t stream) {
+  const size_t total = (size_t)B * cout * HW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_out_finish_kernel<<<blocks, 256, 0, stream>>>(acc16, bias, x, sigma, B, HW, cout, denoised);
   LDN_CUDA(cudaGetLastError());
 }
 

@@ -724,16 +724,30 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
   // ---- head: GroupNorm + SiLU + conv3x3 -> eps; denoised = x - eps * sigma (fp32 NCHW)
   bd.groupnorm("out.gn", h, ch, nullptr, 0, H * W, 1e-5f, "out.0", true, bd.sA);
   {
-    const bf16* src = bd.sA;
-    const bf16* wt = e->W(0, "out.2.weight").b();
     const float* bias = e->W(0, "out.2.bias").f();
     const float* x = prog->in_x;
     const float* sig = prog->in_sigma;
     float* out = prog->out;
     const int cin = ch, cout = U.out_ch;
-    bd.add("conv_out", [=](cudaStream_t st) {
-      launch_conv_out(src, wt, bias, x, sig, B, H, W, cin, cout, out, nullptr, st);
-    });
+    if (cin % 64 == 0 && cout <= 16) {
+      // tensor-core path: implicit-GEMM conv with the 4 output channels padded to one 16-column MMA (weight rows past
+      // cout read as zero through the tensor map), fp32 accumulators to a [pixels, 16] scratch, then the fused
+      // bias / x - eps * sigma / NCHW pass
+      float* acc16 = A.get<float>((size_t)B * H * W * 16);
+      GemmArgs a;
+      a.conv = true; a.A0 = bd.sA; a.B = B; a.H = H; a.W = W; a.Cin = cin;
+      a.Wt = e->W(0, "out.2.weight").b(); a.N = 16; a.wt_rows = cout; a.BN = 16;
+      a.out_f32 = acc16; a.ldo = 16;
+      bd.gemm("out.conv", a);
+      const int HW = H * W;
+      bd.add("conv_out_finish", [=](cudaStream_t st) { launch_conv_out_finish(acc16, bias, x, sig, B, HW, cout, out, st); });
+    } else {
+      const bf16* src = bd.sA;
+      const bf16* wt = e->W(0, "out.2.weight").b();
+      bd.add("conv_out", [=](cudaStream_t st) {
+        launch_conv_out(src, wt, bias, x, sig, B, H, W, cin, cout, out, nullptr, st);
+      });
+    }
   }
   return prog.release();
 }
