@@ -20,17 +20,17 @@ namespace ldn {
 #define LDN_GN_MAX_SPLITS 1024
 
 __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
-                                int cpg, int rows_per_block, double2* __restrict__ partial, unsigned int* __restrict__ counters,
+                                int cpg, int rows_per_block, int R, double2* __restrict__ partial, unsigned int* __restrict__ counters,
                                 float eps, float2* __restrict__ mean_rstd) {
   const int C = C0 + C1;
   const int nvec = C >> 3;
-  const int R = blockDim.x / nvec;
+  const bool active = (int)threadIdx.x < nvec * R;  // the block is padded to whole warps
   const int cv = threadIdx.x % nvec;
   const int prow = threadIdx.x / nvec;
   const int b = blockIdx.y;
   __shared__ float s_part[1024][4];  // per thread: {sum_lo, sq_lo, sum_hi, sq_hi} for groups g_lo = c/cpg and g_lo+1
   const int c = cv * 8;
-  {
+  if (active) {
     const bf16* src;
     int ld;
     if (c < C0) {
@@ -154,50 +154,65 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16*
   }
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU)
-// grid: (pixel chunks, B); dynamic smem: 2*C floats (per-channel scale / shift)
+// Same thread layout as the statistics kernel: grid (splits, B), block (C/8)*R threads; a thread owns 8 consecutive
+// channels (scale / shift held in registers) and walks a strided set of pixels with four 16-byte loads in flight.
 __global__ void gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
-                                int cpg, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                int silu, const float2* __restrict__ mean_rstd, bf16* __restrict__ out,
-                                int rows_per_block) {
-  extern __shared__ float s_ab[];
+                                int cpg, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                const float2* __restrict__ mean_rstd, bf16* __restrict__ out, int rows_per_block,
+                                int R) {
   const int C = C0 + C1;
-  float* s_a = s_ab;
-  float* s_b = s_ab + C;
-  const int b = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float2 mr = mean_rstd[b * 32 + c / cpg];
-    const float a = mr.y * gamma[c];
-    s_a[c] = a;
-    s_b[c] = beta[c] - mr.x * a;
-  }
-  __syncthreads();
   const int nvec = C >> 3;
+  if ((int)threadIdx.x >= nvec * R) return;  // the block is padded to whole warps
+  const int cv = threadIdx.x % nvec;
+  const int prow = threadIdx.x / nvec;
+  const int b = blockIdx.y;
+  const int c = cv * 8;
+  float a[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 mr = mean_rstd[b * 32 + (c + i) / cpg];
+    a[i] = mr.y * gamma[c + i];
+    sh[i] = beta[c + i] - mr.x * a[i];
+  }
+  const bf16* src;
+  int ld;
+  if (c < C0) {
+    src = x0 + (size_t)b * HW * C0 + c;
+    ld = C0;
+  } else {
+    src = x1 + (size_t)b * HW * C1 + (c - C0);
+    ld = C1;
+  }
+  bf16* dst = out + (size_t)b * HW * C + c;
   const int p_begin = blockIdx.x * rows_per_block;
   const int p_end = min(HW, p_begin + rows_per_block);
-  const int total = (p_end - p_begin) * nvec;
-#pragma unroll 2
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int pix = p_begin + idx / nvec;
-    const int c = (idx % nvec) * 8;
-    const bf16* src = (c < C0) ? x0 + ((size_t)b * HW + pix) * C0 + c : x1 + ((size_t)b * HW + pix) * C1 + (c - C0);
-    const uint4 v = *reinterpret_cast<const uint4*>(src);
+  auto apply = [&](const uint4& v, int pix) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float a = bf16_lo(w[i]) * s_a[c + 2 * i] + s_b[c + 2 * i];
-      float bb = bf16_hi(w[i]) * s_a[c + 2 * i + 1] + s_b[c + 2 * i + 1];
+      float y0 = fmaf(bf16_lo(w[i]), a[2 * i], sh[2 * i]);
+      float y1 = fmaf(bf16_hi(w[i]), a[2 * i + 1], sh[2 * i + 1]);
       if (silu) {
-        a = silu_f(a);
-        bb = silu_f(bb);
+        y0 = silu_f(y0);
+        y1 = silu_f(y1);
       }
-      o[i] = pack_bf16x2(a, bb);
+      o[i] = pack_bf16x2(y0, y1);
     }
-    *reinterpret_cast<uint4*>(out + ((size_t)b * HW + pix) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(dst + (size_t)pix * C) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int pix = p_begin + prow;
+  for (; pix + 3 * R < p_end; pix += 4 * R) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(pix + u * R) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) apply(v[u], pix + u * R);
   }
+  for (; pix < p_end; pix += R) apply(*reinterpret_cast<const uint4*>(src + (size_t)pix * ld), pix);
 }
 
 void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
@@ -213,22 +228,25 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   float2* mean_rstd = reinterpret_cast<float2*>(partial + (size_t)B * LDN_GN_MAX_SPLITS * 32);
   unsigned int* counters = reinterpret_cast<unsigned int*>(mean_rstd + (size_t)B * 32);  // zero-initialised workspace
   const int nvec = C / 8;
+  // R pixel rows per block pass; every thread should see >= 4 pixels (>= 8 when the tensor is large) so that its
+  // 16-byte loads overlap, and the grid should still cover the 148 SMs where the tensor is big enough for that.
   int R = 1024 / nvec;
   if (R > 16) R = 16;
-  const int threads = nvec * R;
-  // enough blocks to fill the machine: ~4 waves of 148 SMs split over B
-  int splits = (148 * 4 + B - 1) / B;
-  int rows_per_block = (HW + splits - 1) / splits;
-  if (rows_per_block < R) rows_per_block = R;
-  splits = (HW + rows_per_block - 1) / rows_per_block;
-  LDN_CHECK(splits <= LDN_GN_MAX_SPLITS, "groupnorm: too many splits");
-  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, partial, counters,
+  while (R > 1 && (HW / (R * 4)) * B < 148) R >>= 1;
+  const int threads = (nvec * R + 31) / 32 * 32;
+  const int want_blocks = (148 * 2 + B - 1) / B;  // per batch row
+  int rows_per_block = (HW + want_blocks - 1) / want_blocks;
+  if (rows_per_block < 8 * R) rows_per_block = (HW >= 8 * R * want_blocks / 2) ? 8 * R : 4 * R;
+  int splits = (HW + rows_per_block - 1) / rows_per_block;
+  if (splits > LDN_GN_MAX_SPLITS) {
+    rows_per_block = (HW + LDN_GN_MAX_SPLITS - 1) / LDN_GN_MAX_SPLITS;
+    splits = (HW + rows_per_block - 1) / rows_per_block;
+  }
+  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, R, partial, counters,
                                                            eps, mean_rstd);
   LDN_CUDA(cudaGetLastError());
-  int rpb2 = (HW + splits - 1) / splits;
-  const size_t smem = sizeof(float) * 2 * C;
-  gn_apply_kernel<<<dim3((HW + rpb2 - 1) / rpb2, B), 512, smem, stream>>>(x0, C0, x1, C1, HW, cpg, eps, gamma, beta,
-                                                                          silu ? 1 : 0, mean_rstd, out, rpb2);
+  gn_apply_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, gamma, beta, silu ? 1 : 0,
+                                                           mean_rstd, out, rows_per_block, R);
   LDN_CUDA(cudaGetLastError());
 }
 
