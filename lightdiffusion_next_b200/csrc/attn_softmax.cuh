@@ -21,22 +21,6 @@ __device__ __forceinline__ float ex2p(float x) {
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-// Packed fp32 pairs (FFMA2 / FADD2 on sm_100): one issue slot for two lanes' worth of scale / polynomial arithmetic.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n"
-      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd; }"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  float2 d;
-  asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd; }"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
 // exp2(s * sc + neg_m) for one 8-column chunk of a score row, packed to 4 bf16x2 words.
 // mode 0: MUFU ex2; mode 1: degree-3 polynomial on the FMA pipe (same arithmetic as ex2p, two lanes per instruction);
 // mode 2: experiment only (no exponential). `mode` is a compile-time constant after unrolling.
