@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--size", type=int, default=1024, help="image size in pixels (config 2 = 1024)")
     ap.add_argument("--bs", type=int, default=1, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the full-run / pipe() end-to-end secondary numbers")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -341,6 +342,8 @@ def main():
             line["step_roofline"] = {"bound": "tensor", "achieved": whole, "peak": peaks["bf16_sus"], "unit": "TFLOP/s",
                                      "frac": whole / peaks["bf16_sus"], "tflop_per_step": step_tflop,
                                      "peak_source": peaks["source"] + " (sustained)"}
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = secondary_metrics(eng, args.size, dev)
         if world == 1 and not args.no_cpu_baseline:
             n, dt, done_w, threads = cpu_oracle_step_time(lat, max_seconds=60.0, max_steps=1, warmup=0)
             line["cpu_baseline"] = {"value": n / dt, "unit": "it/s", "cores": threads, "kind": "port",
@@ -350,6 +353,44 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def secondary_metrics(eng, size: int, dev) -> dict:
+    """SURVEY.md 8(d) secondary numbers, all through the public host API and wall-clocked with a device sync:
+    whole 30-step KSampler runs with multiscale off and with the reference-default multiscale schedule (which runs
+    8 of the 30 steps at half resolution), and end-to-end images/s of the pipe() surface (CLIP encode of two prompts +
+    30 sampler steps + VAE decode + image D2H)."""
+    import torch
+    from lightdiffusion_next_b200 import sampling as S
+    from lightdiffusion_next_b200.pipeline import Pipeline, EMPTY_TOKENS
+    from lightdiffusion_next_b200.synth import synth_state_dict, vae_decoder_shapes, clip_shapes
+    out = {}
+    g = torch.Generator().manual_seed(99)
+    pos = torch.randn(1, 77, 768, generator=g)
+    neg = torch.randn(1, 77, 768, generator=g)
+    latent = {"samples": torch.zeros(1, 4, size // 8, size // 8)}
+    for name, ms_flag in (("full_run_multiscale_off", False), ("full_run_multiscale_default", True)):
+        S.sample(eng, 42, 30, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, latent, enable_multiscale=ms_flag)  # warm-up / graph capture
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        S.sample(eng, 42, 30, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, latent, enable_multiscale=ms_flag)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[name] = {"it_per_s": 30 / dt, "seconds": dt, "steps": 30}
+    eng.load_vae(synth_state_dict(vae_decoder_shapes(), seed=4321))
+    eng.load_clip(synth_state_dict(clip_shapes(), seed=777))
+    pipe = Pipeline(eng)
+    toks = [[(49406, 1.0)] + [(1000 + i, 1.0) for i in range(20)] + [(49407, 1.0)] * 56]
+    pipe(toks, width=size, height=size, steps=30, sampler_name="dpmpp_2m_cfgpp", scheduler="karras")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    img = pipe(toks, width=size, height=size, steps=30, sampler_name="dpmpp_2m_cfgpp", scheduler="karras")
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["pipe_e2e"] = {"images_per_s": 1.0 / dt, "seconds_per_image": dt, "finite": bool(torch.isfinite(img).all().item()),
+                       "what": "CLIP encode (positive + empty negative) + 30 steps dpmpp_2m_cfgpp (reference-default multiscale) "
+                               "+ VAE decode + image to host, %dx%d, synthetic weights" % (size, size)}
+    return out
 
 
 def eng_launches(eng) -> int:

@@ -106,3 +106,62 @@ def synth_tensor(name: str, shape: Tuple[int, ...], seed: int = 1234, dtype=torc
 
 def synth_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int = 1234, dtype=torch.float16) -> Dict[str, torch.Tensor]:
     return {k: synth_tensor(k, v, seed, dtype) for k, v in shapes.items()}
+
+
+def vae_decoder_shapes(ch: int = 128, ch_mult=(1, 2, 4, 4), num_res: int = 2, z: int = 4, out_ch: int = 3) -> Dict[str, Tuple[int, ...]]:
+    """State-dict layout of the SD1.5 VAE decoder side (keys below `first_stage_model.`; Decoder,
+    src/AutoEncoders/VariationalAE.py:416-567)."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(p, o, i, k):
+        s[p + ".weight"] = (o, i, k, k)
+        s[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        s[p + ".weight"] = s[p + ".bias"] = (c,)
+
+    def res(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cout, cin, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".nin_shortcut", cout, cin, 1)
+
+    conv("post_quant_conv", z, z, 1)
+    c = ch * ch_mult[-1]
+    conv("decoder.conv_in", c, z, 3)
+    res("decoder.mid.block_1", c, c)
+    norm("decoder.mid.attn_1.norm", c)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"decoder.mid.attn_1.{n}", c, c, 1)
+    res("decoder.mid.block_2", c, c)
+    for lvl in reversed(range(len(ch_mult))):
+        co = ch * ch_mult[lvl]
+        for i in range(num_res + 1):
+            res(f"decoder.up.{lvl}.block.{i}", c, co)
+            c = co
+        if lvl != 0:
+            conv(f"decoder.up.{lvl}.upsample.conv", c, c, 3)
+    norm("decoder.norm_out", c)
+    conv("decoder.conv_out", out_ch, c, 3)
+    return s
+
+
+def clip_shapes(width: int = 768, mlp: int = 3072, layers: int = 12, vocab: int = 49408, positions: int = 77) -> Dict[str, Tuple[int, ...]]:
+    """State-dict layout of CLIP-L's text model (keys below `text_model.`; CLIPTextModel_, src/clip/CLIPTextModel.py:3-107)."""
+    s: Dict[str, Tuple[int, ...]] = {"embeddings.token_embedding.weight": (vocab, width),
+                                     "embeddings.position_embedding.weight": (positions, width)}
+    for i in range(layers):
+        p = f"encoder.layers.{i}"
+        for n in ("layer_norm1", "layer_norm2"):
+            s[f"{p}.{n}.weight"] = s[f"{p}.{n}.bias"] = (width,)
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            s[f"{p}.self_attn.{n}.weight"] = (width, width)
+            s[f"{p}.self_attn.{n}.bias"] = (width,)
+        s[f"{p}.mlp.fc1.weight"] = (mlp, width)
+        s[f"{p}.mlp.fc1.bias"] = (mlp,)
+        s[f"{p}.mlp.fc2.weight"] = (width, mlp)
+        s[f"{p}.mlp.fc2.bias"] = (width,)
+    s["final_layer_norm.weight"] = s["final_layer_norm.bias"] = (width,)
+    return s

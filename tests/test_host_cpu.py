@@ -142,3 +142,12 @@ def test_two_rank_gloo_sharded_sampling_equals_single_process(tmp_path, unet_sd)
                       {"samples": torch.zeros(3, 4, 16, 16)})[0]["samples"]
     assert sharded.shape == single.shape
     assert rel(sharded, single) < 1e-5
+
+
+def test_synth_shape_tables_match_oracle():
+    """The package-side VAE / CLIP layout tables (used by bench.py, which may not import the oracle on the product arm)
+    name exactly the tensors the oracle's restatement of the reference modules consumes."""
+    from oracle import sd15_oracle as O
+    from lightdiffusion_next_b200 import synth
+    assert synth.vae_decoder_shapes() == O.vae_decoder_param_shapes()
+    assert synth.clip_shapes() == O.clip_param_shapes()
