@@ -1,0 +1,161 @@
+"""Weight ingest from real SD1.5 checkpoints: file -> the three state dicts the engine loads.
+
+Mirrors the reference's on-disk contract, not its loader classes:
+  * container: `.safetensors` (or a pickled `.ckpt` / `.pt` with an optional top-level "state_dict"), as
+    `load_torch_file` accepts (src/Utilities/util.py, used from src/FileManaging/Loader.py:11-111);
+  * key prefixes of an LDM SD1.5 checkpoint: `model.diffusion_model.` (UNet), `first_stage_model.` (VAE),
+    `cond_stage_model.transformer.[text_model.]` (CLIP-L; the older layout without `text_model.` is renamed exactly as
+    SD15.process_clip_state_dict does, src/SD15/SD15.py:32-69);
+  * LoRA merge: kohya-style `lora_unet_*` / `lora_te_text_model_encoder_layers_*` keys (src/Model/LoRas.py:15-121) folded
+    into the weights with `W += strength * (alpha / rank) * (up @ down)` (ModelPatcher.calculate_weight,
+    src/Model/ModelPatcher.py:621-650): fp32 product, rounded to the weight's storage dtype before the add.
+
+The engine never sees file formats: it takes the resulting `{name: tensor}` dicts through `Engine.load_unet / load_vae /
+load_clip` (C ABI `ldn_load_weights`), which repack to the HBM layout once.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Mapping, Optional, Tuple
+
+import torch
+
+from . import synth
+
+UNET_PREFIX = "model.diffusion_model."
+VAE_PREFIX = "first_stage_model."
+CLIP_PREFIXES = ("cond_stage_model.transformer.text_model.", "cond_stage_model.transformer.")
+
+# src/Model/LoRas.py:5-12
+_LORA_CLIP_MAP = {
+    "mlp.fc1": "mlp_fc1",
+    "mlp.fc2": "mlp_fc2",
+    "self_attn.k_proj": "self_attn_k_proj",
+    "self_attn.q_proj": "self_attn_q_proj",
+    "self_attn.v_proj": "self_attn_v_proj",
+    "self_attn.out_proj": "self_attn_out_proj",
+}
+
+
+def load_state_dict_file(path: str) -> Dict[str, torch.Tensor]:
+    """Read a checkpoint container into a flat `{key: cpu tensor}` dict."""
+    if path.endswith((".safetensors", ".sft")):
+        from safetensors.torch import load_file
+
+        return load_file(path, device="cpu")
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    if isinstance(sd, dict) and "state_dict" in sd and isinstance(sd["state_dict"], dict):
+        sd = sd["state_dict"]
+    return sd
+
+
+def _strip(sd: Mapping[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def split_sd15_checkpoint(sd: Mapping[str, torch.Tensor], strict: bool = True) -> Dict[str, Dict[str, torch.Tensor]]:
+    """Full-checkpoint state dict -> {"unet": ..., "vae": ..., "clip": ...} in the engine's key layout
+    (UNet keys below `model.diffusion_model.`, VAE decoder-side keys below `first_stage_model.`, CLIP keys below
+    `text_model.`).  Parts that are absent from the file are returned empty; with `strict` every present part is checked
+    against the SD1.5 layout tables (names and shapes) and a ValueError lists what is missing or mis-shaped."""
+    unet = _strip(sd, UNET_PREFIX)
+    vae_all = _strip(sd, VAE_PREFIX)
+    vae = {k: v for k, v in vae_all.items() if k.startswith(("decoder.", "post_quant_conv."))}
+    clip: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if k.startswith(CLIP_PREFIXES[0]):
+            clip[k[len(CLIP_PREFIXES[0]):]] = v
+        elif k.startswith(CLIP_PREFIXES[1]):  # pre-`text_model.` layout (SD15.py:43-53)
+            clip[k[len(CLIP_PREFIXES[1]):]] = v
+    clip.pop("embeddings.position_ids", None)  # a buffer, not a weight
+    parts = {"unet": unet, "vae": vae, "clip": clip}
+    if strict:
+        problems = []
+        for name, table in (("unet", synth.unet_shapes()), ("vae", synth.vae_decoder_shapes()), ("clip", synth.clip_shapes())):
+            part = parts[name]
+            if not part:
+                continue
+            for k, shape in table.items():
+                if k not in part:
+                    problems.append(f"{name}: missing {k}")
+                elif tuple(part[k].shape) != tuple(shape):
+                    # 1x1 convs stored as linear weights (or vice versa) are the same tensor
+                    if part[k].numel() == _numel(shape) and _squeeze(part[k].shape) == _squeeze(shape):
+                        part[k] = part[k].reshape(shape)
+                    else:
+                        problems.append(f"{name}: {k} has shape {tuple(part[k].shape)}, expected {tuple(shape)}")
+            parts[name] = {k: part[k] for k in table if k in part}  # drop keys the SD1.5 path does not use
+        if problems:
+            raise ValueError("not an SD1.5 checkpoint this engine can load:\n  " + "\n  ".join(problems[:20])
+                             + (f"\n  ... and {len(problems) - 20} more" if len(problems) > 20 else ""))
+    return parts
+
+
+def _numel(shape: Iterable[int]) -> int:
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+def _squeeze(shape: Iterable[int]) -> Tuple[int, ...]:
+    return tuple(int(s) for s in shape if int(s) != 1)
+
+
+def lora_key_map(parts: Mapping[str, Mapping[str, torch.Tensor]]) -> Dict[str, Tuple[str, str]]:
+    """LoRA module name -> (part, weight key).  UNet: `lora_unet_` + key with dots replaced by underscores
+    (LoRas.py:95-99); CLIP: the three text-encoder spellings of LoRas.py:69-83."""
+    m: Dict[str, Tuple[str, str]] = {}
+    for k in parts.get("unet", {}):
+        if k.endswith(".weight"):
+            m["lora_unet_" + k[: -len(".weight")].replace(".", "_")] = ("unet", k)
+    for k in parts.get("clip", {}):
+        if not (k.startswith("encoder.layers.") and k.endswith(".weight")):
+            continue
+        _, _, b, rest = k.split(".", 3)
+        mod = rest[: -len(".weight")]
+        if mod in _LORA_CLIP_MAP:
+            m[f"lora_te_text_model_encoder_layers_{b}_{_LORA_CLIP_MAP[mod]}"] = ("clip", k)
+            m[f"lora_te1_text_model_encoder_layers_{b}_{_LORA_CLIP_MAP[mod]}"] = ("clip", k)
+            m[f"text_encoder.text_model.encoder.layers.{b}.{mod}"] = ("clip", k)
+    return m
+
+
+def merge_lora(parts: Dict[str, Dict[str, torch.Tensor]], lora: Mapping[str, torch.Tensor], strength_model: float = 1.0,
+               strength_clip: float = 1.0) -> int:
+    """Fold a LoRA into `parts` in place; returns the number of weights patched.  Unknown LoRA modules are ignored, like
+    the reference's load_lora (it only walks the keys it can map)."""
+    keymap = lora_key_map(parts)
+    n = 0
+    for mod, (part, wkey) in keymap.items():
+        up_k, down_k = mod + ".lora_up.weight", mod + ".lora_down.weight"
+        if up_k not in lora or down_k not in lora:
+            continue
+        strength = strength_model if part == "unet" else strength_clip
+        if strength == 0.0:
+            continue
+        up, down = lora[up_k].float(), lora[down_k].float()
+        alpha = strength
+        a_k = mod + ".alpha"
+        if a_k in lora:
+            alpha *= float(lora[a_k].item()) / down.shape[0]
+        w = parts[part][wkey]
+        delta = (alpha * torch.mm(up.flatten(start_dim=1), down.flatten(start_dim=1))).reshape(w.shape)
+        parts[part][wkey] = w + delta.to(w.dtype)
+        n += 1
+    return n
+
+
+def load_sd15(engine, path: str, lora_path: Optional[str] = None, strength_model: float = 1.0,
+              strength_clip: float = 1.0) -> Dict[str, int]:
+    """Checkpoint file (+ optional LoRA) -> engine.  Returns the tensor count loaded per part."""
+    parts = split_sd15_checkpoint(load_state_dict_file(path))
+    if lora_path:
+        merge_lora(parts, load_state_dict_file(lora_path), strength_model, strength_clip)
+    if parts["unet"]:
+        engine.load_unet(parts["unet"])
+    if parts["vae"]:
+        engine.load_vae(parts["vae"])
+    if parts["clip"]:
+        engine.load_clip(parts["clip"])
+    return {k: len(v) for k, v in parts.items()}

@@ -84,6 +84,14 @@ class Engine:
     def load_clip(self, state_dict: Dict[str, torch.Tensor]) -> None:
         self.load_weights(CLIP, state_dict)
 
+    def load_checkpoint(self, path: str, lora_path: Optional[str] = None, strength_model: float = 1.0,
+                        strength_clip: float = 1.0) -> Dict[str, int]:
+        """SD1.5 checkpoint file (.safetensors / .ckpt), optionally with a LoRA folded in -> UNet / VAE / CLIP weights
+        (see checkpoint.py; the reference side is load_checkpoint_guess_config, src/FileManaging/Loader.py:11-111)."""
+        from . import checkpoint
+
+        return checkpoint.load_sd15(self, path, lora_path, strength_model, strength_clip)
+
     # ------------------------------------------------------------------ UNet hot path
     def set_context(self, ctx: torch.Tensor) -> None:
         """ctx: [rows, tokens, 768]; rows ordered as the UNet batch rows (uncond first, then cond)."""

@@ -1,0 +1,123 @@
+"""Host-side checkpoint ingest (lightdiffusion_next_b200/checkpoint.py): container read, SD1.5 prefix split + layout
+validation, LoRA merge arithmetic (reference: Loader.py:11-111, SD15.py:32-69, LoRas.py:15-121, ModelPatcher.py:621-650)."""
+import pytest
+import torch
+
+from lightdiffusion_next_b200 import checkpoint as C
+from lightdiffusion_next_b200 import synth
+
+
+def test_safetensors_roundtrip_and_prefix_split(tmp_path):
+    from safetensors.torch import save_file
+    g = torch.Generator().manual_seed(0)
+    sd = {
+        "model.diffusion_model.time_embed.0.weight": torch.randn(8, 4, generator=g).half(),
+        "model.diffusion_model.out.2.bias": torch.randn(4, generator=g).half(),
+        "first_stage_model.decoder.conv_in.weight": torch.randn(8, 4, 3, 3, generator=g).half(),
+        "first_stage_model.post_quant_conv.bias": torch.randn(4, generator=g).half(),
+        "first_stage_model.encoder.conv_in.weight": torch.randn(8, 3, 3, 3, generator=g).half(),  # not on the decode path
+        # old CLIP layout (no `text_model.`), renamed like SD15.process_clip_state_dict
+        "cond_stage_model.transformer.embeddings.position_embedding.weight": torch.randn(77, 8, generator=g).half(),
+        "cond_stage_model.transformer.text_model.final_layer_norm.bias": torch.randn(8, generator=g).half(),
+        "cond_stage_model.transformer.text_model.embeddings.position_ids": torch.arange(77)[None],
+        "model_ema.decay": torch.tensor(0.999),
+    }
+    path = str(tmp_path / "tiny.safetensors")
+    save_file(sd, path)
+    loaded = C.load_state_dict_file(path)
+    assert set(loaded) == set(sd)
+    parts = C.split_sd15_checkpoint(loaded, strict=False)
+    assert set(parts["unet"]) == {"time_embed.0.weight", "out.2.bias"}
+    assert set(parts["vae"]) == {"decoder.conv_in.weight", "post_quant_conv.bias"}
+    assert set(parts["clip"]) == {"embeddings.position_embedding.weight", "final_layer_norm.bias"}
+    assert torch.equal(parts["unet"]["time_embed.0.weight"], sd["model.diffusion_model.time_embed.0.weight"])
+    # pickled container with a top-level "state_dict"
+    p2 = str(tmp_path / "tiny.ckpt")
+    torch.save({"state_dict": sd}, p2)
+    assert set(C.load_state_dict_file(p2)) == set(sd)
+
+
+def _meta_checkpoint():
+    sd = {}
+    for k, s in synth.unet_shapes().items():
+        sd[C.UNET_PREFIX + k] = torch.empty(s, dtype=torch.float16, device="meta")
+    for k, s in synth.vae_decoder_shapes().items():
+        sd[C.VAE_PREFIX + k] = torch.empty(s, dtype=torch.float16, device="meta")
+    for k, s in synth.clip_shapes().items():
+        sd[C.CLIP_PREFIXES[0] + k] = torch.empty(s, dtype=torch.float16, device="meta")
+    return sd
+
+
+def test_strict_layout_validation():
+    sd = _meta_checkpoint()
+    parts = C.split_sd15_checkpoint(sd)
+    assert len(parts["unet"]) == len(synth.unet_shapes()) == 686
+    assert len(parts["vae"]) == len(synth.vae_decoder_shapes())
+    assert len(parts["clip"]) == len(synth.clip_shapes())
+    # a 1x1 conv stored as a linear weight is accepted and reshaped
+    k = C.UNET_PREFIX + "input_blocks.1.1.proj_in.weight"
+    sd2 = dict(sd)
+    sd2[k] = torch.empty(320, 320, dtype=torch.float16, device="meta")
+    assert tuple(C.split_sd15_checkpoint(sd2)["unet"]["input_blocks.1.1.proj_in.weight"].shape) == (320, 320, 1, 1)
+    # missing / mis-shaped tensors are reported by name
+    sd3 = dict(sd)
+    del sd3[C.UNET_PREFIX + "middle_block.1.transformer_blocks.0.attn2.to_k.weight"]
+    sd3[C.VAE_PREFIX + "decoder.conv_out.weight"] = torch.empty(3, 64, 3, 3, dtype=torch.float16, device="meta")
+    with pytest.raises(ValueError) as ei:
+        C.split_sd15_checkpoint(sd3)
+    msg = str(ei.value)
+    assert "middle_block.1.transformer_blocks.0.attn2.to_k.weight" in msg and "decoder.conv_out.weight" in msg
+    # a UNet-only file loads (other parts empty)
+    only = {k: v for k, v in sd.items() if k.startswith(C.UNET_PREFIX)}
+    p = C.split_sd15_checkpoint(only)
+    assert p["vae"] == {} and p["clip"] == {} and len(p["unet"]) == 686
+
+
+def test_merge_lora_matches_reference_formula():
+    g = torch.Generator().manual_seed(1)
+    parts = {
+        "unet": {
+            "input_blocks.1.1.transformer_blocks.0.attn1.to_q.weight": torch.randn(32, 32, generator=g).half(),
+            "input_blocks.1.0.in_layers.2.weight": torch.randn(16, 8, 3, 3, generator=g).half(),
+            "input_blocks.1.0.in_layers.2.bias": torch.randn(16, generator=g).half(),
+        },
+        "clip": {"encoder.layers.3.self_attn.k_proj.weight": torch.randn(24, 24, generator=g).half(),
+                 "encoder.layers.3.mlp.fc1.weight": torch.randn(48, 24, generator=g).half()},
+        "vae": {},
+    }
+    ref = {p: {k: v.clone() for k, v in d.items()} for p, d in parts.items()}
+    r = 4
+    lora = {
+        "lora_unet_input_blocks_1_1_transformer_blocks_0_attn1_to_q.lora_up.weight": torch.randn(32, r, generator=g),
+        "lora_unet_input_blocks_1_1_transformer_blocks_0_attn1_to_q.lora_down.weight": torch.randn(r, 32, generator=g),
+        "lora_unet_input_blocks_1_1_transformer_blocks_0_attn1_to_q.alpha": torch.tensor(2.0),
+        "lora_unet_input_blocks_1_0_in_layers_2.lora_up.weight": torch.randn(16, r, 1, 1, generator=g),
+        "lora_unet_input_blocks_1_0_in_layers_2.lora_down.weight": torch.randn(r, 8, 3, 3, generator=g),
+        "lora_te_text_model_encoder_layers_3_self_attn_k_proj.lora_up.weight": torch.randn(24, r, generator=g),
+        "lora_te_text_model_encoder_layers_3_self_attn_k_proj.lora_down.weight": torch.randn(r, 24, generator=g),
+        "lora_te_text_model_encoder_layers_3_self_attn_k_proj.alpha": torch.tensor(4.0),
+        "lora_unet_some_module_not_in_the_model.lora_up.weight": torch.randn(4, r, generator=g),
+        "lora_unet_some_module_not_in_the_model.lora_down.weight": torch.randn(r, 4, generator=g),
+    }
+    n = C.merge_lora(parts, lora, strength_model=0.8, strength_clip=0.5)
+    assert n == 3
+
+    def expect(w, up, down, strength, alpha):
+        a = strength * (alpha / down.shape[0] if alpha is not None else 1.0)
+        return w + (a * torch.mm(up.float().flatten(1), down.float().flatten(1))).reshape(w.shape).to(w.dtype)
+
+    k = "input_blocks.1.1.transformer_blocks.0.attn1.to_q.weight"
+    m = "lora_unet_input_blocks_1_1_transformer_blocks_0_attn1_to_q"
+    assert torch.equal(parts["unet"][k], expect(ref["unet"][k], lora[m + ".lora_up.weight"], lora[m + ".lora_down.weight"], 0.8, 2.0))
+    k = "input_blocks.1.0.in_layers.2.weight"
+    m = "lora_unet_input_blocks_1_0_in_layers_2"
+    assert torch.equal(parts["unet"][k], expect(ref["unet"][k], lora[m + ".lora_up.weight"], lora[m + ".lora_down.weight"], 0.8, None))
+    k = "encoder.layers.3.self_attn.k_proj.weight"
+    m = "lora_te_text_model_encoder_layers_3_self_attn_k_proj"
+    assert torch.equal(parts["clip"][k], expect(ref["clip"][k], lora[m + ".lora_up.weight"], lora[m + ".lora_down.weight"], 0.5, 4.0))
+    # untouched tensors stay bit-identical
+    assert torch.equal(parts["unet"]["input_blocks.1.0.in_layers.2.bias"], ref["unet"]["input_blocks.1.0.in_layers.2.bias"])
+    assert torch.equal(parts["clip"]["encoder.layers.3.mlp.fc1.weight"], ref["clip"]["encoder.layers.3.mlp.fc1.weight"])
+    # zero strength is a no-op
+    again = {p: {k: v.clone() for k, v in d.items()} for p, d in ref.items()}
+    assert C.merge_lora(again, lora, 0.0, 0.0) == 0
