@@ -16,8 +16,12 @@ SHAPES = [  # name, M, N, K, epi, bias, residual
     ("L2 out 1280x1280", 2048, 1280, 1280, 0, True, True),
     ("L2 geglu", 2048, 10240, 1280, 1, True, False),
     ("L2 ff.out", 2048, 1280, 5120, 0, True, True),
+    ("L3 out 1280x1280", 512, 1280, 1280, 0, True, True),
+    ("L3 ff.out", 512, 1280, 5120, 0, True, True),
+    ("L3 geglu", 512, 10240, 1280, 1, True, False),
 ]
 only = int(sys.argv[1]) if len(sys.argv) > 1 else -1
+BN = int(os.environ.get("BN", "0"))
 for i, (name, M, N, K, epi, hb, hr) in enumerate(SHAPES):
     if only >= 0 and i != only: continue
     A = torch.randn(M, K, device=dev).bfloat16(); W = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
@@ -27,7 +31,7 @@ for i, (name, M, N, K, epi, hb, hr) in enumerate(SHAPES):
     out = torch.empty(M, No, device=dev, dtype=torch.bfloat16)
     def run():
         L.check(lib.ldn_gemm_bf16(A.data_ptr(), K, K, 0, 0, 0, W.data_ptr(), M, N, bias.data_ptr() if hb else 0, 0, 0, 0,
-                                  res.data_ptr() if hr else 0, No, out.data_ptr(), No, 0, epi, 0, 0, 0, L.cur_stream()))
+                                  res.data_ptr() if hr else 0, No, out.data_ptr(), No, 0, epi, 0, 0, BN, L.cur_stream()))
     run(); torch.cuda.synchronize()
     ts = []
     for _ in range(5):
