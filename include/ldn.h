@@ -11,6 +11,7 @@
  *   ldn_set_context    <- CrossAttention.to_k/to_v        src/Attention/Attention.py:118-121 (hoisted out of the loop)
  *   ldn_cfg_step       <- cfg_function + sampler update   src/sample/CFG.py:55-60, src/sample/samplers.py:728-732,952-953
  *   ldn_vae_decode     <- VAE.decode                      src/AutoEncoders/VariationalAE.py:690-722
+ *   ldn_vae_encode     <- AutoencodingEngine.encode (w/o the sampling step)  src/AutoEncoders/VariationalAE.py:148-172, 377-413
  *   ldn_clip_encode    <- CLIPTextModel_.forward          src/clip/CLIPTextModel.py:51-107
  *   op-level entries   <- the torch library calls of      src/cond/cast.py:107,174,241,281 and
  *                         optimized_attention             src/Attention/Attention.py:34-41
@@ -74,6 +75,10 @@ int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond,
 /* ---- VAE decode / CLIP encode */
 /* z: [B,4,h,w] fp32 (already divided by 0.18215); rgb: [B,8h,8w,3] fp32 in [0,1] */
 int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, int lat_w, void* stream);
+/* pixels: [B,3,H,W] fp32 already mapped to [-1,1] (process_input, VariationalAE.py:601); moments: [B,8,H/8,W/8] fp32
+ * (mean | logvar after quant_conv). The reparameterised sample mean + exp(0.5*clamp(logvar,-30,20))*randn stays with the
+ * caller, which owns the RNG (DiagonalGaussianDistribution.sample, VariationalAE.py:42-51). Needs encoder.* weights. */
+int ldn_vae_encode(ldn_handle h, const float* pixels, float* moments, int B, int H, int W, void* stream);
 /* ids: [S,77] int64 (device); out_last: [S,77,768] fp32 final-LN of last layer (may be NULL);
  * out_penultimate: [S,77,768] fp32 final-LN of layer -2 (what SD1.5 uses) */
 int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultimate, float* out_last, void* stream);

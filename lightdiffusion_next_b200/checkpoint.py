@@ -60,7 +60,7 @@ def split_sd15_checkpoint(sd: Mapping[str, torch.Tensor], strict: bool = True) -
     against the SD1.5 layout tables (names and shapes) and a ValueError lists what is missing or mis-shaped."""
     unet = _strip(sd, UNET_PREFIX)
     vae_all = _strip(sd, VAE_PREFIX)
-    vae = {k: v for k, v in vae_all.items() if k.startswith(("decoder.", "post_quant_conv."))}
+    vae = {k: v for k, v in vae_all.items() if k.startswith(("decoder.", "post_quant_conv.", "encoder.", "quant_conv."))}
     clip: Dict[str, torch.Tensor] = {}
     for k, v in sd.items():
         if k.startswith(CLIP_PREFIXES[0]):
@@ -71,7 +71,10 @@ def split_sd15_checkpoint(sd: Mapping[str, torch.Tensor], strict: bool = True) -
     parts = {"unet": unet, "vae": vae, "clip": clip}
     if strict:
         problems = []
-        for name, table in (("unet", synth.unet_shapes()), ("vae", synth.vae_decoder_shapes()), ("clip", synth.clip_shapes())):
+        vae_table = dict(synth.vae_decoder_shapes())
+        if any(k.startswith("encoder.") for k in vae):  # encoder side is optional (VAE-decode-only files exist)
+            vae_table.update(synth.vae_encoder_shapes())
+        for name, table in (("unet", synth.unet_shapes()), ("vae", vae_table), ("clip", synth.clip_shapes())):
             part = parts[name]
             if not part:
                 continue

@@ -196,7 +196,9 @@ void launch_conv_out(const bf16* h, const bf16* Wt, const float* bias, const flo
                      int H, int W, int Cin, int Cout, float* denoised, float* eps_out, cudaStream_t stream);
 void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);
 // stride-2 3x3 pad-1 im2col gather: [B,H,W,C] -> [B*(H/2)*(W/2), 9*C]
-void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);
+void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream, int pad_before = 1);
+void launch_vae_moments_finish(const float* acc16, const float* bc, const float* Wq, const float* bq, int B, int HW,
+                               int zc2, float* out, cudaStream_t stream);
 // dst[c, b*nk_pad + k] = src[c, b*N + k]: V^T re-laid with 16-byte aligned per-batch column offsets
 void launch_pad_vt_cols(const bf16* src, int ld_src, int C, int Bn, int N, int nk_pad, bf16* dst, cudaStream_t stream);
 void launch_fill_bf16(bf16* p, size_t n, float v, cudaStream_t stream);

@@ -240,6 +240,14 @@ int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, i
   LDN_API_END
 }
 
+int ldn_vae_encode(ldn_handle h, const float* pixels, float* moments, int B, int H, int W, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && pixels && moments, "ldn_vae_encode: bad argument");
+  if (!h->finalized[1]) vae_finalize(h, (cudaStream_t)stream);
+  vae_encode(h, pixels, moments, B, H, W, (cudaStream_t)stream);
+  LDN_API_END
+}
+
 int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultimate, float* out_last, void* stream) {
   LDN_API_BEGIN
   LDN_CHECK(h && ids, "ldn_clip_encode: bad argument");

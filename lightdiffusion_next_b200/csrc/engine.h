@@ -93,6 +93,7 @@ void unet_denoise(ldn_engine* e, const float* x, const float* sigma, float* out,
 int unet_last_launches(ldn_engine* e);
 void vae_finalize(ldn_engine* e, cudaStream_t stream);
 void vae_decode(ldn_engine* e, const float* z, float* rgb, int B, int h, int w, cudaStream_t stream);
+void vae_encode(ldn_engine* e, const float* pixels, float* moments, int B, int H, int W, cudaStream_t stream);
 void clip_finalize(ldn_engine* e, cudaStream_t stream);
 void clip_encode(ldn_engine* e, const int64_t* ids, int S, float* out_pen, float* out_last, cudaStream_t stream);
 }  // namespace ldn

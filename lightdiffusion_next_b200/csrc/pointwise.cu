@@ -363,6 +363,34 @@ void launch_conv_out_finish(const float* acc16, const float* bias, const float* 
   LDN_CUDA(cudaGetLastError());
 }
 
+// VAE encoder tail: moments[b, o, pix] = bq[o] + sum_i Wq[o, i] * (acc16[pix, i] + bc[i])  -- the encoder's conv_out
+// (512 -> 8, run as a 16-column tensor-core conv into fp32 scratch) followed by quant_conv 1x1 (8 -> 8), NCHW fp32 out
+// (AutoencodingEngine.encode, src/AutoEncoders/VariationalAE.py:148-172).
+__global__ void vae_moments_finish_kernel(const float* __restrict__ acc16, const float* __restrict__ bc,
+                                          const float* __restrict__ Wq, const float* __restrict__ bq, int B, int HW, int zc2,
+                                          float* __restrict__ out) {
+  const size_t total = (size_t)B * zc2 * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const int o = (int)((i / HW) % zc2);
+    const int b = (int)(i / ((size_t)HW * zc2));
+    const float* a = acc16 + ((size_t)b * HW + pix) * 16;
+    float acc = bq[o];
+    for (int k = 0; k < zc2; ++k) acc = fmaf(Wq[o * zc2 + k], a[k] + bc[k], acc);
+    out[i] = acc;
+  }
+}
+void launch_vae_moments_finish(const float* acc16, const float* bc, const float* Wq, const float* bq, int B, int HW,
+                               int zc2, float* out, cudaStream_t stream) {
+  LDN_CHECK(zc2 <= 16, "vae_moments_finish: at most 16 channels");
+  const size_t total = (size_t)B * zc2 * HW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  vae_moments_finish_kernel<<<blocks, 256, 0, stream>>>(acc16, bc, Wq, bq, B, HW, zc2, out);
+  LDN_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ nearest 2x upsample (F.interpolate nearest, ResBlock.py:135)
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ out) {
   const int nvec = C >> 3;
@@ -386,10 +414,12 @@ void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cud
   LDN_CUDA(cudaGetLastError());
 }
 
-// ------------------------------------------------------------------ stride-2 3x3 pad-1 patch gather (Downsample1, ResBlock.py:173-182)
-// out[(b,oy,ox), tap*C + c] = x[b, 2oy+ky-1, 2ox+kx-1, c]
-__global__ void im2col_s2_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ out) {
-  const int Ho = H / 2, Wo = W / 2;
+// ------------------------------------------------------------------ stride-2 3x3 patch gather
+// pad_before = 1: UNet Downsample1 (conv stride 2, padding 1; ResBlock.py:173-182), Ho = ceil(H/2).
+// pad_before = 0: VAE encoder Downsample (F.pad (0,1,0,1) then conv stride 2, padding 0; VariationalAE.py:224-254), Ho = floor(H/2).
+// out[(b,oy,ox), tap*C + c] = x[b, 2oy+ky-pad_before, 2ox+kx-pad_before, c]  (zero outside the image)
+__global__ void im2col_s2_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, int pad_before,
+                                 bf16* __restrict__ out) {
   const int nvec = C >> 3;
   const size_t total = (size_t)B * Ho * Wo * 9 * nvec;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -400,20 +430,21 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, int B, int H, int W
     const int ox = (int)(r % Wo);
     const int oy = (int)((r / Wo) % Ho);
     const int b = (int)(r / ((size_t)Wo * Ho));
-    const int yy = 2 * oy + tap / 3 - 1;
-    const int xx = 2 * ox + tap % 3 - 1;
+    const int yy = 2 * oy + tap / 3 - pad_before;
+    const int xx = 2 * ox + tap % 3 - pad_before;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (yy >= 0 && yy < H && xx >= 0 && xx < W)
       u = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + v * 8);
     *reinterpret_cast<uint4*>(out + (r * 9 + tap) * C + v * 8) = u;
   }
 }
-void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream) {
-  LDN_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad shape");
-  const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
+void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream, int pad_before) {
+  LDN_CHECK(C % 8 == 0 && H >= 2 && W >= 2, "im2col_s2: bad shape");
+  const int Ho = pad_before ? (H + 1) / 2 : H / 2, Wo = pad_before ? (W + 1) / 2 : W / 2;
+  const size_t total = (size_t)B * Ho * Wo * 9 * (C / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col_s2_kernel<<<blocks, 256, 0, stream>>>(x, B, H, W, C, out);
+  im2col_s2_kernel<<<blocks, 256, 0, stream>>>(x, B, H, W, C, Ho, Wo, pad_before, out);
   LDN_CUDA(cudaGetLastError());
 }
 

@@ -23,8 +23,12 @@ struct ldn_engine::VaeState {
   int ch = 128, zc = 4, out_ch = 3, num_res = 2;
   std::vector<int> ch_mult = {1, 2, 4, 4};
   Arena arena;
-  float* attn_bias = nullptr;  // Wp bv + bp
+  float* attn_bias = nullptr;      // decoder mid attention: Wp bv + bp
+  float* attn_bias_enc = nullptr;  // encoder mid attention (only when encoder weights were loaded)
+  float* quant_w = nullptr;        // quant_conv weight as fp32 [8, 8]
+  bool has_decoder = false, has_encoder = false;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Program>> programs;
+  std::map<std::tuple<int, int, int>, std::unique_ptr<Program>> enc_programs;
   std::vector<std::unique_ptr<Arena>> program_arenas;
 };
 
@@ -35,11 +39,25 @@ void vae_finalize(ldn_engine* e, cudaStream_t stream) {
   e->vae.reset(new ldn_engine::VaeState());
   auto& V = *e->vae;
   const int C = V.ch * V.ch_mult.back();
-  const std::string p = "decoder.mid.attn_1";
-  V.attn_bias = V.arena.get<float>(C);
+  V.has_decoder = e->has(1, "decoder.conv_in.weight");
+  V.has_encoder = e->has(1, "encoder.conv_in.weight");
+  LDN_CHECK(V.has_decoder || V.has_encoder, "VAE weights hold neither decoder.* nor encoder.* tensors");
   // attn_bias = proj_out.weight @ v.bias + proj_out.bias  (tiny mat-vec on the device)
-  launch_small_linear(e->W(1, p + ".v.bias").f(), 1, C, e->W(1, p + ".proj_out.weight").b(),
-                      e->W(1, p + ".proj_out.bias").f(), C, false, false, V.attn_bias, stream);
+  if (V.has_decoder) {
+    const std::string p = "decoder.mid.attn_1";
+    V.attn_bias = V.arena.get<float>(C);
+    launch_small_linear(e->W(1, p + ".v.bias").f(), 1, C, e->W(1, p + ".proj_out.weight").b(),
+                        e->W(1, p + ".proj_out.bias").f(), C, false, false, V.attn_bias, stream);
+  }
+  if (V.has_encoder) {
+    const std::string p = "encoder.mid.attn_1";
+    V.attn_bias_enc = V.arena.get<float>(C);
+    launch_small_linear(e->W(1, p + ".v.bias").f(), 1, C, e->W(1, p + ".proj_out.weight").b(),
+                        e->W(1, p + ".proj_out.bias").f(), C, false, false, V.attn_bias_enc, stream);
+    const int z2 = 2 * V.zc;
+    V.quant_w = V.arena.get<float>(z2 * z2);
+    launch_convert_to_f32(e->W(1, "quant_conv.weight").p, 2, (size_t)z2 * z2, V.quant_w, stream);
+  }
   LDN_CUDA(cudaStreamSynchronize(stream));
   e->finalized[1] = true;
 }
@@ -93,6 +111,48 @@ struct VB {
       res = sC;
     }
     conv(p + ".conv2", p + ".conv2", sA, H, W, Cout, Cout, res, out);
+    return out;
+  }
+  // AttnBlock (single head of C channels over all h*w pixels; src/Attention/Attention.py:159-178)
+  const bf16* attn(const std::string& p, const bf16* x, int h, int w, int C, const float* attn_bias) {
+    const int N = h * w, T = B * N;
+    LDN_CHECK(N % 16 == 0, "VAE attention needs h*w to be a multiple of 16");
+    bf16* q = A.get<bf16>((size_t)T * C);
+    bf16* k = A.get<bf16>((size_t)T * C);
+    bf16* vt = A.get<bf16>((size_t)C * T);
+    bf16* o = A.get<bf16>((size_t)T * C);
+    bf16* S = A.get<bf16>((size_t)N * N);
+    bf16* out = A.get<bf16>((size_t)T * C);
+    gn(p + ".norm", x, C, N, p + ".norm", false, sA);
+    for (const char* nm : {"q", "k"}) {
+      GemmArgs a;
+      a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = e->W(1, p + "." + nm + ".weight").b(); a.M = T; a.N = C;
+      a.bias = e->W(1, p + "." + nm + ".bias").f(); a.out = (nm[0] == 'q') ? q : k; a.ldo = C;
+      gemm(p + "." + nm, a);
+    }
+    {
+      GemmArgs a;  // V^T = Wv * X^T (bias folded into proj_out)
+      a.A0 = e->W(1, p + ".v.weight").b(); a.lda0 = C; a.K0 = C; a.Wt = sA; a.M = C; a.N = T; a.out = vt; a.ldo = T;
+      gemm(p + ".vt", a);
+    }
+    const float scale = 1.0f / sqrtf((float)C);
+    for (int b = 0; b < B; ++b) {
+      GemmArgs s;
+      s.A0 = q + (size_t)b * N * C; s.lda0 = C; s.K0 = C; s.Wt = k + (size_t)b * N * C; s.M = N; s.N = N;
+      s.out = S; s.ldo = N;
+      gemm(p + ".scores", s);
+      bf16* Sp = S;
+      add(p + ".softmax", [=](cudaStream_t st) { launch_softmax_rows(Sp, N, Sp, N, N, N, scale, st); });
+      GemmArgs pv;
+      pv.A0 = S; pv.lda0 = N; pv.K0 = N; pv.Wt = vt + (size_t)b * N; pv.M = N; pv.N = C; pv.out = o + (size_t)b * N * C;
+      pv.ldo = C;
+      pv.wt_ld = T;  // V^T rows are T apart: describe the weight operand with its true leading dimension
+      gemm(p + ".pv", pv);
+    }
+    GemmArgs po;
+    po.A0 = o; po.lda0 = C; po.K0 = C; po.Wt = e->W(1, p + ".proj_out.weight").b(); po.M = T; po.N = C;
+    po.bias = attn_bias; po.residual = x; po.ldr = C; po.out = out; po.ldo = C;
+    gemm(p + ".proj_out", po);
     return out;
   }
 };
@@ -153,50 +213,7 @@ static Program* build_vae_program(ldn_engine* e, int B, int h, int w) {
     vb.add("decoder.conv_in", [=](cudaStream_t st) { launch_conv_in(zq, nullptr, wt, bias, B, h, w, zc, C, o, st); });
   }
   const bf16* x = vb.resnet("decoder.mid.block_1", hcur, h, w, C, C);
-  // ---- mid attention
-  {
-    const std::string p = "decoder.mid.attn_1";
-    const int N = h * w, T = B * N;
-    LDN_CHECK(N % 16 == 0, "VAE attention needs h*w to be a multiple of 16");
-    bf16* q = A.get<bf16>((size_t)T * C);
-    bf16* k = A.get<bf16>((size_t)T * C);
-    bf16* vt = A.get<bf16>((size_t)C * T);
-    bf16* o = A.get<bf16>((size_t)T * C);
-    bf16* S = A.get<bf16>((size_t)N * N);
-    bf16* out = A.get<bf16>((size_t)T * C);
-    vb.gn(p + ".norm", x, C, N, p + ".norm", false, vb.sA);
-    for (const char* nm : {"q", "k"}) {
-      GemmArgs a;
-      a.A0 = vb.sA; a.lda0 = C; a.K0 = C; a.Wt = e->W(1, p + "." + nm + ".weight").b(); a.M = T; a.N = C;
-      a.bias = e->W(1, p + "." + nm + ".bias").f(); a.out = (nm[0] == 'q') ? q : k; a.ldo = C;
-      vb.gemm(p + "." + nm, a);
-    }
-    {
-      GemmArgs a;  // V^T = Wv * X^T (bias folded into proj_out)
-      a.A0 = e->W(1, p + ".v.weight").b(); a.lda0 = C; a.K0 = C; a.Wt = vb.sA; a.M = C; a.N = T; a.out = vt; a.ldo = T;
-      vb.gemm(p + ".vt", a);
-    }
-    const float scale = 1.0f / sqrtf((float)C);
-    for (int b = 0; b < B; ++b) {
-      GemmArgs s;
-      s.A0 = q + (size_t)b * N * C; s.lda0 = C; s.K0 = C; s.Wt = k + (size_t)b * N * C; s.M = N; s.N = N;
-      s.out = S; s.ldo = N;
-      vb.gemm(p + ".scores", s);
-      bf16* Sp = S;
-      vb.add(p + ".softmax", [=](cudaStream_t st) { launch_softmax_rows(Sp, N, Sp, N, N, N, scale, st); });
-      GemmArgs pv;
-      pv.A0 = S; pv.lda0 = N; pv.K0 = N; pv.Wt = vt + (size_t)b * N; pv.M = N; pv.N = C; pv.out = o + (size_t)b * N * C;
-      pv.ldo = C;
-      // V^T rows are T apart: describe the weight operand with its true leading dimension
-      pv.wt_ld = T;
-      vb.gemm(p + ".pv", pv);
-    }
-    GemmArgs po;
-    po.A0 = o; po.lda0 = C; po.K0 = C; po.Wt = e->W(1, p + ".proj_out.weight").b(); po.M = T; po.N = C;
-    po.bias = V.attn_bias; po.residual = x; po.ldr = C; po.out = out; po.ldo = C;
-    vb.gemm(p + ".proj_out", po);
-    x = out;
-  }
+  x = vb.attn("decoder.mid.attn_1", x, h, w, C, V.attn_bias);
   x = vb.resnet("decoder.mid.block_2", x, h, w, C, C);
   int hh = h, ww = w, c = C;
   for (int lvl = nlev - 1; lvl >= 0; --lvl) {
@@ -230,8 +247,112 @@ static Program* build_vae_program(ldn_engine* e, int B, int h, int w) {
   return prog.release();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Encoder (VAE.encode -> AutoencodingEngine.encode -> Encoder.forward; VariationalAE.py:725-760, 148-172, 377-413).
+// Input: fp32 NCHW [B, 3, H, W] already mapped to [-1, 1] (process_input); output: Gaussian moments fp32 NCHW
+// [B, 8, H/8, W/8] (mean | logvar) after quant_conv. The reparameterised sample stays with the host (torch RNG).
+static Program* build_vae_enc_program(ldn_engine* e, int B, int H, int W) {
+  auto& V = *e->vae;
+  std::unique_ptr<Program> prog(new Program());
+  V.program_arenas.emplace_back(new Arena());
+  Arena& A = *V.program_arenas.back();
+  prog->arena = &A;
+  VB vb{e, V, *prog, A, B};
+  const int nlev = (int)V.ch_mult.size();
+  size_t max_act = 0, max_col = 0;
+  {
+    int hh = H, ww = W, c = V.ch;
+    for (int lvl = 0; lvl < nlev; ++lvl) {
+      const int cout = V.ch * V.ch_mult[lvl];
+      max_act = std::max(max_act, (size_t)B * hh * ww * std::max(c, cout));
+      c = cout;
+      if (lvl != nlev - 1) {
+        hh /= 2;
+        ww /= 2;
+        max_col = std::max(max_col, (size_t)B * hh * ww * 9 * c);
+      }
+    }
+  }
+  vb.sA = A.get<bf16>(max_act);
+  vb.sB = A.get<bf16>(max_act);
+  vb.sC = A.get<bf16>(max_act);
+  bf16* col = A.get<bf16>(std::max<size_t>(max_col, 16));
+  vb.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B), true));
+  prog->io_elems = (size_t)B * 3 * H * W;
+  prog->in_x = A.get<float>(prog->io_elems);
+
+  int hh = H, ww = W, c = V.ch;
+  bf16* h0 = A.get<bf16>((size_t)B * H * W * c);
+  {
+    const float* x = prog->in_x;
+    const bf16* wt = e->W(1, "encoder.conv_in.weight").b();
+    const float* bias = e->W(1, "encoder.conv_in.bias").f();
+    const int cc = c;
+    vb.add("encoder.conv_in", [=](cudaStream_t st) { launch_conv_in(x, nullptr, wt, bias, B, H, W, 3, cc, h0, st); });
+  }
+  const bf16* x = h0;
+  for (int lvl = 0; lvl < nlev; ++lvl) {
+    const int cout = V.ch * V.ch_mult[lvl];
+    for (int i = 0; i < V.num_res; ++i) {
+      x = vb.resnet("encoder.down." + std::to_string(lvl) + ".block." + std::to_string(i), x, hh, ww, c, cout);
+      c = cout;
+    }
+    if (lvl != nlev - 1) {
+      const std::string p = "encoder.down." + std::to_string(lvl) + ".downsample.conv";
+      const int ho = hh / 2, wo = ww / 2, h1 = hh, w1 = ww, cc = c;
+      const bf16* src = x;
+      vb.add(p + ".gather", [=](cudaStream_t st) { launch_im2col_s2(src, B, h1, w1, cc, col, st, 0); });
+      bf16* o = A.get<bf16>((size_t)B * ho * wo * c);
+      GemmArgs a;
+      a.A0 = col; a.lda0 = 9LL * c; a.K0 = 9 * c; a.Wt = e->W(1, p + ".weight").b(); a.M = B * ho * wo; a.N = c;
+      a.bias = e->W(1, p + ".bias").f(); a.out = o; a.ldo = c;
+      vb.gemm(p, a);
+      x = o;
+      hh = ho;
+      ww = wo;
+    }
+  }
+  x = vb.resnet("encoder.mid.block_1", x, hh, ww, c, c);
+  x = vb.attn("encoder.mid.attn_1", x, hh, ww, c, V.attn_bias_enc);
+  x = vb.resnet("encoder.mid.block_2", x, hh, ww, c, c);
+  vb.gn("encoder.norm_out", x, c, hh * ww, "encoder.norm_out", true, vb.sA);
+  const int z2 = 2 * V.zc;
+  prog->out = A.get<float>((size_t)B * z2 * hh * ww);
+  {
+    float* acc16 = A.get<float>((size_t)B * hh * ww * 16);
+    GemmArgs a;
+    a.conv = true; a.A0 = vb.sA; a.B = B; a.H = hh; a.W = ww; a.Cin = c;
+    a.Wt = e->W(1, "encoder.conv_out.weight").b(); a.N = 16; a.wt_rows = z2; a.BN = 16;
+    a.out_f32 = acc16; a.ldo = 16;
+    vb.gemm("encoder.conv_out", a);
+    const float* bc = e->W(1, "encoder.conv_out.bias").f();
+    const float* wq = V.quant_w;
+    const float* bq = e->W(1, "quant_conv.bias").f();
+    float* out = prog->out;
+    const int HW = hh * ww;
+    vb.add("quant_conv", [=](cudaStream_t st) { launch_vae_moments_finish(acc16, bc, wq, bq, B, HW, z2, out, st); });
+  }
+  return prog.release();
+}
+
+void vae_encode(ldn_engine* e, const float* pixels, float* moments, int B, int H, int W, cudaStream_t stream) {
+  auto& V = *e->vae;
+  LDN_CHECK(V.has_encoder, "ldn_vae_encode: the loaded VAE weights hold no encoder.* tensors");
+  LDN_CHECK(H >= 8 && W >= 8, "ldn_vae_encode: image smaller than one latent pixel");
+  auto key = std::make_tuple(B, H, W);
+  auto it = V.enc_programs.find(key);
+  if (it == V.enc_programs.end())
+    it = V.enc_programs.emplace(key, std::unique_ptr<Program>(build_vae_enc_program(e, B, H, W))).first;
+  Program& P = *it->second;
+  LDN_CUDA(cudaMemcpyAsync(P.in_x, pixels, P.io_elems * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  run_program(P, e->cfg.use_graph != 0, stream);
+  const size_t n = (size_t)B * 2 * V.zc * (H / 8) * (W / 8);
+  LDN_CUDA(cudaMemcpyAsync(moments, P.out, n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+}
+
 void vae_decode(ldn_engine* e, const float* z, float* rgb, int B, int h, int w, cudaStream_t stream) {
   auto& V = *e->vae;
+  LDN_CHECK(V.has_decoder, "ldn_vae_decode: the loaded VAE weights hold no decoder.* tensors");
   auto key = std::make_tuple(B, h, w);
   auto it = V.programs.find(key);
   if (it == V.programs.end()) it = V.programs.emplace(key, std::unique_ptr<Program>(build_vae_program(e, B, h, w))).first;

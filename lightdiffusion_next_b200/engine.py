@@ -131,6 +131,26 @@ class Engine:
             L.check(self.lib.ldn_vae_decode(self.h, z.data_ptr(), out.data_ptr(), B, h, w, L.cur_stream()))
         return out
 
+    def vae_encode_moments(self, pixels: torch.Tensor) -> torch.Tensor:
+        """pixels [B,H,W,3] fp32 in [0,1] -> Gaussian moments [B,8,H/8,W/8] fp32 on the device (quant_conv(Encoder(2x-1))).
+        Like the reference (whose vae_encode_crop_pixels is a no-op, VariationalAE.py:677-688) nothing is cropped."""
+        x = (pixels[..., :3].to(self.device, torch.float32).movedim(-1, 1) * 2.0 - 1.0).contiguous()
+        B, _, H, W = x.shape
+        out = torch.empty(B, 8, H // 8, W // 8, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_vae_encode(self.h, x.data_ptr(), out.data_ptr(), B, H, W, L.cur_stream()))
+        return out
+
+    def vae_encode(self, pixels: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """VAE.encode semantics (VariationalAE.py:725-760): a posterior SAMPLE, fp32 on the CPU. The noise is drawn like
+        DiagonalGaussianDistribution.sample does -- torch.randn(mean.shape) from the global CPU generator -- unless given."""
+        m = self.vae_encode_moments(pixels)
+        mean, logvar = m.chunk(2, dim=1)
+        if noise is None:
+            noise = torch.randn(mean.shape)
+        std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+        return (mean + std * noise.to(m.device)).float().cpu()
+
     def clip_encode(self, ids: torch.Tensor):
         """ids [S,77] int64 -> (penultimate-layer output after final LN, last-layer output after final LN)."""
         ids = ids.to(self.device, torch.int64).contiguous()

@@ -51,6 +51,19 @@ class Pipeline:
         """latents (already divided by 0.18215, as KSampler returns them) -> [B,H,W,3] fp32 in [0,1] on the CPU."""
         return self.e.vae_decode(samples).cpu()
 
+    # ---------------------------------------------------------------- VAEEncode + img2img (VariationalAE.py:787-801)
+    def encode_image(self, pixels: torch.Tensor) -> torch.Tensor:
+        """pixels [B,H,W,3] in [0,1] -> latent samples as VAEEncode returns them (unscaled; KSampler applies 0.18215)."""
+        return self.e.vae_encode(pixels)
+
+    def img2img(self, pixels: torch.Tensor, positive: torch.Tensor, negative: torch.Tensor, seed: int = 0, steps: int = 20,
+                cfg: float = 7.0, denoise: float = 0.6, sampler_name: str = "dpmpp_2m_cfgpp", scheduler: str = "karras",
+                enable_multiscale: bool = True) -> torch.Tensor:
+        """Encode -> partial-denoise KSampler pass (the schedule tail of steps/denoise, sampling.py:655-675) -> latents."""
+        latent = {"samples": self.encode_image(pixels)}
+        return S.sample(self.e, seed, steps, cfg, sampler_name, scheduler, positive, negative, latent, denoise=denoise,
+                        enable_multiscale=enable_multiscale)[0]["samples"]
+
     def __call__(self, tokens, negative_tokens=None, width: int = 512, height: int = 512, batch: int = 1, seed: int = 0,
                  steps: int = 20, cfg: float = 7.0, sampler_name: str = "dpmpp_2m_cfgpp", scheduler: str = "karras"):
         pos = self.encode(tokens)

@@ -148,6 +148,45 @@ def vae_decoder_shapes(ch: int = 128, ch_mult=(1, 2, 4, 4), num_res: int = 2, z:
     return s
 
 
+def vae_encoder_shapes(ch: int = 128, ch_mult=(1, 2, 4, 4), num_res: int = 2, z: int = 4) -> Dict[str, Tuple[int, ...]]:
+    """State-dict layout of the SD1.5 VAE encoder side + quant_conv (Encoder, src/AutoEncoders/VariationalAE.py:257-413)."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(p, o, i, k):
+        s[p + ".weight"] = (o, i, k, k)
+        s[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        s[p + ".weight"] = s[p + ".bias"] = (c,)
+
+    def res(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cout, cin, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".nin_shortcut", cout, cin, 1)
+
+    conv("encoder.conv_in", ch, 3, 3)
+    c = ch
+    for lvl in range(len(ch_mult)):
+        co = ch * ch_mult[lvl]
+        for i in range(num_res):
+            res(f"encoder.down.{lvl}.block.{i}", c, co)
+            c = co
+        if lvl != len(ch_mult) - 1:
+            conv(f"encoder.down.{lvl}.downsample.conv", c, c, 3)
+    res("encoder.mid.block_1", c, c)
+    norm("encoder.mid.attn_1.norm", c)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{n}", c, c, 1)
+    res("encoder.mid.block_2", c, c)
+    norm("encoder.norm_out", c)
+    conv("encoder.conv_out", 2 * z, c, 3)
+    conv("quant_conv", 2 * z, 2 * z, 1)
+    return s
+
+
 def clip_shapes(width: int = 768, mlp: int = 3072, layers: int = 12, vocab: int = 49408, positions: int = 77) -> Dict[str, Tuple[int, ...]]:
     """State-dict layout of CLIP-L's text model (keys below `text_model.`; CLIPTextModel_, src/clip/CLIPTextModel.py:3-107)."""
     s: Dict[str, Tuple[int, ...]] = {"embeddings.token_embedding.weight": (vocab, width),

@@ -522,6 +522,84 @@ def vae_decode(sd: Dict[str, Tensor], z: Tensor, cfg=VAE_CFG) -> Tensor:
     return torch.clamp((h + 1.0) / 2.0, min=0.0, max=1.0).movedim(1, -1)
 
 
+def vae_encoder_param_shapes(cfg=VAE_CFG) -> Dict[str, Tuple[int, ...]]:
+    """Encoder-side state-dict keys (without the 'first_stage_model.' prefix) -> shapes
+    (Encoder.__init__ src/AutoEncoders/VariationalAE.py:260-356; quant_conv AutoencodingEngine :115-126)."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(p, o, i, k):
+        s[p + ".weight"] = (o, i, k, k)
+        s[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        s[p + ".weight"] = (c,)
+        s[p + ".bias"] = (c,)
+
+    def res(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cout, cin, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".nin_shortcut", cout, cin, 1)
+
+    ch, mult, nres, zc = cfg["ch"], cfg["ch_mult"], cfg["num_res_blocks"], cfg["z_channels"]
+    conv("encoder.conv_in", ch, 3, 3)
+    block_in = ch
+    for lvl in range(len(mult)):
+        block_out = ch * mult[lvl]
+        for i in range(nres):
+            res(f"encoder.down.{lvl}.block.{i}", block_in, block_out)
+            block_in = block_out
+        if lvl != len(mult) - 1:
+            conv(f"encoder.down.{lvl}.downsample.conv", block_in, block_in, 3)
+    res("encoder.mid.block_1", block_in, block_in)
+    norm("encoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{n}", block_in, block_in, 1)
+    res("encoder.mid.block_2", block_in, block_in)
+    norm("encoder.norm_out", block_in)
+    conv("encoder.conv_out", 2 * zc, block_in, 3)
+    conv("quant_conv", 2 * zc, 2 * zc, 1)
+    return s
+
+
+def vae_encode_moments(sd: Dict[str, Tensor], pixels: Tensor, cfg=VAE_CFG) -> Tensor:
+    """pixels [B,H,W,3] fp32 in [0,1] -> Gaussian moments [B,8,H/8,W/8] fp32 (mean | logvar), i.e. quant_conv(Encoder(2x-1)).
+    VAE.encode (VariationalAE.py:725-760) moves channels first and applies process_input (2x-1). NOTE: the reference's
+    vae_encode_crop_pixels (:677-688) computes the cropped sizes and discards them -- pixels are NOT cropped; odd sizes
+    are absorbed by the (0,1,0,1) pad + stride-2 convs (floor division at every level);
+    Encoder.forward :377-413; Downsample pads (0,1,0,1) then conv stride 2 pad 0 (:224-254);
+    AutoencodingEngine.encode :148-172 applies quant_conv, then DiagonalGaussianRegularizer samples
+    mean + exp(0.5*clamp(logvar,-30,20)) * randn (:70-100) -- the stochastic part stays on the host."""
+    mult, nres = cfg["ch_mult"], cfg["num_res_blocks"]
+    B, H, W, _ = pixels.shape
+    x = pixels[..., :3].movedim(-1, 1).float() * 2.0 - 1.0
+    h = _conv(sd, "encoder.conv_in", x)
+    for lvl in range(len(mult)):
+        for i in range(nres):
+            h = _vae_res(sd, f"encoder.down.{lvl}.block.{i}", h)
+        if lvl != len(mult) - 1:
+            h = _conv(sd, f"encoder.down.{lvl}.downsample.conv", F.pad(h, (0, 1, 0, 1)), stride=2, padding=0)
+    h = _vae_res(sd, "encoder.mid.block_1", h)
+    p = "encoder.mid.attn_1"
+    n = _gn(sd, p + ".norm", h, 1e-6)
+    q, k, v = (_conv(sd, f"{p}.{t}", n, padding=0) for t in ("q", "k", "v"))
+    b, c, hh, ww = q.shape
+    q, k, v = (t.reshape(b, c, hh * ww).transpose(1, 2) for t in (q, k, v))
+    a = attention(q, k, v, heads=1).transpose(1, 2).reshape(b, c, hh, ww)
+    h = h + _conv(sd, p + ".proj_out", a, padding=0)
+    h = _vae_res(sd, "encoder.mid.block_2", h)
+    h = _conv(sd, "encoder.conv_out", F.silu(_gn(sd, "encoder.norm_out", h, 1e-6)))
+    return _conv(sd, "quant_conv", h, padding=0)
+
+
+def vae_sample_posterior(moments: Tensor, noise: Tensor) -> Tensor:
+    """DiagonalGaussianDistribution.sample (VariationalAE.py:28-67): mean + exp(0.5 * clamp(logvar, -30, 20)) * noise."""
+    mean, logvar = moments.chunk(2, dim=1)
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # CLIP-L text encoder  (CLIPTextModel_.forward src/clip/CLIPTextModel.py:51-107; CLIPLayer / CLIPAttention / CLIPMLP
 # src/clip/Clip.py:14-180; config include/clip/sd1_clip_config.json: 12 layers, 768 wide, 12 heads, quick_gelu)

@@ -15,7 +15,7 @@ def test_safetensors_roundtrip_and_prefix_split(tmp_path):
         "model.diffusion_model.out.2.bias": torch.randn(4, generator=g).half(),
         "first_stage_model.decoder.conv_in.weight": torch.randn(8, 4, 3, 3, generator=g).half(),
         "first_stage_model.post_quant_conv.bias": torch.randn(4, generator=g).half(),
-        "first_stage_model.encoder.conv_in.weight": torch.randn(8, 3, 3, 3, generator=g).half(),  # not on the decode path
+        "first_stage_model.encoder.conv_in.weight": torch.randn(8, 3, 3, 3, generator=g).half(),  # encoder side (img2img)
         # old CLIP layout (no `text_model.`), renamed like SD15.process_clip_state_dict
         "cond_stage_model.transformer.embeddings.position_embedding.weight": torch.randn(77, 8, generator=g).half(),
         "cond_stage_model.transformer.text_model.final_layer_norm.bias": torch.randn(8, generator=g).half(),
@@ -28,7 +28,7 @@ def test_safetensors_roundtrip_and_prefix_split(tmp_path):
     assert set(loaded) == set(sd)
     parts = C.split_sd15_checkpoint(loaded, strict=False)
     assert set(parts["unet"]) == {"time_embed.0.weight", "out.2.bias"}
-    assert set(parts["vae"]) == {"decoder.conv_in.weight", "post_quant_conv.bias"}
+    assert set(parts["vae"]) == {"decoder.conv_in.weight", "post_quant_conv.bias", "encoder.conv_in.weight"}
     assert set(parts["clip"]) == {"embeddings.position_embedding.weight", "final_layer_norm.bias"}
     assert torch.equal(parts["unet"]["time_embed.0.weight"], sd["model.diffusion_model.time_embed.0.weight"])
     # pickled container with a top-level "state_dict"
@@ -67,6 +67,14 @@ def test_strict_layout_validation():
         C.split_sd15_checkpoint(sd3)
     msg = str(ei.value)
     assert "middle_block.1.transformer_blocks.0.attn2.to_k.weight" in msg and "decoder.conv_out.weight" in msg
+    # with the encoder side present it is validated too (img2img needs it); decode-only VAE files stay valid
+    sd4 = dict(sd)
+    for k, shp in synth.vae_encoder_shapes().items():
+        sd4[C.VAE_PREFIX + k] = torch.empty(shp, dtype=torch.float16, device="meta")
+    assert len(C.split_sd15_checkpoint(sd4)["vae"]) == len(synth.vae_decoder_shapes()) + len(synth.vae_encoder_shapes())
+    del sd4[C.VAE_PREFIX + "quant_conv.weight"]
+    with pytest.raises(ValueError, match="quant_conv.weight"):
+        C.split_sd15_checkpoint(sd4)
     # a UNet-only file loads (other parts empty)
     only = {k: v for k, v in sd.items() if k.startswith(C.UNET_PREFIX)}
     p = C.split_sd15_checkpoint(only)

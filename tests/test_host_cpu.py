@@ -151,3 +151,4 @@ def test_synth_shape_tables_match_oracle():
     from lightdiffusion_next_b200 import synth
     assert synth.vae_decoder_shapes() == O.vae_decoder_param_shapes()
     assert synth.clip_shapes() == O.clip_param_shapes()
+    assert synth.vae_encoder_shapes() == O.vae_encoder_param_shapes()

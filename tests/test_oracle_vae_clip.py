@@ -37,3 +37,21 @@ def test_clip_encode_matches_reference():
     z = (pen[0] - pen_empty[0]) * w + pen_empty[0]
     assert rel(z[None], g["weighted_cond"]) < 2e-5
     assert float((g["weighted_weights"] != 1).sum()) >= 2
+
+
+def test_oracle_vae_encoder_matches_reference_golden():
+    """oracle.vae_encode_moments / vae_sample_posterior vs the reference Encoder + quant_conv + regulariser
+    (fixture: tests/golden/make_golden_vae_enc.py; b has a width that is not a multiple of 8)."""
+    import os
+    import torch
+    from oracle import sd15_oracle as O
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vae_enc_small.pt"))
+    sd = O.synth_state_dict(O.vae_encoder_param_shapes(), seed=2468)
+    for name in ("a", "b"):
+        m = O.vae_encode_moments(sd, gold[f"pixels_{name}"])
+        ref = gold[f"moments_{name}"]
+        assert m.shape == ref.shape
+        assert ((m - ref).norm() / ref.norm()).item() < 1e-4
+        torch.manual_seed(int(gold["sample_seed"]))
+        lat = O.vae_sample_posterior(m, torch.randn(ref[:, :4].shape))
+        assert ((lat - gold[f"latent_{name}"]).norm() / gold[f"latent_{name}"].norm()).item() < 1e-4
