@@ -197,6 +197,7 @@ void launch_conv_out(const bf16* h, const bf16* Wt, const float* bias, const flo
 void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);
 // stride-2 3x3 pad-1 im2col gather: [B,H,W,C] -> [B*(H/2)*(W/2), 9*C]
 void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream, int pad_before = 1);
+void launch_vae_rgb_finish(const float* acc16, const float* bias, size_t npix, int cout, float* out, cudaStream_t stream);
 void launch_vae_moments_finish(const float* acc16, const float* bc, const float* Wq, const float* bq, int B, int HW,
                                int zc2, float* out, cudaStream_t stream);
 // dst[c, b*nk_pad + k] = src[c, b*N + k]: V^T re-laid with 16-byte aligned per-batch column offsets

@@ -391,6 +391,27 @@ void launch_vae_moments_finish(const float* acc16, const float* bc, const float*
   LDN_CUDA(cudaGetLastError());
 }
 
+// VAE decoder tail: rgb[pix, o] = clamp((acc16[pix, o] + bias[o] + 1) / 2, 0, 1), o < 3 -- the decoder's conv_out (128 -> 3,
+// run as a 16-column tensor-core conv into fp32 scratch) + process_output (VariationalAE.py:602-604), NHWC fp32 out.
+__global__ void vae_rgb_finish_kernel(const float* __restrict__ acc16, const float* __restrict__ bias, size_t npix,
+                                      int cout, float* __restrict__ out) {
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(acc16 + pix * 16);
+    const float v[4] = {a.x, a.y, a.z, a.w};
+    for (int o = 0; o < cout; ++o) {
+      const float y = (v[o] + bias[o] + 1.0f) * 0.5f;
+      out[pix * cout + o] = fminf(fmaxf(y, 0.f), 1.f);
+    }
+  }
+}
+void launch_vae_rgb_finish(const float* acc16, const float* bias, size_t npix, int cout, float* out, cudaStream_t stream) {
+  LDN_CHECK(cout <= 4, "vae_rgb_finish: at most 4 channels");
+  int blocks = (int)((npix + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  vae_rgb_finish_kernel<<<blocks, 256, 0, stream>>>(acc16, bias, npix, cout, out);
+  LDN_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ nearest 2x upsample (F.interpolate nearest, ResBlock.py:135)
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ out) {
   const int nvec = C >> 3;

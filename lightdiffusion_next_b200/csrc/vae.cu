@@ -79,7 +79,10 @@ struct VB {
   }
   void gemm(const std::string& name, const GemmArgs& a) {
     GemmPlan plan = make_gemm_plan(a);
-    add(name, [plan](cudaStream_t st) { launch_gemm(plan, st); });
+    const long long Mm = a.conv ? (long long)a.B * a.H * a.W : a.M;
+    const long long Kk = a.conv ? 9LL * a.Cin : (long long)a.K0 + a.K1;
+    add(name + " [M=" + std::to_string(Mm) + " N=" + std::to_string(a.N) + " K=" + std::to_string(Kk) + "]",
+        [plan](cudaStream_t st) { launch_gemm(plan, st); });
   }
   void gn(const std::string& name, const bf16* x, int C, int HW, const std::string& wp, bool silu, bf16* out) {
     const float* g = e->W(1, wp + ".weight").f();
@@ -237,12 +240,24 @@ static Program* build_vae_program(ldn_engine* e, int B, int h, int w) {
   }
   vb.gn("decoder.norm_out", x, c, hh * ww, "decoder.norm_out", true, vb.sA);
   {
-    const bf16* src = vb.sA;
-    const bf16* wt = e->W(1, "decoder.conv_out.weight").b();
     const float* bias = e->W(1, "decoder.conv_out.bias").f();
     float* out = prog->out;
-    const int H8 = hh, W8 = ww, cin = c;
-    vb.add("decoder.conv_out", [=](cudaStream_t st) { launch_conv_out_rgb(src, wt, bias, B, H8, W8, cin, out, st); });
+    const int H8 = hh, W8 = ww, cin = c, cout = V.out_ch;
+    if (cin % 64 == 0 && cout <= 4) {
+      // tensor-core path: 3 output channels padded to one 16-column MMA (weight rows past 3 read as zero), fp32 scratch
+      float* acc16 = A.get<float>((size_t)B * H8 * W8 * 16);
+      GemmArgs a;
+      a.conv = true; a.A0 = vb.sA; a.B = B; a.H = H8; a.W = W8; a.Cin = cin;
+      a.Wt = e->W(1, "decoder.conv_out.weight").b(); a.N = 16; a.wt_rows = cout; a.BN = 16;
+      a.out_f32 = acc16; a.ldo = 16;
+      vb.gemm("decoder.conv_out", a);
+      const size_t npix = (size_t)B * H8 * W8;
+      vb.add("decoder.rgb", [=](cudaStream_t st) { launch_vae_rgb_finish(acc16, bias, npix, cout, out, st); });
+    } else {
+      const bf16* src = vb.sA;
+      const bf16* wt = e->W(1, "decoder.conv_out.weight").b();
+      vb.add("decoder.conv_out", [=](cudaStream_t st) { launch_conv_out_rgb(src, wt, bias, B, H8, W8, cin, out, st); });
+    }
   }
   return prog.release();
 }
