@@ -592,9 +592,81 @@ __global__ void softmax_rows_kernel(const bf16* __restrict__ in, long long ld_in
   for (int c = threadIdx.x; c < cols; c += blockDim.x)
     dst[c] = __float2bfloat16(__expf((__bfloat162float(src[c]) - mx) * scale) * inv);
 }
+// Register-resident variant: one block per row, the row is read once with 16-byte loads (MAXV per thread), reduced, and
+// written once -- 2 bytes read + 2 bytes written per element instead of three scalar passes.
+template <int MAXV>
+__global__ void __launch_bounds__(512) softmax_rows_vec_kernel(const bf16* __restrict__ in, long long ld_in,
+                                                               bf16* __restrict__ out, long long ld_out, int cols,
+                                                               float scale) {
+  const bf16* src = in + (size_t)blockIdx.x * ld_in;
+  bf16* dst = out + (size_t)blockIdx.x * ld_out;
+  __shared__ float red[32];
+  const int nvec = cols >> 3;
+  const float sl = scale * 1.4426950408889634f;
+  float v[MAXV][8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = threadIdx.x + k * 512;
+    if (vi < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src + (size_t)vi * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[k][2 * i] = bf16_lo(w[i]);
+        v[k][2 * i + 1] = bf16_hi(w[i]);
+        mx = fmaxf(mx, fmaxf(v[k][2 * i], v[k][2 * i + 1]));
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < 16; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  const float moff = mx * sl;
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = threadIdx.x + k * 512;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[k][i] = exp2f(fmaf(v[k][i], sl, -moff));
+        sum += v[k][i];
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < 16; ++w) sum += red[w];
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = threadIdx.x + k * 512;
+    if (vi < nvec) {
+      uint4 o;
+      o.x = pack_bf16x2(v[k][0] * inv, v[k][1] * inv);
+      o.y = pack_bf16x2(v[k][2] * inv, v[k][3] * inv);
+      o.z = pack_bf16x2(v[k][4] * inv, v[k][5] * inv);
+      o.w = pack_bf16x2(v[k][6] * inv, v[k][7] * inv);
+      *reinterpret_cast<uint4*>(dst + (size_t)vi * 8) = o;
+    }
+  }
+}
 void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
                          cudaStream_t stream) {
-  softmax_rows_kernel<<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+  const bool vec_ok = cols % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec_ok && cols <= 512 * 8 * 4)
+    softmax_rows_vec_kernel<4><<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+  else if (vec_ok && cols <= 512 * 8 * 16)
+    softmax_rows_vec_kernel<16><<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+  else
+    softmax_rows_kernel<<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
   LDN_CUDA(cudaGetLastError());
 }
 
