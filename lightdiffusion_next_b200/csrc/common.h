@@ -37,6 +37,7 @@ CUtensorMap make_tmap_nhwc(const bf16* base, int B, int H, int W, int C, int bb,
 // ---- GEMM / implicit-GEMM conv3x3 on tcgen05 (gemm.cu)
 struct GemmParams {
   CUtensorMap tmA0, tmA1, tmB;
+  CUtensorMap tmB2;  // CTA-pair kernel: same matrix as tmB with a box of BN/2 rows (each CTA of the pair loads half the B tile)
   int M, N;          // logical output rows / weight rows
   int BN;            // N tile (multiple of 16, <= 256)
   int num_k_chunks;  // 64-wide K chunks in total
@@ -75,6 +76,8 @@ struct GemmPlan {
   int smem_bytes;
   bool persistent = false;
   int pgrid = 0;  // CTAs of the persistent kernel (<= SM count)
+  bool pair = false;  // CTA-pair kernel (gemm_pair.cu); pgrid is then an even CTA count
+  int pair_smem_bytes = 0;
 };
 
 struct GemmArgs {
@@ -113,6 +116,7 @@ struct GemmArgs {
 
 GemmPlan make_gemm_plan(const GemmArgs& a);
 void launch_gemm(const GemmPlan& plan, cudaStream_t stream);
+void launch_gemm_pair(const GemmPlan& plan, cudaStream_t stream);
 
 // ---- attention (attention.cu)
 struct AttnParams {

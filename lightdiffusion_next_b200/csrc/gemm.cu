@@ -21,218 +21,11 @@
 //               GEGLU (value * gelu_erf(gate)), bf16 (or fp32) store.
 #include "common.h"
 #include "ptx.cuh"
+#include "gemm_epilogue.cuh"
 
 #include <cstdlib>
 
 namespace ldn {
-
-static constexpr int kBM = 128;
-static constexpr int kBK = 64;
-static constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-
-// GELU(x) = x * Phi(x) with the exact-erf definition the reference uses (F.gelu, src/cond/Activation.py:31).
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 output rounding): 2 MUFU + ~12 FMA/ALU per value
-// instead of erff's ~40 instructions -- the GEGLU GEMMs (K = C only) are epilogue-bound, so this is their critical path.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = __expf(-z * z);        // exp(-x^2 / 2)
-  const float erf_abs = fmaf(-p, e, 1.0f);  // erf(|x| / sqrt(2))
-  const float phi = 0.5f * (1.0f + copysignf(erf_abs, x));
-  return x * phi;
-}
-
-// Two GELUs per instruction stream (FFMA2 / FMUL2): same A&S 7.1.26 arithmetic as gelu_erf, evaluated on a pair.
-// Returns a * gelu(g) element-wise.
-__device__ __forceinline__ float2 geglu2(float2 a, float2 g) {
-  const float2 ax = make_float2(fabsf(g.x), fabsf(g.y));
-  const float2 den = ffma2(ax, make_float2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f),
-                           make_float2(1.0f, 1.0f));
-  float2 t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
-  // negated polynomial: q = -(a1 t + a2 t^2 + ... + a5 t^5)
-  float2 q = ffma2(make_float2(-1.061405429f, -1.061405429f), t, make_float2(1.453152027f, 1.453152027f));
-  q = ffma2(q, t, make_float2(-1.421413741f, -1.421413741f));
-  q = ffma2(q, t, make_float2(0.284496736f, 0.284496736f));
-  q = ffma2(q, t, make_float2(-0.254829592f, -0.254829592f));
-  q = fmul2(q, t);
-  const float2 u = fmul2(fmul2(g, g), make_float2(-0.72134752044448170368f, -0.72134752044448170368f));  // -x^2/2 * log2(e)
-  float2 e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(u.x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(u.y));
-  const float2 erf_abs = ffma2(q, e, make_float2(1.0f, 1.0f));  // erf(|x| / sqrt(2))
-  const float2 phi = ffma2(make_float2(copysignf(erf_abs.x, g.x), copysignf(erf_abs.y, g.y)), make_float2(0.5f, 0.5f),
-                           make_float2(0.5f, 0.5f));
-  return fmul2(a, fmul2(g, phi));
-}
-
-// Drains one 128 x BN fp32 accumulator tile from TMEM (columns starting at t_lane) through the fused epilogue.
-// Executed by the 8 epilogue warps; `ehalf` selects which alternate 16-column chunks this warp handles.
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const int BN, const int n0, const long long out_row,
-                                                   const int batch, const uint32_t t_lane, const int ehalf,
-                                                   const int split_z) {
-
-    if (p.splits > 1) {
-      // split-K: raw fp32 partial tile; bias / residual are applied by splitk_reduce_kernel
-      float* wbase = p.ws + (long long)split_z * p.ws_split_stride;
-      for (int c = ehalf * 16; c < BN; c += 32) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + (uint32_t)c, v);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        if (out_row >= 0 && n < p.N) {
-          float4* op = reinterpret_cast<float4*>(wbase + out_row * p.N + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            op[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                __uint_as_float(v[4 * i + 3]));
-        }
-        __syncwarp();
-      }
-    } else if (p.epi == 0) {
-      for (int c = ehalf * 16; c < BN; c += 32) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + (uint32_t)c, v);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        if (out_row >= 0 && n < p.N) {
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(p.bias + n + i);
-            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-          }
-        }
-        if (p.rowbias) {
-          const float* rb = p.rowbias + (long long)batch * p.ld_rowbias + n;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(rb + i);
-            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-          }
-        }
-        if (p.act == 1) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = f[i] / (1.0f + __expf(-1.702f * f[i]));
-        }
-        if (p.residual) {
-          uint32_t w[8];
-          if (p.epi_opt & 1) {
-            ld_global_256(p.residual + out_row * p.ldr + n, w);  // one full 32-byte sector per thread
-          } else {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + n);
-            const uint4 r0 = rp[0], r1 = rp[1];
-            w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w; w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            f[2 * i] += bf16_lo(w[i]);
-            f[2 * i + 1] += bf16_hi(w[i]);
-          }
-        }
-        if (p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldo + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        } else if ((p.epi_opt & 1) && p.head_dim == 0) {
-          uint32_t o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-          st_global_256(p.out + out_row * p.ldo + n, o);
-        } else {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            int col = n + h * 8;
-            if (p.head_dim > 0) col = (col / p.head_dim) * p.head_slot + (col % p.head_dim);
-            uint4 ov;
-            ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
-            ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
-            ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
-            ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
-            *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + col) = ov;
-          }
-        }
-        }
-        __syncwarp();
-      }
-    } else {
-      // GEGLU: weight rows were interleaved at load time so that this tile holds BN/2 value columns followed
-      // by the BN/2 matching gate columns (Activation.py:30-31: x, gate = proj(x).chunk(2); x * gelu(gate)).
-      const int half = BN / 2;
-      const int o0 = n0 / 2;
-      for (int c = ehalf * 16; c < half; c += 32) {
-        uint32_t va[16], vg[16];
-        tmem_ld16(t_lane + (uint32_t)c, va);
-        tmem_ld16(t_lane + (uint32_t)(half + c), vg);
-        float ba[16], bg[16];  // bias vectors fetched while the TMEM loads are in flight
-        if (p.bias && (n0 + c) < p.N) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 x4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + i));
-            const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + half + c + i));
-            ba[i] = x4.x; ba[i + 1] = x4.y; ba[i + 2] = x4.z; ba[i + 3] = x4.w;
-            bg[i] = y4.x; bg[i + 1] = y4.y; bg[i + 2] = y4.z; bg[i + 3] = y4.w;
-          }
-        }
-        tmem_ld_wait();
-        if (out_row >= 0 && (n0 + c) < p.N) {
-        float f[16];
-#pragma unroll
-        if (!(p.epi_opt & 2)) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(va[i]);
-            float g = __uint_as_float(vg[i]);
-            if (p.bias) {
-              a += ba[i];
-              g += bg[i];
-            }
-            f[i] = a * gelu_erf(g);
-          }
-        } else
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float2 a = make_float2(__uint_as_float(va[i]), __uint_as_float(va[i + 1]));
-          float2 g = make_float2(__uint_as_float(vg[i]), __uint_as_float(vg[i + 1]));
-          if (p.bias) {
-            a = fadd2(a, make_float2(ba[i], ba[i + 1]));
-            g = fadd2(g, make_float2(bg[i], bg[i + 1]));
-          }
-          const float2 r2 = geglu2(a, g);
-          f[i] = r2.x;
-          f[i + 1] = r2.y;
-        }
-        if (p.epi_opt & 1) {
-          uint32_t o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-          st_global_256(p.out + out_row * p.ldo + o0 + c, o);
-        } else {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 ov;
-          ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
-          ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
-          ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
-          ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
-          *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + o0 + c + h * 8) = ov;
-        }
-        }
-        }
-        __syncwarp();
-      }
-    }
-}
 
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -613,8 +406,11 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
 
 // ----------------------------------------------------------------------------------- host side
 
-static int pick_bn(int N, bool geglu) {
+static int pick_bn(int N, bool geglu, long long m_tiles) {
   // Prefer tiles that divide N exactly (N in the UNet is 5*64*{1,2,4,8,...}); 160 wastes nothing for 320/640/1280.
+  // The widest MMA (N = 256) is the most efficient one (measured: 1.38 PFLOP/s against ~1.1 at 160 and ~0.9 at 128): take it
+  // whenever it divides N and still leaves at least two waves of tiles.
+  if (N % 256 == 0 && (N / 256) * m_tiles >= 2 * 148) return 256;
   if (geglu) {
     const int cands[] = {160, 128, 256, 192, 96, 64, 32};
     for (int c : cands)
@@ -634,7 +430,8 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   memset(&p, 0, sizeof(p));
   LDN_CHECK(a.Wt && a.A0 && (a.out || a.out_f32), "gemm: null operand");
   LDN_CHECK(a.N % 16 == 0, "gemm: N must be a multiple of 16");
-  int BN = a.BN ? a.BN : pick_bn(a.N, a.epi == 1);
+  const long long m_rows = a.conv ? (long long)a.B * a.H * a.W : a.M;
+  int BN = a.BN ? a.BN : pick_bn(a.N, a.epi == 1, (m_rows + kBM - 1) / kBM);
   if (a.epi == 1) LDN_CHECK(a.N % BN == 0 && BN % 32 == 0, "geglu: N must be a multiple of BN, BN of 32");
   LDN_CHECK(BN % 16 == 0 && BN >= 16 && BN <= 256, "gemm: bad BN");
   p.BN = BN;
@@ -761,6 +558,25 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
     const int total = (int)(plan.grid.x * plan.grid.y * plan.grid.z);
     plan.pgrid = total < 148 ? total : 148;
   }
+  // CTA-pair variant (gemm_pair.cu): 256 x BN tiles, each CTA loads half of the B tile
+  static const int pair_mode = getenv("LDN_GEMM_PAIR") ? atoi(getenv("LDN_GEMM_PAIR")) : 0;
+  // 1: every eligible GEMM; 2: only those that would otherwise run the one-tile-per-CTA kernel (long K: convs)
+  const bool pair_ok = BN >= 32 && BN % 16 == 0 && plan.grid.y >= 2 && !force_v1;
+  plan.pair = pair_ok && (pair_mode == 1 || (pair_mode == 2 && !plan.persistent) || (pair_mode == 3 && plan.persistent));
+  if (plan.pair) {
+    p.tmB2 = make_tmap_2d(a.Wt, a.wt_rows > 0 ? a.wt_rows : a.N, K, a.wt_ld > 0 ? a.wt_ld : K, BN / 2);
+    int acc_stride = 32;
+    while (acc_stride < BN) acc_stride <<= 1;
+    p.tmem_cols = 2 * acc_stride;
+    const int stage2 = kBM * kBK * 2 + (BN / 2) * kBK * 2;
+    int pst = (225 * 1024 - 2048) / stage2;
+    if (pst > 10) pst = 10;
+    p.stages = pst;
+    plan.pair_smem_bytes = pst * stage2 + 1024 + 512;
+    const int m_pairs = ((int)plan.grid.y + 1) / 2;
+    const int total_pairs = (int)plan.grid.x * m_pairs * (int)plan.grid.z;
+    plan.pgrid = 2 * (total_pairs < 74 ? total_pairs : 74);
+  }
   return plan;
 }
 
@@ -770,7 +586,9 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (plan.persistent) {
+  if (plan.pair) {
+    launch_gemm_pair(plan, stream);
+  } else if (plan.persistent) {
     static bool attr2 = false;
     if (!attr2) {
       LDN_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -92,7 +92,7 @@ struct STW {
   bf16* Wqk = nullptr;    // [2C, C]
   bf16* Wff1 = nullptr;   // interleaved [8C, C]
   float* bff1 = nullptr;  // interleaved [8C]
-  int ff_bn = 160;
+  int ff_bn = 256;
   int index;  // 0..15, order of execution
 };
 
@@ -273,7 +273,7 @@ void unet_finalize(ldn_engine* e, cudaStream_t stream) {
     const DevTensor& wf = e->W(0, tb + ".ff.net.0.proj.weight");
     const DevTensor& bf = e->W(0, tb + ".ff.net.0.proj.bias");
     LDN_CHECK(wf.shape[0] == 8 * C && wf.shape[1] == C, "GEGLU proj shape mismatch at " + s.prefix);
-    s.ff_bn = 160;
+    s.ff_bn = 256;  // GEGLU tile: 128 value + 128 gate columns (N = 8C is a multiple of 256 for every SD1.5 level)
     LDN_CHECK((8 * C) % s.ff_bn == 0, "GEGLU width not a multiple of the tile");
     s.Wff1 = U.arena.get<bf16>((size_t)8 * C * C);
     s.bff1 = U.arena.get<float>((size_t)8 * C);

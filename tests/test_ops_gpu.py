@@ -189,3 +189,37 @@ def test_cfg_step_matches_torch(lib):
     L.check(l.ldn_cfg_step(x.data_ptr(), u.data_ptr(), c.data_ptr(), 7.0, 1, -0.4, 0.25, 2.0, nz.data_ptr(), xo.data_ptr(),
                            do.data_ptr(), n, L.cur_stream()))
     assert torch.allclose(xo, x + ((x - den) / 2.0) * (-0.4) + nz * 0.25, rtol=1e-5, atol=1e-5)
+
+
+def test_gemm_cta_pair_kernel_subprocess():
+    """The opt-in CTA-pair GEMM (gemm_pair.cu: cluster of 2, tcgen05.mma.cta_group::2, LDN_GEMM_PAIR=1) computes the same
+    results as the default kernels. The mode is latched per process, hence the subprocess."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import torch, torch.nn.functional as F
+        from lightdiffusion_next_b200 import _lib as L
+        lib = L.load(); torch.manual_seed(0)
+        def rel(a, b): return float((a.float() - b.float()).norm() / b.float().norm())
+        for (M, N, K) in [(1000, 320, 320), (4096, 640, 1280), (300, 2560, 320)]:
+            A = torch.randn(M, K, device="cuda").bfloat16(); W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+            b = torch.randn(N, device="cuda"); R = torch.randn(M, N, device="cuda").bfloat16()
+            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            L.check(lib.ldn_gemm_bf16(A.data_ptr(), K, K, 0, 0, 0, W.data_ptr(), M, N, b.data_ptr(), 0, 0, 0, R.data_ptr(), N,
+                                      out.data_ptr(), N, 0, 0, 0, 0, 0, L.cur_stream()))
+            ref = A.float() @ W.float().t() + b + R.float()
+            assert rel(out, ref) < 4e-3, (M, N, K, rel(out, ref))
+        for (B, H, Wd, Cin, Cout) in [(2, 16, 16, 64, 64), (1, 32, 32, 320, 320), (3, 8, 8, 128, 320)]:
+            x = torch.randn(B, H, Wd, Cin, device="cuda").bfloat16()
+            w = (torch.randn(Cout, 3, 3, Cin, device="cuda") / (9 * Cin) ** 0.5).bfloat16()
+            b = torch.randn(Cout, device="cuda")
+            out = torch.empty(B, H, Wd, Cout, device="cuda", dtype=torch.bfloat16)
+            L.check(lib.ldn_conv3x3_bf16(x.data_ptr(), w.data_ptr(), B, H, Wd, Cin, Cout, b.data_ptr(), 0, 0, 0,
+                                         out.data_ptr(), L.cur_stream()))
+            ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b, padding=1)
+            assert rel(out.permute(0, 3, 1, 2), ref) < 4e-3, (B, H, Wd, Cin, Cout)
+        print("PAIR_OK")
+    ''')
+    env = dict(os.environ, LDN_GEMM_PAIR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "PAIR_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
