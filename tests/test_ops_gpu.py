@@ -1,6 +1,8 @@
 """GPU parity of every hand-written kernel, called through the C ABI, against plain torch fp32 on the same inputs.
 Tolerances: inputs/outputs are bf16 with fp32 accumulation, so one op carries ~2^-9 relative rounding on its output
 (rel-L2 <= 4e-3 asserted; measured ~1.7e-3 for GEMM/conv, ~2.2e-3 for attention)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
