@@ -1,0 +1,70 @@
+"""Checks at BASELINE.json's full size (SD1.5 1024x1024: latent 128x128, UNet batch 2): the engine against the oracle on
+one whole CFG-pair forward, plus the size-independent properties of the path (bit-determinism, row independence, CFG
+linearity of the fused solver update)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+EPS_TOL = 2.5e-2  # bf16 engine vs fp32 reference, per forward (the reference's own bf16 path is at 1.06e-2)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.fixture(scope="module")
+def engine(unet_sd):
+    from lightdiffusion_next_b200.engine import Engine
+    e = Engine(max_rows=2, max_h=128, max_w=128, max_ctx_tokens=77)
+    e.load_unet(unet_sd)
+    return e
+
+
+@pytest.fixture(scope="module")
+def inputs():
+    g = torch.Generator().manual_seed(2024)
+    x = torch.randn(2, 4, 128, 128, generator=g) * 3.0
+    sigma = torch.tensor([2.5, 2.5])
+    ctx = torch.randn(2, 77, 768, generator=g)
+    return x, sigma, ctx
+
+
+def test_full_size_forward_matches_oracle(engine, unet_sd, inputs):
+    """One 1024x1024 CFG-pair forward (9.35 TFLOP): engine vs the fp32 oracle restatement of BaseModel.apply_model."""
+    from oracle import sd15_oracle as O
+    x, sigma, ctx = inputs
+    engine.set_context(ctx.cuda())
+    out = engine.denoise(x.cuda(), sigma.cuda()).cpu()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = O.apply_model(unet_sd, x, sigma, ctx)
+    s = sigma.view(-1, 1, 1, 1)
+    err = rel((x - out) / s, (x - ref) / s)
+    assert err < EPS_TOL, err
+
+
+def test_full_size_bit_determinism_and_row_independence(engine, inputs):
+    x, sigma, ctx = inputs
+    engine.set_context(ctx.cuda())
+    a = engine.denoise(x.cuda(), sigma.cuda()).clone()
+    b = engine.denoise(x.cuda(), sigma.cuda()).clone()
+    assert torch.equal(a, b)  # no atomics anywhere on the path: run-to-run bit-identical
+    x2 = x.clone()
+    x2[1] = torch.randn_like(x2[1]) * 5.0
+    ctx2 = ctx.clone()
+    ctx2[1] = torch.randn_like(ctx2[1])
+    engine.set_context(ctx2.cuda())
+    c = engine.denoise(x2.cuda(), torch.tensor([2.5, 7.0]).cuda())
+    assert torch.equal(a[0], c[0])  # the uncond row never sees the cond row's latent, sigma or context
+    assert not torch.equal(a[1], c[1])
+
+
+def test_full_size_cfg_step_linearity(engine):
+    """ldn_cfg_step (mode 0) is affine in (x, uncond, cond): x' = c0 x - c1 (u + cfg (c - u)); check against torch."""
+    g = torch.Generator().manual_seed(7)
+    x, u, c = (torch.randn(1, 4, 128, 128, generator=g).cuda() for _ in range(3))
+    out = torch.empty_like(x)
+    den = torch.empty_like(x)
+    engine.cfg_step(x, u, c, 7.0, 0, c0=0.83, c1=-0.21, x_out=out, denoised_out=den)
+    d = u + 7.0 * (c - u)
+    assert torch.allclose(den, d, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(out, 0.83 * x - (-0.21) * d, rtol=1e-6, atol=1e-5)
