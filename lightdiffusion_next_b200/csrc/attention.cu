@@ -327,10 +327,9 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   if (a.d == 40 && p.vt_head_stride == 48) {
     // ones-row V^T. (An experiment with two softmax threads per row / 16 softmax warps measured slower -- 2.21 ms vs
     // 1.92 ms at N = 16384 -- and was dropped: the limiter was MMA issue, not softmax latency.)
-    static const bool use_v3 = getenv("LDN_ATTN_V3") != nullptr;
-    // default: generation 5 (generation 3 + P kept in tensor memory, TS-form P*V)
-    if (use_v3) finish_attn3_plan(plan, a.Nq, a.Nk, a.heads, a.B);
-    else finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+    // generation 5 (P kept in tensor memory, TS-form P*V); generation 3 (P through shared memory) was retired once v5
+    // had replaced it on every path
+    finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   } else if (a.d == 80 && p.vt_head_stride == 96 && !a.causal) {
     finish_attn6_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // generation 6: ones-row V^T, P aliased over S in TMEM
   } else {
@@ -354,7 +353,6 @@ static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
   if (plan.p.variant == 6) return launch_attn6(plan, stream);
   if (plan.p.variant == 5) return launch_attn5(plan, stream);
-  if (plan.p.variant == 3) return launch_attn3(plan, stream);
   if (plan.p.variant == 2) return launch_attn2(plan, stream);
   switch (plan.p.dv) {
     case 48: launch_attn_t<48>(plan, stream); break;

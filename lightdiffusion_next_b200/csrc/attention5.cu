@@ -1,4 +1,4 @@
-// Attention kernel, fifth generation, head dim 40: generation 3 (attention3.cu) with the probabilities P kept in
+// Attention kernel, fifth generation, head dim 40: generation 3 (retired; P through shared memory) with the probabilities P kept in
 // TENSOR MEMORY instead of shared memory. After the MMA-issue fix, generation 3 without exponentials still needed
 // 2330 clk per key tile against 1781 clk of pure shared-memory traffic (228 KB per tile pair at 128 B/clk: P written by the
 // softmax threads, P re-read as the A operand of P*V, K / V^T tiles, TMA fills) -- it sat on the shared-memory roofline.

@@ -133,7 +133,7 @@ struct AttnParams {
   int kv_stages;
   float scale_log2;  // softmax scale * log2(e)
   int vt_head_stride; // rows per head in Vt (d, or 48 when a ones row at index d supplies the softmax row sum)
-  int variant;       // 3: attention3.cu (d = 40, row sums on the tensor core, O resident in TMEM); 1: attention.cu (one query tile per CTA), 2: attention2.cu (two query tiles, d <= 64)
+  int variant;       // 1: attention.cu (one query tile per CTA); 2: attention2.cu (two query tiles, d <= 64); 5: attention5.cu (d = 40, S / O / P in TMEM); 6: attention6.cu (d = 80)
   int pingpong;      // variant 3: softmax warpgroups alternate on the MUFU
   int p_bufs;        // variant 3: P buffers per query tile in shared memory (1 or 2)
   int poly_mod;      // variant 2: every poly_mod-th group of 8 exponentials runs on the FMA pipes (0 = all MUFU)
@@ -164,8 +164,6 @@ struct AttnArgs {
 AttnPlan make_attn_plan(const AttnArgs& a);
 void finish_attn2_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn2(const AttnPlan& plan, cudaStream_t stream);
-void finish_attn3_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
-void launch_attn3(const AttnPlan& plan, cudaStream_t stream);
 void finish_attn5_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn5(const AttnPlan& plan, cudaStream_t stream);
 void finish_attn6_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);

@@ -65,7 +65,7 @@ void launch_pad_vt_cols(const bf16* src, int ld_src, int C, int Bn, int N, int n
 }
 
 // V^T buffers of head-dim-40 layers carry 48 rows per head; row 40 of every head is all ones (softmax row sums on the
-// tensor core, attention3.cu), rows 41..47 stay zero.
+// tensor core, attention5.cu / attention6.cu), the remaining pad rows stay zero.
 __global__ void fill_ones_rows_kernel(bf16* __restrict__ vt, int heads, long long ld, int head_stride, int row) {
   const long long total = (long long)heads * ld;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {

@@ -106,7 +106,7 @@ def test_conv3x3(lib, B, H, W, Cin, Cout):
                                                      (2, 8, 64, 64, 160, False, False), (2, 8, 16, 16, 160, False, False),
                                                      (3, 12, 77, 77, 64, True, False), (2, 8, 4096, 154, 40, False, False),
                                                      (1, 8, 4096, 4096, 40, False, False),
-                                                     # head dim 40 with the ones-row V^T layout (attention3.cu: row sums on the
+                                                     # head dim 40 with the ones-row V^T layout (attention5.cu: row sums on the
                                                      # tensor core, O resident in TMEM, lazy rescale)
                                                      (2, 8, 1024, 1024, 40, False, True), (2, 8, 1024, 77, 40, False, True),
                                                      (1, 8, 4096, 4096, 40, False, True), (2, 8, 64, 64, 40, False, True),
