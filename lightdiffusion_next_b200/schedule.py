@@ -52,12 +52,41 @@ def normal_scheduler(ms: DiscreteSchedule, steps: int) -> torch.Tensor:
     return torch.FloatTensor(sigs + [0.0])
 
 
+def simple_scheduler(ms: DiscreteSchedule, steps: int) -> torch.Tensor:
+    """Every (1000 / steps)-th discrete sigma, walking down from sigma_max (ksampler_util.py:180-199)."""
+    n = len(ms.sigmas)
+    ss = n / steps
+    sigs = [float(ms.sigmas[-(1 + int(x * ss))]) for x in range(steps)]
+    return torch.FloatTensor(sigs + [0.0])
+
+
+def beta_scheduler(ms: DiscreteSchedule, steps: int, alpha: float = 0.6, beta: float = 0.6) -> torch.Tensor:
+    """Timesteps at the Beta(alpha, beta) quantiles of an even grid, duplicates dropped (arXiv 2407.12173;
+    ksampler_util.py:202-241): the schedule may hold fewer than `steps` sigmas."""
+    import numpy as np
+    import scipy.stats
+
+    total = len(ms.sigmas) - 1
+    ts = scipy.stats.beta.ppf(1 - np.linspace(0, 1, steps, endpoint=False), alpha, beta)
+    idx = np.rint(ts * total).astype(np.int32)
+    uniq, first = np.unique(idx, return_index=True)
+    ordered = uniq[np.argsort(first)]
+    return torch.FloatTensor([float(ms.sigmas[i]) for i in ordered] + [0.0])
+
+
+SCHEDULERS = ("karras", "normal", "simple", "beta")
+
+
 def calculate_sigmas(ms: DiscreteSchedule, scheduler_name: str, steps: int) -> torch.Tensor:
     if scheduler_name == "karras":
         return get_sigmas_karras(steps, float(ms.sigma_min), float(ms.sigma_max))
     if scheduler_name == "normal":
         return normal_scheduler(ms, steps)
-    raise ValueError(f"unsupported scheduler {scheduler_name!r} (karras | normal)")
+    if scheduler_name == "simple":
+        return simple_scheduler(ms, steps)
+    if scheduler_name == "beta":
+        return beta_scheduler(ms, steps)
+    raise ValueError(f"unsupported scheduler {scheduler_name!r} ({' | '.join(SCHEDULERS)})")
 
 
 def get_ancestral_step(sigma_from: torch.Tensor, sigma_to: torch.Tensor, eta: float = 1.0):

@@ -81,6 +81,16 @@ def calculate_sigmas(scheduler: str, steps: int) -> Tensor:
         return sigmas_karras(steps, float(sigmas[0]), float(sigmas[-1]))
     if scheduler == "normal":
         return sigmas_normal(steps, sigmas, log_sigmas)
+    if scheduler == "simple":  # simple_scheduler, ksampler_util.py:180-199
+        ss = len(sigmas) / steps
+        return torch.FloatTensor([float(sigmas[-(1 + int(x * ss))]) for x in range(steps)] + [0.0])
+    if scheduler == "beta":  # beta_scheduler (alpha = beta = 0.6), ksampler_util.py:202-241
+        import numpy as np
+        import scipy.stats
+        ts = scipy.stats.beta.ppf(1 - np.linspace(0, 1, steps, endpoint=False), 0.6, 0.6)
+        idx = np.rint(ts * (len(sigmas) - 1)).astype(np.int32)
+        uniq, first = np.unique(idx, return_index=True)
+        return torch.FloatTensor([float(sigmas[i]) for i in uniq[np.argsort(first)]] + [0.0])
     raise ValueError(scheduler)
 
 

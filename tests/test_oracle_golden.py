@@ -70,3 +70,18 @@ def test_ksample_dpmpp_2m_multiscale_default_on(golden_sample, unet_sd):
     # 15 steps: steps 6 is low-res (8x8) under the sampler's own defaults
     out = _run(golden_sample, unet_sd, "dpmpp_2m_cfgpp", "karras", 15)
     assert rel(out, golden_sample["dpmpp_2m_ms_final"]) < 1e-4
+
+
+def test_all_scheduler_names_bit_exact():
+    """Every scheduler the reference's calculate_sigmas knows (karras, normal, simple, beta) at several step counts:
+    oracle and the product's host schedule code both reproduce the reference bit for bit."""
+    import os
+    import torch
+    from oracle import sd15_oracle as O
+    from lightdiffusion_next_b200 import schedule as S
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "schedules.pt"))
+    ms = S.DiscreteSchedule()
+    for key, ref in gold.items():
+        name, steps = key.rsplit("_", 1)
+        assert torch.equal(O.calculate_sigmas(name, int(steps)), ref), key
+        assert torch.equal(S.calculate_sigmas(ms, name, int(steps)), ref), key
