@@ -116,40 +116,46 @@ struct VB {
     conv(p + ".conv2", p + ".conv2", sA, H, W, Cout, Cout, res, out);
     return out;
   }
-  // AttnBlock (single head of C channels over all h*w pixels; src/Attention/Attention.py:159-178)
+  // AttnBlock (single head of C channels over all h*w pixels; src/Attention/Attention.py:159-178).
+  // Any token count: per image, Q / K / V^T / S live in layouts padded to Np = roundup(N, 16) tokens. Pad rows of K and pad
+  // columns of V^T are produced as exact zeros by the GEMMs themselves (operand rows past N read as zero through the
+  // tensor map), so the pad columns of S are 0 before and after the in-place softmax over the first N columns and
+  // contribute nothing to P V.
   const bf16* attn(const std::string& p, const bf16* x, int h, int w, int C, const float* attn_bias) {
     const int N = h * w, T = B * N;
-    LDN_CHECK(N % 16 == 0, "VAE attention needs h*w to be a multiple of 16");
-    bf16* q = A.get<bf16>((size_t)T * C);
-    bf16* k = A.get<bf16>((size_t)T * C);
-    bf16* vt = A.get<bf16>((size_t)C * T);
+    const int Np = (N + 15) / 16 * 16;
+    bf16* q = A.get<bf16>((size_t)B * Np * C, true);
+    bf16* k = A.get<bf16>((size_t)B * Np * C, true);
+    bf16* vt = A.get<bf16>((size_t)C * B * Np + 64, true);
     bf16* o = A.get<bf16>((size_t)T * C);
-    bf16* S = A.get<bf16>((size_t)N * N);
+    bf16* S = A.get<bf16>((size_t)Np * Np, true);
     bf16* out = A.get<bf16>((size_t)T * C);
     gn(p + ".norm", x, C, N, p + ".norm", false, sA);
-    for (const char* nm : {"q", "k"}) {
-      GemmArgs a;
-      a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = e->W(1, p + "." + nm + ".weight").b(); a.M = T; a.N = C;
-      a.bias = e->W(1, p + "." + nm + ".bias").f(); a.out = (nm[0] == 'q') ? q : k; a.ldo = C;
-      gemm(p + "." + nm, a);
-    }
-    {
-      GemmArgs a;  // V^T = Wv * X^T (bias folded into proj_out)
-      a.A0 = e->W(1, p + ".v.weight").b(); a.lda0 = C; a.K0 = C; a.Wt = sA; a.M = C; a.N = T; a.out = vt; a.ldo = T;
-      gemm(p + ".vt", a);
-    }
     const float scale = 1.0f / sqrtf((float)C);
     for (int b = 0; b < B; ++b) {
+      const bf16* xb = sA + (size_t)b * N * C;
+      for (const char* nm : {"q", "k"}) {
+        GemmArgs a;
+        a.A0 = xb; a.lda0 = C; a.K0 = C; a.Wt = e->W(1, p + "." + nm + ".weight").b(); a.M = N; a.N = C;
+        a.bias = e->W(1, p + "." + nm + ".bias").f(); a.out = ((nm[0] == 'q') ? q : k) + (size_t)b * Np * C; a.ldo = C;
+        gemm(p + "." + nm, a);
+      }
+      {
+        GemmArgs a;  // V^T = Wv * X^T (bias folded into proj_out); token columns N..Np-1 come out as zeros
+        a.A0 = e->W(1, p + ".v.weight").b(); a.lda0 = C; a.K0 = C; a.Wt = xb; a.wt_rows = N; a.M = C; a.N = Np;
+        a.out = vt + (size_t)b * Np; a.ldo = (long long)B * Np;
+        gemm(p + ".vt", a);
+      }
       GemmArgs s;
-      s.A0 = q + (size_t)b * N * C; s.lda0 = C; s.K0 = C; s.Wt = k + (size_t)b * N * C; s.M = N; s.N = N;
-      s.out = S; s.ldo = N;
+      s.A0 = q + (size_t)b * Np * C; s.lda0 = C; s.K0 = C; s.Wt = k + (size_t)b * Np * C; s.M = N; s.N = Np;
+      s.out = S; s.ldo = Np;
       gemm(p + ".scores", s);
       bf16* Sp = S;
-      add(p + ".softmax", [=](cudaStream_t st) { launch_softmax_rows(Sp, N, Sp, N, N, N, scale, st); });
+      add(p + ".softmax", [=](cudaStream_t st) { launch_softmax_rows(Sp, Np, Sp, Np, N, N, scale, st); });
       GemmArgs pv;
-      pv.A0 = S; pv.lda0 = N; pv.K0 = N; pv.Wt = vt + (size_t)b * N; pv.M = N; pv.N = C; pv.out = o + (size_t)b * N * C;
+      pv.A0 = S; pv.lda0 = Np; pv.K0 = Np; pv.Wt = vt + (size_t)b * Np; pv.M = N; pv.N = C; pv.out = o + (size_t)b * N * C;
       pv.ldo = C;
-      pv.wt_ld = T;  // V^T rows are T apart: describe the weight operand with its true leading dimension
+      pv.wt_ld = (long long)B * Np;  // V^T rows are B*Np apart: describe the weight operand with its true leading dimension
       gemm(p + ".pv", pv);
     }
     GemmArgs po;
