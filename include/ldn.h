@@ -12,6 +12,7 @@
  *   ldn_cfg_step       <- cfg_function + sampler update   src/sample/CFG.py:55-60, src/sample/samplers.py:728-732,952-953
  *   ldn_vae_decode     <- VAE.decode                      src/AutoEncoders/VariationalAE.py:690-722
  *   ldn_vae_encode     <- AutoencodingEngine.encode (w/o the sampling step)  src/AutoEncoders/VariationalAE.py:148-172, 377-413
+ *   ldn_taesd_decode   <- TAESD.decode (preview)           src/AutoEncoders/taesd.py:104-136,190-197
  *   ldn_clip_encode    <- CLIPTextModel_.forward          src/clip/CLIPTextModel.py:51-107
  *   op-level entries   <- the torch library calls of      src/cond/cast.py:107,174,241,281 and
  *                         optimized_attention             src/Attention/Attention.py:34-41
@@ -49,8 +50,9 @@ int ldn_version(void);
 /* ---- engine lifecycle */
 int ldn_create(const ldn_config* cfg, ldn_handle* out);
 void ldn_destroy(ldn_handle h);
-/* which: 0 = UNet ("model.diffusion_model." prefix stripped), 1 = VAE decoder ("first_stage_model." stripped),
- *        2 = CLIP-L text model ("...text_model." stripped) */
+/* which: 0 = UNet ("model.diffusion_model." prefix stripped), 1 = VAE ("first_stage_model." stripped; decoder.* +
+ *        post_quant_conv.* and/or encoder.* + quant_conv.*), 2 = CLIP-L text model ("...text_model." stripped),
+ *        3 = TAESD preview decoder (keys of taesd_decoder.safetensors) */
 int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream);
 /* Discrete schedule tables (ModelSamplingDiscrete.sigmas / .log_sigmas, src/sample/sampling.py:221-356): host
  * pointers, n entries each. log_sigmas is passed separately because the reference computes it in float64. */
@@ -79,6 +81,10 @@ int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, i
  * (mean | logvar after quant_conv). The reparameterised sample mean + exp(0.5*clamp(logvar,-30,20))*randn stays with the
  * caller, which owns the RNG (DiagonalGaussianDistribution.sample, VariationalAE.py:42-51). Needs encoder.* weights. */
 int ldn_vae_encode(ldn_handle h, const float* pixels, float* moments, int B, int H, int W, void* stream);
+/* TAESD preview decoder (src/AutoEncoders/taesd.py:104-136, TAESD.decode :190-197 before its sub(0.5).mul(2)):
+ * z: [B,4,h,w] fp32 raw latent; rgb: [B,8h,8w,3] fp32, the decoder's raw output (~[0,1], not clamped).
+ * Weights: ldn_load_weights(which = 3) with the keys of taesd_decoder.safetensors (nn.Sequential indices). */
+int ldn_taesd_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, int lat_w, void* stream);
 /* ids: [S,77] int64 (device); out_last: [S,77,768] fp32 final-LN of last layer (may be NULL);
  * out_penultimate: [S,77,768] fp32 final-LN of layer -2 (what SD1.5 uses) */
 int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultimate, float* out_last, void* stream);

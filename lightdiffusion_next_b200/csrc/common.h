@@ -60,7 +60,8 @@ struct GemmParams {
   long long ldr;
   int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
   int epi_opt;       // bit 0: prefetching epilogue (persistent kernel), bit 1: packed-pair GEGLU arithmetic
-  int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77)
+  int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77),
+            // 2 ReLU after the bias, 3 ReLU after the residual add (TAESD, src/AutoEncoders/taesd.py:39-63)
   int row_head_dim, row_head_slot;  // GEMM mode, row_head_dim > 0: output row m -> (m / dim) * slot + m % dim
   // split-K (small-M problems): grid.z splits, each writes an fp32 partial tile; splitk_reduce_kernel finishes
   int splits, chunks_per_split;
@@ -190,7 +191,7 @@ void launch_scale_in(const float* x, const float* sigma, int B, int C, int H, in
                      cudaStream_t stream);
 // conv_in: 3x3, Cin=4 (NCHW fp32 input scaled by 1/sqrt(sigma^2+1)), Cout=N -> NHWC bf16
 void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const float* bias, int B, int H, int W,
-                    int Cin, int Cout, bf16* out, cudaStream_t stream);
+                    int Cin, int Cout, bf16* out, cudaStream_t stream, int flags = 0);  // flags: 1 = tanh(x/3)*3 on the input (TAESD Clamp), 2 = ReLU on the output
 // conv_out: 3x3 Cin -> 4 on NHWC bf16 input; writes denoised = x - eps*sigma (NCHW fp32) and optionally eps
 void launch_conv_out_finish(const float* acc16, const float* bias, const float* x, const float* sigma, int B, int HW,
                             int cout, float* denoised, cudaStream_t stream);
@@ -199,7 +200,8 @@ void launch_conv_out(const bf16* h, const bf16* Wt, const float* bias, const flo
 void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream);
 // stride-2 3x3 pad-1 im2col gather: [B,H,W,C] -> [B*(H/2)*(W/2), 9*C]
 void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream, int pad_before = 1);
-void launch_vae_rgb_finish(const float* acc16, const float* bias, size_t npix, int cout, float* out, cudaStream_t stream);
+void launch_vae_rgb_finish(const float* acc16, const float* bias, size_t npix, int cout, float* out, cudaStream_t stream,
+                           int raw = 0);  // raw = 1: acc + bias without the [0,1] image mapping (TAESD)
 void launch_vae_moments_finish(const float* acc16, const float* bc, const float* Wq, const float* bq, int B, int HW,
                                int zc2, float* out, cudaStream_t stream);
 // dst[c, b*nk_pad + k] = src[c, b*N + k]: V^T re-laid with 16-byte aligned per-batch column offsets

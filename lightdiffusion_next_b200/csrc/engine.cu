@@ -157,7 +157,7 @@ void ldn_destroy(ldn_handle h) {
 
 int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream_) {
   LDN_API_BEGIN
-  LDN_CHECK(h && tensors && which >= 0 && which < 3, "ldn_load_weights: bad argument");
+  LDN_CHECK(h && tensors && which >= 0 && which < 4, "ldn_load_weights: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   for (int i = 0; i < n; ++i) {
     const ldn_tensor& t = tensors[i];
@@ -245,6 +245,13 @@ int ldn_vae_encode(ldn_handle h, const float* pixels, float* moments, int B, int
   LDN_CHECK(h && pixels && moments, "ldn_vae_encode: bad argument");
   if (!h->finalized[1]) vae_finalize(h, (cudaStream_t)stream);
   vae_encode(h, pixels, moments, B, H, W, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_taesd_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, int lat_w, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && z && rgb, "ldn_taesd_decode: bad argument");
+  taesd_decode(h, z, rgb, B, lat_h, lat_w, (cudaStream_t)stream);
   LDN_API_END
 }
 

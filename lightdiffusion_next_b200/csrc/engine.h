@@ -62,8 +62,8 @@ struct Arena {
 struct ldn_engine {
   ldn_config cfg;
   ldn::Arena weights_arena;
-  std::unordered_map<std::string, ldn::DevTensor> w[3];  // 0 unet, 1 vae, 2 clip
-  bool finalized[3] = {false, false, false};
+  std::unordered_map<std::string, ldn::DevTensor> w[4];  // 0 unet, 1 vae, 2 clip, 3 taesd (preview decoder)
+  bool finalized[4] = {false, false, false, false};
   float* log_sigmas = nullptr;
   int n_sigmas = 0;
 
@@ -75,6 +75,8 @@ struct ldn_engine {
   std::shared_ptr<VaeState> vae;
   struct ClipState;
   std::shared_ptr<ClipState> clip;
+  struct TaesdState;
+  std::shared_ptr<TaesdState> taesd;
 
   ldn_engine();
   ~ldn_engine();
@@ -94,6 +96,7 @@ int unet_last_launches(ldn_engine* e);
 void vae_finalize(ldn_engine* e, cudaStream_t stream);
 void vae_decode(ldn_engine* e, const float* z, float* rgb, int B, int h, int w, cudaStream_t stream);
 void vae_encode(ldn_engine* e, const float* pixels, float* moments, int B, int H, int W, cudaStream_t stream);
+void taesd_decode(ldn_engine* e, const float* z, float* rgb, int B, int h, int w, cudaStream_t stream);
 void clip_finalize(ldn_engine* e, cudaStream_t stream);
 void clip_encode(ldn_engine* e, const int64_t* ids, int S, float* out_pen, float* out_last, cudaStream_t stream);
 }  // namespace ldn

@@ -104,6 +104,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
         if (p.act == 1) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = f[i] / (1.0f + __expf(-1.702f * f[i]));
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
         }
         if (p.residual) {
           uint32_t w[8];
@@ -119,6 +122,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
             f[2 * i] += bf16_lo(w[i]);
             f[2 * i + 1] += bf16_hi(w[i]);
           }
+        }
+        if (p.act == 3) {  // ReLU after the residual add (TAESD Block: relu(conv(x) + skip(x)))
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
         }
         if (p.out_f32) {
           float4* op = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldo + n);

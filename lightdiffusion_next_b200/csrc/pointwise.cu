@@ -166,7 +166,7 @@ void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const flo
 // from shared memory feeds 32 FMAs (the one-pixel version sat on the shared-memory bandwidth).
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                const bf16* __restrict__ Wt, const float* __restrict__ bias, int B, int H, int W, int Cin,
-                               int Cout, bf16* __restrict__ out) {
+                               int Cout, bf16* __restrict__ out, int flags) {
   extern __shared__ float s_w[];  // transposed: [9*Cin][Cout] so the 8 output channels of a thread are contiguous
   const int K = 9 * Cin;
   for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) {  // consecutive threads -> consecutive o: conflict-free
@@ -199,7 +199,9 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           const int xx = x0 + i - 1;
-          in[i] = (xx >= 0 && xx < W) ? row[xx] * scale : 0.f;
+          float v = (xx >= 0 && xx < W) ? row[xx] * scale : 0.f;
+          if (flags & 1) v = tanhf(v * (1.0f / 3.0f)) * 3.0f;
+          in[i] = v;
         }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
@@ -219,6 +221,10 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       if (x0 + px < W) {
+        if (flags & 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[px][i] = fmaxf(acc[px][i], 0.f);
+        }
         uint4 ov;
         ov.x = pack_bf16x2(acc[px][0], acc[px][1]);
         ov.y = pack_bf16x2(acc[px][2], acc[px][3]);
@@ -231,7 +237,7 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 }
 
 void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const float* bias, int B, int H, int W,
-                    int Cin, int Cout, bf16* out, cudaStream_t stream) {
+                    int Cin, int Cout, bf16* out, cudaStream_t stream, int flags) {
   LDN_CHECK(Cout % 8 == 0, "conv_in: Cout must be a multiple of 8");
   const size_t smem = sizeof(float) * Cout * 9 * Cin;
   LDN_CHECK(smem <= 200 * 1024, "conv_in: weights do not fit in shared memory");
@@ -243,7 +249,7 @@ void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const fl
   const size_t total = (size_t)B * H * ((W + 3) / 4) * (Cout / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  conv_in_kernel<<<blocks, 256, smem, stream>>>(x, sigma, Wt, bias, B, H, W, Cin, Cout, out);
+  conv_in_kernel<<<blocks, 256, smem, stream>>>(x, sigma, Wt, bias, B, H, W, Cin, Cout, out, flags);
   LDN_CUDA(cudaGetLastError());
 }
 
@@ -394,21 +400,22 @@ void launch_vae_moments_finish(const float* acc16, const float* bc, const float*
 // VAE decoder tail: rgb[pix, o] = clamp((acc16[pix, o] + bias[o] + 1) / 2, 0, 1), o < 3 -- the decoder's conv_out (128 -> 3,
 // run as a 16-column tensor-core conv into fp32 scratch) + process_output (VariationalAE.py:602-604), NHWC fp32 out.
 __global__ void vae_rgb_finish_kernel(const float* __restrict__ acc16, const float* __restrict__ bias, size_t npix,
-                                      int cout, float* __restrict__ out) {
+                                      int cout, float* __restrict__ out, int raw) {
   for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(acc16 + pix * 16);
     const float v[4] = {a.x, a.y, a.z, a.w};
     for (int o = 0; o < cout; ++o) {
-      const float y = (v[o] + bias[o] + 1.0f) * 0.5f;
-      out[pix * cout + o] = fminf(fmaxf(y, 0.f), 1.f);
+      const float e = v[o] + bias[o];
+      out[pix * cout + o] = raw ? e : fminf(fmaxf((e + 1.0f) * 0.5f, 0.f), 1.f);
     }
   }
 }
-void launch_vae_rgb_finish(const float* acc16, const float* bias, size_t npix, int cout, float* out, cudaStream_t stream) {
+void launch_vae_rgb_finish(const float* acc16, const float* bias, size_t npix, int cout, float* out, cudaStream_t stream,
+                           int raw) {
   LDN_CHECK(cout <= 4, "vae_rgb_finish: at most 4 channels");
   int blocks = (int)((npix + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  vae_rgb_finish_kernel<<<blocks, 256, 0, stream>>>(acc16, bias, npix, cout, out);
+  vae_rgb_finish_kernel<<<blocks, 256, 0, stream>>>(acc16, bias, npix, cout, out, raw);
   LDN_CUDA(cudaGetLastError());
 }
 

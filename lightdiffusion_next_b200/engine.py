@@ -14,7 +14,7 @@ from . import _lib as L
 from .schedule import DiscreteSchedule
 
 _DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
-UNET, VAE, CLIP = 0, 1, 2
+UNET, VAE, CLIP, TAESD = 0, 1, 2, 3
 
 
 class Engine:
@@ -84,6 +84,10 @@ class Engine:
     def load_clip(self, state_dict: Dict[str, torch.Tensor]) -> None:
         self.load_weights(CLIP, state_dict)
 
+    def load_taesd(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """TAESD preview decoder weights (keys of `taesd_decoder.safetensors`: nn.Sequential indices, taesd.py:104-136)."""
+        self.load_weights(TAESD, state_dict)
+
     def load_checkpoint(self, path: str, lora_path: Optional[str] = None, strength_model: float = 1.0,
                         strength_clip: float = 1.0) -> Dict[str, int]:
         """SD1.5 checkpoint file (.safetensors / .ckpt), optionally with a LoRA folded in -> UNet / VAE / CLIP weights
@@ -150,6 +154,16 @@ class Engine:
             noise = torch.randn(mean.shape)
         std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
         return (mean + std * noise.to(m.device)).float().cpu()
+
+    def taesd_decode(self, z: torch.Tensor) -> torch.Tensor:
+        """Raw latent [B,4,h,w] -> the TAESD decoder's raw output [B,8h,8w,3] fp32 on the device (~[0,1], unclamped).
+        TAESD.decode returns this * 2 - 1 (taesd.py:190-197); taesd_preview maps it back and clamps for display."""
+        z = z.to(self.device, torch.float32).contiguous()
+        B, _, h, w = z.shape
+        out = torch.empty(B, 8 * h, 8 * w, 3, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_taesd_decode(self.h, z.data_ptr(), out.data_ptr(), B, h, w, L.cur_stream()))
+        return out
 
     def clip_encode(self, ids: torch.Tensor):
         """ids [S,77] int64 -> (penultimate-layer output after final LN, last-layer output after final LN)."""

@@ -64,6 +64,12 @@ class Pipeline:
         return S.sample(self.e, seed, steps, cfg, sampler_name, scheduler, positive, negative, latent, denoise=denoise,
                         enable_multiscale=enable_multiscale)[0]["samples"]
 
+    # ---------------------------------------------------------------- taesd_preview (taesd.py:219-255)
+    def preview(self, x: torch.Tensor) -> torch.Tensor:
+        """Current sampler latent [B,4,h,w] -> preview images [B,8h,8w,3] in [0,1] on the CPU (what the reference shows every
+        5 steps); usable as / from a sampler `callback`."""
+        return self.e.taesd_decode(x[:, :4]).clamp_(0.0, 1.0).cpu()
+
     def __call__(self, tokens, negative_tokens=None, width: int = 512, height: int = 512, batch: int = 1, seed: int = 0,
                  steps: int = 20, cfg: float = 7.0, sampler_name: str = "dpmpp_2m_cfgpp", scheduler: str = "karras"):
         pos = self.encode(tokens)

@@ -187,6 +187,20 @@ def vae_encoder_shapes(ch: int = 128, ch_mult=(1, 2, 4, 4), num_res: int = 2, z:
     return s
 
 
+def taesd_decoder_shapes(latent_channels: int = 4) -> Dict[str, Tuple[int, ...]]:
+    """State-dict layout of `taesd_decoder.safetensors` (Decoder2, src/AutoEncoders/taesd.py:104-136): nn.Sequential indices."""
+    s: Dict[str, Tuple[int, ...]] = {"1.weight": (64, latent_channels, 3, 3), "1.bias": (64,)}
+    for blk in (3, 4, 5, 8, 9, 10, 13, 14, 15, 18):
+        for c in (0, 2, 4):
+            s[f"{blk}.conv.{c}.weight"] = (64, 64, 3, 3)
+            s[f"{blk}.conv.{c}.bias"] = (64,)
+    for up in (7, 12, 17):
+        s[f"{up}.weight"] = (64, 64, 3, 3)  # bias=False
+    s["19.weight"] = (3, 64, 3, 3)
+    s["19.bias"] = (3,)
+    return s
+
+
 def clip_shapes(width: int = 768, mlp: int = 3072, layers: int = 12, vocab: int = 49408, positions: int = 77) -> Dict[str, Tuple[int, ...]]:
     """State-dict layout of CLIP-L's text model (keys below `text_model.`; CLIPTextModel_, src/clip/CLIPTextModel.py:3-107)."""
     s: Dict[str, Tuple[int, ...]] = {"embeddings.token_embedding.weight": (vocab, width),

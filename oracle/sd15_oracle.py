@@ -610,6 +610,46 @@ def vae_sample_posterior(moments: Tensor, noise: Tensor) -> Tensor:
     return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
 
 
+def taesd_decoder_param_shapes() -> Dict[str, Tuple[int, ...]]:
+    """Keys of taesd_decoder.safetensors = nn.Sequential indices of Decoder2 (src/AutoEncoders/taesd.py:104-136)."""
+    s: Dict[str, Tuple[int, ...]] = {"1.weight": (64, 4, 3, 3), "1.bias": (64,)}
+    for blk in (3, 4, 5, 8, 9, 10, 13, 14, 15, 18):
+        for c in (0, 2, 4):
+            s[f"{blk}.conv.{c}.weight"] = (64, 64, 3, 3)
+            s[f"{blk}.conv.{c}.bias"] = (64,)
+    for up in (7, 12, 17):
+        s[f"{up}.weight"] = (64, 64, 3, 3)
+    s["19.weight"] = (3, 64, 3, 3)
+    s["19.bias"] = (3,)
+    return s
+
+
+def taesd_decode(sd: Dict[str, Tensor], z: Tensor) -> Tensor:
+    """Raw latent [B,4,h,w] -> Decoder2(z) as [B,8h,8w,3] fp32 (taesd.py: Clamp :30-36, Block :39-63, Decoder2 :104-136).
+    TAESD.decode (:190-197) returns this * 2 - 1; taesd_preview (:219-255) maps it back to [0,1] and clamps."""
+    def blk(i, x):
+        h = F.relu(_conv(sd, f"{i}.conv.0", x))
+        h = F.relu(_conv(sd, f"{i}.conv.2", h))
+        return F.relu(_conv(sd, f"{i}.conv.4", h) + x)
+
+    def conv_nb(i, x):
+        return F.conv2d(x, _w(sd, f"{i}.weight"), None, padding=1)
+
+    x = torch.tanh(z.float() / 3) * 3
+    x = F.relu(_conv(sd, "1", x))
+    for i in (3, 4, 5):
+        x = blk(i, x)
+    x = conv_nb(7, F.interpolate(x, scale_factor=2.0, mode="nearest"))
+    for i in (8, 9, 10):
+        x = blk(i, x)
+    x = conv_nb(12, F.interpolate(x, scale_factor=2.0, mode="nearest"))
+    for i in (13, 14, 15):
+        x = blk(i, x)
+    x = conv_nb(17, F.interpolate(x, scale_factor=2.0, mode="nearest"))
+    x = blk(18, x)
+    return _conv(sd, "19", x).movedim(1, -1)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # CLIP-L text encoder  (CLIPTextModel_.forward src/clip/CLIPTextModel.py:51-107; CLIPLayer / CLIPAttention / CLIPMLP
 # src/clip/Clip.py:14-180; config include/clip/sd1_clip_config.json: 12 layers, 768 wide, 12 heads, quick_gelu)

@@ -152,3 +152,4 @@ def test_synth_shape_tables_match_oracle():
     assert synth.vae_decoder_shapes() == O.vae_decoder_param_shapes()
     assert synth.clip_shapes() == O.clip_param_shapes()
     assert synth.vae_encoder_shapes() == O.vae_encoder_param_shapes()
+    assert synth.taesd_decoder_shapes() == O.taesd_decoder_param_shapes()

@@ -55,3 +55,17 @@ def test_oracle_vae_encoder_matches_reference_golden():
         torch.manual_seed(int(gold["sample_seed"]))
         lat = O.vae_sample_posterior(m, torch.randn(ref[:, :4].shape))
         assert ((lat - gold[f"latent_{name}"]).norm() / gold[f"latent_{name}"].norm()).item() < 1e-4
+
+
+def test_oracle_taesd_decoder_matches_reference_golden():
+    """oracle.taesd_decode vs the reference's Decoder2 (fixture: tests/golden/make_golden_taesd.py)."""
+    import os
+    import torch
+    from oracle import sd15_oracle as O
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "taesd_small.pt"))
+    sd = O.synth_state_dict(O.taesd_decoder_param_shapes(), seed=1357)
+    for name in ("a", "b"):
+        y = O.taesd_decode(sd, gold[f"z_{name}"])
+        ref = gold[f"dec_{name}"]
+        assert y.shape == ref.shape
+        assert ((y - ref).norm() / ref.norm()).item() < 1e-5
