@@ -12,6 +12,7 @@
  *   ldn_cfg_step       <- cfg_function + sampler update   src/sample/CFG.py:55-60, src/sample/samplers.py:728-732,952-953
  *   ldn_vae_decode     <- VAE.decode                      src/AutoEncoders/VariationalAE.py:690-722
  *   ldn_vae_encode     <- AutoencodingEngine.encode (w/o the sampling step)  src/AutoEncoders/VariationalAE.py:148-172, 377-413
+ *   ldn_flux_forward   <- Flux3.forward_orig                src/BlackForest/Flux.py:658-730
  *   ldn_taesd_decode   <- TAESD.decode (preview)           src/AutoEncoders/taesd.py:104-136,190-197
  *   ldn_clip_encode    <- CLIPTextModel_.forward          src/clip/CLIPTextModel.py:51-107
  *   op-level entries   <- the torch library calls of      src/cond/cast.py:107,174,241,281 and
@@ -52,7 +53,7 @@ int ldn_create(const ldn_config* cfg, ldn_handle* out);
 void ldn_destroy(ldn_handle h);
 /* which: 0 = UNet ("model.diffusion_model." prefix stripped), 1 = VAE ("first_stage_model." stripped; decoder.* +
  *        post_quant_conv.* and/or encoder.* + quant_conv.*), 2 = CLIP-L text model ("...text_model." stripped),
- *        3 = TAESD preview decoder (keys of taesd_decoder.safetensors) */
+ *        3 = TAESD preview decoder (keys of taesd_decoder.safetensors), 4 = Flux.1 DiT (Flux3 state-dict keys) */
 int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream);
 /* Discrete schedule tables (ModelSamplingDiscrete.sigmas / .log_sigmas, src/sample/sampling.py:221-356): host
  * pointers, n entries each. log_sigmas is passed separately because the reference computes it in float64. */
@@ -81,6 +82,13 @@ int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, i
  * (mean | logvar after quant_conv). The reparameterised sample mean + exp(0.5*clamp(logvar,-30,20))*randn stays with the
  * caller, which owns the RNG (DiagonalGaussianDistribution.sample, VariationalAE.py:42-51). Needs encoder.* weights. */
 int ldn_vae_encode(ldn_handle h, const float* pixels, float* moments, int B, int H, int W, void* stream);
+/* Flux.1 DiT forward (Flux3.forward_orig, src/BlackForest/Flux.py:658-730) on already patchified tokens.
+ * img: [B, n_img, 64] fp32 (2x2 patches of the 16-channel latent), ctx: [B, n_txt, ctx_dim] fp32 (T5 states),
+ * pe: [n_txt + n_img, 64, 2] fp32 (cos, sin) rotary table of EmbedND for the concatenated (txt, img) ids -- shared by all rows,
+ * t / guidance: [B] fp32 (sigma in [0,1]; guidance may be NULL for non-distilled models), y: [B, vec_dim] fp32 (CLIP pooled),
+ * out: [B, n_img, 64] fp32. n_txt must be a multiple of 8. Weights: ldn_load_weights(which = 4), Flux3 state-dict keys. */
+int ldn_flux_forward(ldn_handle h, const float* img, const float* ctx, const float* pe, const float* t,
+                     const float* guidance, const float* y, float* out, int B, int n_img, int n_txt, void* stream);
 /* TAESD preview decoder (src/AutoEncoders/taesd.py:104-136, TAESD.decode :190-197 before its sub(0.5).mul(2)):
  * z: [B,4,h,w] fp32 raw latent; rgb: [B,8h,8w,3] fp32, the decoder's raw output (~[0,1], not clamped).
  * Weights: ldn_load_weights(which = 3) with the keys of taesd_decoder.safetensors (nn.Sequential indices). */

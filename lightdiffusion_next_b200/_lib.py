@@ -49,6 +49,7 @@ SIGNATURES = {
     "ldn_vae_decode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_vae_encode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_taesd_decode": [_p, _p, _p, _i, _i, _i, _p],
+    "ldn_flux_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "ldn_clip_encode": [_p, _p, _i, _p, _p, _p],
     "ldn_gemm_bf16": [_p, _l, _i, _p, _l, _i, _p, _i, _i, _p, _p, _i, _i, _p, _l, _p, _l, _p, _i, _i, _i, _i, _p],
     "ldn_conv3x3_bf16": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],

@@ -54,6 +54,8 @@ struct GemmParams {
   float* out_f32;  // if non-null, write fp32 here instead of bf16 `out`
   const float* bias;
   const float* rowbias;  // [batch, ld_rowbias] added per (batch(row), col)
+  const float* colgate;  // [batch, ld_colgate] multiplies (acc + bias) per (batch(row), col) before the residual (Flux gates)
+  int ld_colgate;
   int ld_rowbias;
   int rows_per_batch;
   const bf16* residual;
@@ -61,7 +63,8 @@ struct GemmParams {
   int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
   int epi_opt;       // bit 0: prefetching epilogue (persistent kernel), bit 1: packed-pair GEGLU arithmetic
   int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77),
-            // 2 ReLU after the bias, 3 ReLU after the residual add (TAESD, src/AutoEncoders/taesd.py:39-63)
+            // 2 ReLU after the bias, 3 ReLU after the residual add (TAESD, src/AutoEncoders/taesd.py:39-63),
+            // 4 GELU (tanh approximation) after the bias (Flux MLPs, src/BlackForest/Flux.py:283-294)
   int row_head_dim, row_head_slot;  // GEMM mode, row_head_dim > 0: output row m -> (m / dim) * slot + m % dim
   // split-K (small-M problems): grid.z splits, each writes an fp32 partial tile; splitk_reduce_kernel finishes
   int splits, chunks_per_split;
@@ -101,6 +104,8 @@ struct GemmArgs {
   float* out_f32 = nullptr;
   const float* bias = nullptr;
   const float* rowbias = nullptr;
+  const float* colgate = nullptr;  // per-(batch, column) gate applied before the residual add
+  int ld_colgate = 0;
   int ld_rowbias = 0;
   int rows_per_batch = 0;
   const bf16* residual = nullptr;
@@ -182,7 +187,7 @@ void launch_layernorm(const bf16* x, int rows, int C, float eps, const float* ga
                       cudaStream_t stream, float* out_f32 = nullptr);
 // out[b, n] = act_in(x[b, :]) . W[n, :] + bias[n]   (tiny-M linear; W bf16 [N, K], x fp32 [Bn, K])
 void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
-                         bool silu_out, float* out, cudaStream_t stream);
+                         bool silu_out, float* out, cudaStream_t stream, long long ldw = 0);  // ldw: weight row stride (0 = K)
 // sigma[B] -> nearest discrete timestep index -> sinusoidal embedding [B, dim] fp32
 void launch_timestep_embed(const float* sigma, int Bn, const float* log_sigmas, int n_sigmas, int dim, float* out,
                            float* t_index_out, cudaStream_t stream);
@@ -202,6 +207,15 @@ void launch_upsample2x(const bf16* x, int B, int H, int W, int C, bf16* out, cud
 void launch_im2col_s2(const bf16* x, int B, int H, int W, int C, bf16* out, cudaStream_t stream, int pad_before = 1);
 void launch_vae_rgb_finish(const float* acc16, const float* bias, size_t npix, int cout, float* out, cudaStream_t stream,
                            int raw = 0);  // raw = 1: acc + bias without the [0,1] image mapping (TAESD)
+// ---- Flux DiT helpers (flux_kernels.cu)
+void launch_flux_temb(const float* t, int B, float* out, cudaStream_t stream);  // timestep_embedding_flux(t, 256)
+void launch_vec_add3(const float* a, const float* b, const float* c, int n, float* out, cudaStream_t stream);
+// out[r, :] = (1 + scale) * LayerNorm(x[r, :], eps 1e-6, no affine) + shift   (shift / scale: fp32 [C])
+void launch_modln(const bf16* x, int rows, int C, const float* shift, const float* scale, bf16* out, cudaStream_t stream);
+// in place on rows [0, rows) of a [*, ld] buffer holding `heads` q heads then `heads` k heads of 128: RMS-norm with the
+// learned scales, then RoPE with pe[row, 64, (cos, sin)]
+void launch_qk_norm_rope(bf16* qk, long long ld, int rows, int heads, const float* q_scale, const float* k_scale,
+                         const float* pe, cudaStream_t stream);
 void launch_vae_moments_finish(const float* acc16, const float* bc, const float* Wq, const float* bq, int B, int HW,
                                int zc2, float* out, cudaStream_t stream);
 // dst[c, b*nk_pad + k] = src[c, b*N + k]: V^T re-laid with 16-byte aligned per-batch column offsets

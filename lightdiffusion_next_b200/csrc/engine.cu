@@ -157,7 +157,7 @@ void ldn_destroy(ldn_handle h) {
 
 int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream_) {
   LDN_API_BEGIN
-  LDN_CHECK(h && tensors && which >= 0 && which < 4, "ldn_load_weights: bad argument");
+  LDN_CHECK(h && tensors && which >= 0 && which < 5, "ldn_load_weights: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   for (int i = 0; i < n; ++i) {
     const ldn_tensor& t = tensors[i];
@@ -245,6 +245,14 @@ int ldn_vae_encode(ldn_handle h, const float* pixels, float* moments, int B, int
   LDN_CHECK(h && pixels && moments, "ldn_vae_encode: bad argument");
   if (!h->finalized[1]) vae_finalize(h, (cudaStream_t)stream);
   vae_encode(h, pixels, moments, B, H, W, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_flux_forward(ldn_handle h, const float* img, const float* ctx, const float* pe, const float* t,
+                     const float* guidance, const float* y, float* out, int B, int n_img, int n_txt, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && img && ctx && pe && t && y && out, "ldn_flux_forward: bad argument");
+  flux_forward(h, img, ctx, pe, t, guidance, y, out, B, n_img, n_txt, (cudaStream_t)stream);
   LDN_API_END
 }
 

@@ -62,8 +62,8 @@ struct Arena {
 struct ldn_engine {
   ldn_config cfg;
   ldn::Arena weights_arena;
-  std::unordered_map<std::string, ldn::DevTensor> w[4];  // 0 unet, 1 vae, 2 clip, 3 taesd (preview decoder)
-  bool finalized[4] = {false, false, false, false};
+  std::unordered_map<std::string, ldn::DevTensor> w[5];  // 0 unet, 1 vae, 2 clip, 3 taesd (preview decoder), 4 flux DiT
+  bool finalized[5] = {false, false, false, false, false};
   float* log_sigmas = nullptr;
   int n_sigmas = 0;
 
@@ -77,6 +77,8 @@ struct ldn_engine {
   std::shared_ptr<ClipState> clip;
   struct TaesdState;
   std::shared_ptr<TaesdState> taesd;
+  struct FluxState;
+  std::shared_ptr<FluxState> flux;
 
   ldn_engine();
   ~ldn_engine();
@@ -96,6 +98,8 @@ int unet_last_launches(ldn_engine* e);
 void vae_finalize(ldn_engine* e, cudaStream_t stream);
 void vae_decode(ldn_engine* e, const float* z, float* rgb, int B, int h, int w, cudaStream_t stream);
 void vae_encode(ldn_engine* e, const float* pixels, float* moments, int B, int H, int W, cudaStream_t stream);
+void flux_forward(ldn_engine* e, const float* img, const float* ctx, const float* pe, const float* t, const float* guidance,
+                  const float* y, float* out, int B, int n_img, int n_txt, cudaStream_t stream);
 void taesd_decode(ldn_engine* e, const float* z, float* rgb, int B, int h, int w, cudaStream_t stream);
 void clip_finalize(ldn_engine* e, cudaStream_t stream);
 void clip_encode(ldn_engine* e, const int64_t* ids, int S, float* out_pen, float* out_last, cudaStream_t stream);

@@ -482,6 +482,8 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.out_f32 = a.out_f32;
   p.bias = a.bias;
   p.rowbias = a.rowbias;
+  p.colgate = a.colgate;
+  p.ld_colgate = a.ld_colgate;
   p.ld_rowbias = a.ld_rowbias;
   p.rows_per_batch = a.rows_per_batch;
   p.residual = a.residual;
@@ -519,7 +521,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   const int tiles = plan.grid.x * plan.grid.y;
   static const bool no_split = getenv("LDN_GEMM_NOSPLIT") != nullptr;  // experiments only
   static const int split_max_tiles = getenv("LDN_GEMM_SPLIT_MAX_TILES") ? atoi(getenv("LDN_GEMM_SPLIT_MAX_TILES")) : 74;
-  if (!no_split && a.splitk_ws && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && a.act == 0 && !a.out_f32 && tiles <= split_max_tiles && p.num_k_chunks >= 40) {
+  if (!no_split && a.splitk_ws && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && a.act == 0 && !a.colgate && !a.out_f32 && tiles <= split_max_tiles && p.num_k_chunks >= 40) {
     int splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > p.num_k_chunks / 8) splits = p.num_k_chunks / 8;
     if (splits > 16) splits = 16;

@@ -107,6 +107,22 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
         } else if (p.act == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+        } else if (p.act == 4) {
+          // GELU, tanh approximation: 0.5 x (1 + tanh(u)) = x / (1 + exp(-2u)), u = sqrt(2/pi) (x + 0.044715 x^3)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = f[i];
+            const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+            f[i] = __fdividef(x, 1.0f + __expf(-2.0f * u));
+          }
+        }
+        if (p.colgate) {
+          const float* gp = p.colgate + (long long)batch * p.ld_colgate + n;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 gv = *reinterpret_cast<const float4*>(gp + i);
+            f[i] *= gv.x; f[i + 1] *= gv.y; f[i + 2] *= gv.z; f[i + 3] *= gv.w;
+          }
         }
         if (p.residual) {
           uint32_t w[8];

@@ -69,7 +69,7 @@ void launch_timestep_embed(const float* sigma, int Bn, const float* log_sigmas, 
 template <int KV>  // 16-byte weight vectors per lane and row: K <= 256 * KV
 __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, const bf16* __restrict__ W,
                                     const float* __restrict__ bias, int N, int silu_in, int silu_out,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, long long ldw) {
   extern __shared__ float s_x[];  // [8][K]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -88,7 +88,7 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, 
     }
     __syncthreads();
     for (int n = blockIdx.x * warps + warp; n < N; n += gridDim.x * warps) {
-      const bf16* w = W + (size_t)n * K;
+      const bf16* w = W + (size_t)n * ldw;
       uint4 u[KV];
 #pragma unroll
       for (int j = 0; j < KV; ++j) {
@@ -138,25 +138,30 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, 
 }
 
 void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
-                         bool silu_out, float* out, cudaStream_t stream) {
-  LDN_CHECK(K % 8 == 0 && K <= 2048, "small_linear: K must be a multiple of 8 and at most 2048");
+                         bool silu_out, float* out, cudaStream_t stream, long long ldw) {
+  LDN_CHECK(K % 8 == 0 && K <= 4096, "small_linear: K must be a multiple of 8 and at most 4096");
+  if (ldw == 0) ldw = K;
+  LDN_CHECK(ldw % 8 == 0, "small_linear: weight row stride must be a multiple of 8");
   const int threads = 256, warps = threads / 32;
   int blocks = (N + warps - 1) / warps;
   if (blocks > 148 * 5) blocks = 148 * 5;
   const size_t smem = sizeof(float) * 8 * K;
   static bool attr = false;
   if (!attr) {
+    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
     LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
   if (K <= 512)
-    small_linear_kernel<2><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out);
+    small_linear_kernel<2><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out, ldw);
   else if (K <= 1280)
-    small_linear_kernel<5><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out);
+    small_linear_kernel<5><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out, ldw);
+  else if (K <= 2048)
+    small_linear_kernel<8><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out, ldw);
   else
-    small_linear_kernel<8><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out);
+    small_linear_kernel<16><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out, ldw);
   LDN_CUDA(cudaGetLastError());
 }
 

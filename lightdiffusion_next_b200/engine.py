@@ -14,7 +14,7 @@ from . import _lib as L
 from .schedule import DiscreteSchedule
 
 _DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
-UNET, VAE, CLIP, TAESD = 0, 1, 2, 3
+UNET, VAE, CLIP, TAESD, FLUX = 0, 1, 2, 3, 4
 
 
 class Engine:
@@ -87,6 +87,11 @@ class Engine:
     def load_taesd(self, state_dict: Dict[str, torch.Tensor]) -> None:
         """TAESD preview decoder weights (keys of `taesd_decoder.safetensors`: nn.Sequential indices, taesd.py:104-136)."""
         self.load_weights(TAESD, state_dict)
+
+    def load_flux(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """Flux.1 DiT weights (Flux3 state-dict keys, src/BlackForest/Flux.py:548-656)."""
+        self.load_weights(FLUX, state_dict)
+        self._flux_pe = {}
 
     def load_checkpoint(self, path: str, lora_path: Optional[str] = None, strength_model: float = 1.0,
                         strength_clip: float = 1.0) -> Dict[str, int]:
@@ -164,6 +169,34 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(self.lib.ldn_taesd_decode(self.h, z.data_ptr(), out.data_ptr(), B, h, w, L.cur_stream()))
         return out
+
+    def flux_forward(self, x: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor, y: torch.Tensor,
+                     guidance: Optional[torch.Tensor] = None, axes_dim=(16, 56, 56), theta: int = 10000) -> torch.Tensor:
+        """Flux3.forward (Flux.py:732-778): latent [B,16,h,w] (even h, w), timestep [B], context [B,Nt,ctx], y [B,vec],
+        guidance [B] -> model output [B,16,h,w] fp32. Patchify / unpatchify and the rotary table are boundary work in torch."""
+        from . import flux as FX
+
+        x = x.to(self.device, torch.float32)
+        B, c, h, w = x.shape
+        img, hl, wl = FX.patchify(x)
+        Nt = context.shape[1]
+        key = (hl, wl, Nt, tuple(axes_dim), theta)
+        cache = self.__dict__.setdefault("_flux_pe", {})
+        pe = cache.get(key)
+        if pe is None:
+            pe = FX.rope_table(hl, wl, Nt, axes_dim, theta).to(self.device).contiguous()
+            cache[key] = pe
+        ctx = context.to(self.device, torch.float32).contiguous()
+        t = timestep.to(self.device, torch.float32).contiguous()
+        yv = y.to(self.device, torch.float32).contiguous()
+        g = guidance.to(self.device, torch.float32).contiguous() if guidance is not None else None
+        out = torch.empty_like(img)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_flux_forward(self.h, img.data_ptr(), ctx.data_ptr(), pe.data_ptr(), t.data_ptr(),
+                                              g.data_ptr() if g is not None else 0, yv.data_ptr(), out.data_ptr(), B,
+                                              hl * wl, Nt, L.cur_stream()))
+        self._keep = [img, ctx, t, yv, g, pe]
+        return FX.unpatchify(out, hl, wl)[:, :, :h, :w]
 
     def clip_encode(self, ids: torch.Tensor):
         """ids [S,77] int64 -> (penultimate-layer output after final LN, last-layer output after final LN)."""
