@@ -332,6 +332,8 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
     finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   } else if (a.d == 80 && p.vt_head_stride == 96 && !a.causal) {
     finish_attn6_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // generation 6: ones-row V^T, P aliased over S in TMEM
+  } else if (a.d == 128 && p.vt_head_stride == 128 && !a.causal && !force_v1) {
+    finish_attn6_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // generation 6 at d = 128 (Flux): row sum in registers
   } else {
     LDN_CHECK(p.vt_head_stride == a.d, "attention: vt_head_stride is only supported as 48 (d = 40) or 96 (d = 80)");
     if (dp <= 64 && !force_v1) finish_attn2_plan(plan, a.Nq, a.Nk, a.heads, a.B);

@@ -1,4 +1,5 @@
-// Attention kernel, sixth generation, head dim 80 (level-1 self-attention of the SD1.5 UNet: N = 4096 tokens at 1024^2;
+// Attention kernel, sixth generation, head dims 80 and 128 (80: level-1 self-attention of the SD1.5 UNet, N = 4096 tokens at
+// 1024^2; 128: Flux.1 joint attention, N = 4352, src/BlackForest/Flux.py:18-33;
 // reference call site CrossAttention.forward src/Attention/Attention.py:100-124 -> attention_pytorch
 // src/Attention/AttentionMethods.py:107-134).
 //
@@ -11,7 +12,9 @@
 // tile is issued right behind P*V by the same thread, so the tensor pipe's issue order protects P from being overwritten.
 // The issue bubble this leaves in one tile's softmax (P*V + next S, ~0.9k clk) is covered by the other tile's softmax.
 //
-// TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,352)  O1 [352,448).
+// At d = 128 O takes 128 columns per tile (2 x (128 + 128) = all 512 TMEM columns), so there is no room for a ones row:
+// the softmax row sum is accumulated in registers from the fp32 exponentials (packed FADD2) and rescaled with O.
+// TMEM columns (d = 80): S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,352)  O1 [352,448);  (d = 128): O0 [256,384)  O1 [384,512).
 // Shared memory: Q 2 tiles x 2 atoms x 16 KB; per ring stage K 2 atoms x 16 KB + V^T 2 atoms x 12 KB (96 rows x 64 keys).
 #include "common.h"
 #include "ptx.cuh"
@@ -27,12 +30,15 @@ using namespace asm_sm;
 static constexpr int kThreads = 384;
 static constexpr int kQ = 128;
 static constexpr int kK = 128;
-static constexpr int kD = 80;
-static constexpr int kDV = 96;  // rows per head in V^T: 80 values, row 80 = ones, rows 81..95 = zeros
+// kD = 80: V^T carries 96 rows per head (80 values, row 80 = ones, rows 81..95 = zeros); kD = 128: plain 128-row V^T
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units
 static constexpr uint32_t kPolyMask = 0x9249u;    // chunks (of 8 keys) whose exponentials run on the FMA pipes
 
+template <int kD>
 __global__ void __launch_bounds__(kThreads, 1) attn6_tc_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int kDV = kD == 80 ? 96 : 128;
+  constexpr bool kOnes = kD == 80;
+  constexpr int kQKSteps = kD / 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -125,11 +131,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn6_tc_kernel(const __grid_cons
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
       if (elect_one()) {
-        tc_mma_bf16(tm_s, qd0, kv0, idesc_s, 0u);
-        tc_mma_bf16(tm_s, qd0 + 2, kv0 + 2, idesc_s, 1u);
-        tc_mma_bf16(tm_s, qd0 + 4, kv0 + 4, idesc_s, 1u);
-        tc_mma_bf16(tm_s, qd0 + 6, kv0 + 6, idesc_s, 1u);
-        tc_mma_bf16(tm_s, qd0 + atom_off, kv0 + atom_off, idesc_s, 1u);
+#pragma unroll
+        for (int ks = 0; ks < kQKSteps; ++ks) {
+          const uint64_t off = (ks < 4) ? (uint64_t)(2 * ks) : atom_off + (uint64_t)(2 * (ks - 4));
+          tc_mma_bf16(tm_s, qd0 + off, kv0 + off, idesc_s, ks > 0 ? 1u : 0u);
+        }
         tc_commit(my_s_full);
       }
       __syncwarp();
@@ -161,11 +167,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn6_tc_kernel(const __grid_cons
           const uint64_t kn = kv0 + (uint64_t)(((uint32_t)s1 * stage_bytes) >> 4);
           if (elect_one()) {
             // issued behind P*V by the same thread: executes after P has been consumed
-            tc_mma_bf16(tm_s, qd0, kn, idesc_s, 0u);
-            tc_mma_bf16(tm_s, qd0 + 2, kn + 2, idesc_s, 1u);
-            tc_mma_bf16(tm_s, qd0 + 4, kn + 4, idesc_s, 1u);
-            tc_mma_bf16(tm_s, qd0 + 6, kn + 6, idesc_s, 1u);
-            tc_mma_bf16(tm_s, qd0 + atom_off, kn + atom_off, idesc_s, 1u);
+#pragma unroll
+            for (int ks = 0; ks < kQKSteps; ++ks) {
+              const uint64_t off = (ks < 4) ? (uint64_t)(2 * ks) : atom_off + (uint64_t)(2 * (ks - 4));
+              tc_mma_bf16(tm_s, qd0 + off, kn + off, idesc_s, ks > 0 ? 1u : 0u);
+            }
             tc_commit(my_s_full);
           }
           __syncwarp();
@@ -189,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn6_tc_kernel(const __grid_cons
     uint64_t* const my_p_full = &p_full[t];
     uint64_t* const my_pv_done = &pv_done[t];
     float m_used = 0.f;  // exponent offset currently baked into O (scaled log2 units)
+    float l_run = 0.f;   // softmax row sum (kept in registers when V^T has no ones row)
 
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(my_s_full, (uint32_t)j & 1u);  // S(j) landed -- and, by issue order, P*V(j-1) finished too
@@ -224,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn6_tc_kernel(const __grid_cons
           const float m_new = need ? mx : m_used;
           const float f = ex2m(m_used - m_new);  // 1 for rows that do not need it
           m_used = m_new;
+          l_run *= f;
 #pragma unroll
           for (int c = 0; c < kDV; c += 16) {
             uint32_t v[16];
@@ -238,13 +246,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn6_tc_kernel(const __grid_cons
       }
       const float m_off = m_used;
 #pragma unroll
+      float2 lacc = make_float2(0.f, 0.f);
+#pragma unroll
       for (int c = 0; c < 16; ++c) {
         uint32_t w[4];
-        exp8_pack(sv + c * 8, sc, -m_off, (int)((kPolyMask >> c) & 1u), w);
+        if (kOnes) exp8_pack(sv + c * 8, sc, -m_off, (int)((kPolyMask >> c) & 1u), w);
+        else exp8_pack_sum(sv + c * 8, sc, -m_off, (int)((kPolyMask >> c) & 1u), w, lacc);
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tmem_p + (uint32_t)(c * 4)), "r"(w[0]),
                      "r"(w[1]), "r"(w[2]), "r"(w[3])
                      : "memory");
       }
+      if (!kOnes) l_run += lacc.x + lacc.y;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(my_p_full);
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn6_tc_kernel(const __grid_cons
       for (int c = 0; c < kDV; c += 16) tmem_ld16(tmem_o + (uint32_t)c, v + c);
       tmem_ld_wait();
       if (q_idx < p.Nq) {
-        const float l = __uint_as_float(v[kD]);
+        const float l = kOnes ? __uint_as_float(v[kOnes ? kD : 0]) : l_run;
         const float inv = l > 0.f ? 1.f / l : 0.f;
         bf16* orow = p.out + ((long long)b * p.Nq + q_idx) * p.ldo + (long long)h * kD;
 #pragma unroll
@@ -284,20 +296,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn6_tc_kernel(const __grid_cons
 
 }  // namespace a6
 
-void launch_attn6(const AttnPlan& plan, cudaStream_t stream) {
+template <int kD>
+static void launch_attn6_t(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDN_CUDA(cudaFuncSetAttribute(a6::attn6_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(a6::attn6_tc_kernel<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  a6::attn6_tc_kernel<<<plan.grid, a6::kThreads, plan.smem_bytes, stream>>>(plan.p);
+  a6::attn6_tc_kernel<kD><<<plan.grid, a6::kThreads, plan.smem_bytes, stream>>>(plan.p);
   LDN_CUDA(cudaGetLastError());
+}
+
+void launch_attn6(const AttnPlan& plan, cudaStream_t stream) {
+  if (plan.p.d == 128) launch_attn6_t<128>(plan, stream);
+  else launch_attn6_t<80>(plan, stream);
 }
 
 void finish_attn6_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B) {
   AttnParams& p = plan.p;
-  LDN_CHECK(p.d == 80 && p.vt_head_stride == a6::kDV && !p.causal, "attention6: d = 80 with 96-row V^T heads, non-causal only");
-  const int stage_bytes = 2 * 16384 + 2 * a6::kDV * 128;
+  LDN_CHECK(!p.causal && ((p.d == 80 && p.vt_head_stride == 96) || (p.d == 128 && p.vt_head_stride == 128)),
+            "attention6: d = 80 with 96-row V^T heads or d = 128, non-causal only");
+  const int dv = p.d == 80 ? 96 : 128;
+  const int stage_bytes = 2 * 16384 + 2 * dv * 128;
   const int fixed = 4 * 16384 + 1024 + 512;
   const int n_tiles = (Nk + a6::kK - 1) / a6::kK;
   int stages = (226 * 1024 - fixed) / stage_bytes;

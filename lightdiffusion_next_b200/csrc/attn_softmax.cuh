@@ -64,5 +64,32 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 
+// exp8_pack that also accumulates the eight fp32 exponentials into a packed running sum (softmax denominator kept in
+// registers when V^T carries no ones row).
+__device__ __forceinline__ void exp8_pack_sum(const uint32_t* s, float sc, float neg_m, int mode, uint32_t* w, float2& acc) {
+  const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(neg_m, neg_m);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 e = ffma2(make_float2(__uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1])), sc2, nm2);
+    if (mode == 1) {
+      e.x = fmaxf(e.x, -125.0f);
+      e.y = fmaxf(e.y, -125.0f);
+      const float2 t = fadd2(e, make_float2(12582912.0f, 12582912.0f));
+      const float2 n = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
+      const float2 f = ffma2(n, make_float2(-1.0f, -1.0f), e);
+      float2 q = ffma2(f, make_float2(0.0555041086f, 0.0555041086f), make_float2(0.2402265070f, 0.2402265070f));
+      q = ffma2(q, f, make_float2(0.6931471806f, 0.6931471806f));
+      q = ffma2(q, f, make_float2(1.0f, 1.0f));
+      e.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+      e.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+    } else {
+      e.x = ex2m(e.x);
+      e.y = ex2m(e.y);
+    }
+    acc = fadd2(acc, e);
+    w[k] = pack_bf16x2(e.x, e.y);
+  }
+}
+
 }  // namespace asm_sm
 }  // namespace ldn

@@ -114,7 +114,10 @@ def test_conv3x3(lib, B, H, W, Cin, Cout):
                                                      # head dim 80, ones-row V^T with 96 rows per head (attention6.cu: P aliased over S in TMEM)
                                                      (2, 8, 1024, 1024, 80, False, True), (1, 8, 4096, 4096, 80, False, True),
                                                      (2, 8, 256, 77, 80, False, True), (1, 2, 200, 1000, 80, False, True),
-                                                     (2, 3, 64, 64, 80, False, True)])
+                                                     (2, 3, 64, 64, 80, False, True),
+                                                     # head dim 128 (Flux joint attention): attention6.cu with the row sum in registers
+                                                     (2, 8, 1024, 1024, 128, False, False), (1, 3, 300, 520, 128, False, False),
+                                                     (1, 24, 4352, 4352, 128, False, False)])
 def test_attention(lib, B, H, Nq, Nk, d, causal, ones):
     L, l = lib
     torch.manual_seed(Nq + Nk + d)
