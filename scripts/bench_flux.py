@@ -4,14 +4,14 @@ Usage: python scripts/bench_flux.py [--txt 256] [--size 1024] [--profile]"""
 import argparse, os, sys, time, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ap = argparse.ArgumentParser(); ap.add_argument("--txt", type=int, default=256); ap.add_argument("--size", type=int, default=1024)
-ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--reps", type=int, default=5); ap.add_argument("--no-graph", action="store_true")
 args = ap.parse_args()
 import torch
 from lightdiffusion_next_b200.engine import Engine
 from lightdiffusion_next_b200 import flux as FX
 cfg = FX.FLUX_DEV
 shapes = FX.flux_shapes(cfg)
-eng = Engine(max_rows=1, max_h=8, max_w=8)
+eng = Engine(max_rows=1, max_h=8, max_w=8, use_graph=not args.no_graph)
 t0 = time.time()
 batch = {}
 nbytes = 0
