@@ -66,19 +66,19 @@ void launch_timestep_embed(const float* sigma, int Bn, const float* log_sigmas, 
 // ------------------------------------------------------------------ tiny-M linear (time-embedding MLP, the 22 emb_layers)
 // HBM-bound on the weight matrix: the (optionally SiLU'd) activations are staged once per block in shared memory and every
 // warp streams whole weight rows with all of a row's 16-byte loads in flight before the first use.
-template <int KV>  // 16-byte weight vectors per lane and row: K <= 256 * KV
+template <int KV, int NB>  // KV: 16-byte weight vectors per lane and row (K <= 256 * KV); NB: activation rows per pass
 __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, const bf16* __restrict__ W,
                                     const float* __restrict__ bias, int N, int silu_in, int silu_out,
                                     float* __restrict__ out, long long ldw) {
-  extern __shared__ float s_x[];  // [8][K]
+  extern __shared__ float s_x[];  // [NB][K]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps = blockDim.x >> 5;
-  for (int b0 = 0; b0 < Bn; b0 += 8) {
-    const int nb = min(8, Bn - b0);
+  for (int b0 = 0; b0 < Bn; b0 += NB) {
+    const int nb = min(NB, Bn - b0);
     __syncthreads();
-    for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
-      const int r = i / K;
+    for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
+      const int r = NB == 1 ? 0 : i / K;
       float v = 0.f;
       if (r < nb) {
         v = x[(size_t)(b0 + r) * K + (i - r * K)];
@@ -95,9 +95,9 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, 
         const int k = lane * 8 + j * 256;
         u[j] = (k < K) ? __ldg(reinterpret_cast<const uint4*>(w + k)) : make_uint4(0, 0, 0, 0);
       }
-      float acc[8];
+      float acc[NB];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+      for (int r = 0; r < NB; ++r) acc[r] = 0.f;
 #pragma unroll
       for (int j = 0; j < KV; ++j) {
         const int k = lane * 8 + j * 256;
@@ -110,20 +110,18 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, 
             wf[2 * i + 1] = bf16_hi(ww[i]);
           }
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            if (r < nb) {
-              const float4 x0 = *reinterpret_cast<const float4*>(s_x + r * K + k);
-              const float4 x1 = *reinterpret_cast<const float4*>(s_x + r * K + k + 4);
-              acc[r] = fmaf(x0.x, wf[0], acc[r]); acc[r] = fmaf(x0.y, wf[1], acc[r]);
-              acc[r] = fmaf(x0.z, wf[2], acc[r]); acc[r] = fmaf(x0.w, wf[3], acc[r]);
-              acc[r] = fmaf(x1.x, wf[4], acc[r]); acc[r] = fmaf(x1.y, wf[5], acc[r]);
-              acc[r] = fmaf(x1.z, wf[6], acc[r]); acc[r] = fmaf(x1.w, wf[7], acc[r]);
-            }
+          for (int r = 0; r < NB; ++r) {  // rows past nb hold zeros in shared memory: no branch needed
+            const float4 x0 = *reinterpret_cast<const float4*>(s_x + r * K + k);
+            const float4 x1 = *reinterpret_cast<const float4*>(s_x + r * K + k + 4);
+            acc[r] = fmaf(x0.x, wf[0], acc[r]); acc[r] = fmaf(x0.y, wf[1], acc[r]);
+            acc[r] = fmaf(x0.z, wf[2], acc[r]); acc[r] = fmaf(x0.w, wf[3], acc[r]);
+            acc[r] = fmaf(x1.x, wf[4], acc[r]); acc[r] = fmaf(x1.y, wf[5], acc[r]);
+            acc[r] = fmaf(x1.z, wf[6], acc[r]); acc[r] = fmaf(x1.w, wf[7], acc[r]);
           }
         }
       }
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < NB; ++r) {
         float v = acc[r];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -137,32 +135,42 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int Bn, int K, 
   }
 }
 
+template <int KV, int NB>
+static void launch_small_linear_t(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
+                                  bool silu_out, float* out, cudaStream_t stream, long long ldw) {
+  const int threads = 256, warps = threads / 32;
+  const size_t smem = sizeof(float) * NB * K;
+  static bool attr = false;
+  if (!attr) {
+    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<KV, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
+    attr = true;
+  }
+  // enough warps in flight to cover HBM latency with one weight row (K * 2 bytes) per warp, a few rows per warp overall
+  int blocks = (N + warps - 1) / warps;
+  const int cap = 148 * (smem > 48 * 1024 ? 2 : 6);
+  if (blocks > cap) blocks = cap;
+  small_linear_kernel<KV, NB><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out,
+                                                                ldw);
+  LDN_CUDA(cudaGetLastError());
+}
+
+template <int KV>
+static void launch_small_linear_kv(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
+                                   bool silu_out, float* out, cudaStream_t stream, long long ldw) {
+  if (Bn == 1) launch_small_linear_t<KV, 1>(x, Bn, K, W, bias, N, silu_in, silu_out, out, stream, ldw);
+  else if (Bn == 2) launch_small_linear_t<KV, 2>(x, Bn, K, W, bias, N, silu_in, silu_out, out, stream, ldw);
+  else launch_small_linear_t<KV, 8>(x, Bn, K, W, bias, N, silu_in, silu_out, out, stream, ldw);
+}
+
 void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const float* bias, int N, bool silu_in,
                          bool silu_out, float* out, cudaStream_t stream, long long ldw) {
   LDN_CHECK(K % 8 == 0 && K <= 4096, "small_linear: K must be a multiple of 8 and at most 4096");
   if (ldw == 0) ldw = K;
   LDN_CHECK(ldw % 8 == 0, "small_linear: weight row stride must be a multiple of 8");
-  const int threads = 256, warps = threads / 32;
-  int blocks = (N + warps - 1) / warps;
-  if (blocks > 148 * 5) blocks = 148 * 5;
-  const size_t smem = sizeof(float) * 8 * K;
-  static bool attr = false;
-  if (!attr) {
-    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
-  if (K <= 512)
-    small_linear_kernel<2><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out, ldw);
-  else if (K <= 1280)
-    small_linear_kernel<5><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out, ldw);
-  else if (K <= 2048)
-    small_linear_kernel<8><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out, ldw);
-  else
-    small_linear_kernel<16><<<blocks, threads, smem, stream>>>(x, Bn, K, W, bias, N, silu_in ? 1 : 0, silu_out ? 1 : 0, out, ldw);
-  LDN_CUDA(cudaGetLastError());
+  if (K <= 512) launch_small_linear_kv<2>(x, Bn, K, W, bias, N, silu_in, silu_out, out, stream, ldw);
+  else if (K <= 1280) launch_small_linear_kv<5>(x, Bn, K, W, bias, N, silu_in, silu_out, out, stream, ldw);
+  else if (K <= 2048) launch_small_linear_kv<8>(x, Bn, K, W, bias, N, silu_in, silu_out, out, stream, ldw);
+  else launch_small_linear_kv<16>(x, Bn, K, W, bias, N, silu_in, silu_out, out, stream, ldw);
 }
 
 // ------------------------------------------------------------------ conv_in: 3x3, tiny Cin, NCHW fp32 -> NHWC bf16
