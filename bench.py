@@ -157,9 +157,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the full-run / pipe() end-to-end secondary numbers")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--workload", default="sd15", choices=["sd15", "flux"],
+                    help="sd15 = BASELINE config 2 (the contract line); flux = config 4, Flux.1-dev sized DiT steps (1 GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "flux":
+        return run_flux(args)
 
     import torch
     import torch.distributed as dist
@@ -353,6 +357,148 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_flux(args):
+    """BASELINE config 4: Flux.1-dev txt2img 1024x1024 bs=1 on one B200 -- the DiT part of a sampler step as the reference
+    runs it: two forwards per step (cond + uncond rows, `disable_cfg1_optimization`, samplers.py:517-520), CONST
+    denoising x - v * sigma (sampling.py:100-127), CFG lerp and an Euler update. Seeded synthetic 11.9 G-parameter weights
+    generated on the device. Same JSON contract; no CPU arm (the fp32 weights alone would need 48 GB of host memory)."""
+    import zlib
+
+    import torch
+
+    from lightdiffusion_next_b200 import _lib as L
+    from lightdiffusion_next_b200 import flux as FX
+    from lightdiffusion_next_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    cfg = FX.FLUX_DEV
+    eng = Engine(max_rows=2, max_h=8, max_w=8, use_graph=not args.no_graph, device=dev)
+    batch, nbytes = {}, 0
+    for k, shp in FX.flux_shapes(cfg).items():
+        g = torch.Generator(device=dev).manual_seed(zlib.crc32(k.encode()) & 0x7FFFFFFF)
+        if len(shp) > 1:
+            w = torch.randn(shp, generator=g, device=dev, dtype=torch.bfloat16)
+            w = (w * ((0.5 if any(t in k for t in ("proj.", "mlp.2", "linear2")) else 1.0) / shp[1] ** 0.5)).to(torch.bfloat16)
+        elif k.endswith(".scale"):
+            w = 1.0 + 0.1 * torch.randn(shp, generator=g, device=dev)
+        else:
+            w = 0.02 * torch.randn(shp, generator=g, device=dev)
+        batch[k] = w
+        nbytes += w.numel() * w.element_size()
+        if nbytes > 2 << 30:
+            eng.load_weights(4, batch)
+            batch, nbytes = {}, 0
+            torch.cuda.empty_cache()
+    if batch:
+        eng.load_weights(4, batch)
+    torch.cuda.empty_cache()
+    lat, n_txt, W, K = args.size // 8, 256, max(3, args.warmup), args.steps
+    g = torch.Generator().manual_seed(1234)
+    ctx = torch.randn(2, n_txt, cfg["context_in_dim"], generator=g).to(dev)
+    y = torch.randn(2, cfg["vec_in_dim"], generator=g).to(dev)
+    guid = torch.full((2,), 3.5, device=dev)
+    x0 = torch.randn(1, 16, lat, lat, generator=g).to(dev)
+    sig = torch.linspace(1.0, 0.0, 31)
+    out, den = torch.empty_like(x0), torch.empty_like(x0)
+    stream = torch.cuda.current_stream()
+
+    def one_step(i, x):
+        j = i % 29
+        s, s_next = float(sig[j]), float(sig[j + 1])
+        v = eng.flux_forward(x.expand(2, -1, -1, -1).contiguous(), torch.full((2,), s, device=dev), ctx, y, guid)
+        d = x - v * s  # CONST.calculate_denoised, rows: uncond first
+        eng.cfg_step(x, d[0:1].contiguous(), d[1:2].contiguous(), 1.0, 1, c0=s_next - s, c1=0.0, c2=s, x_out=out, denoised_out=den)
+        return out.clone()
+
+    x = x0.clone()
+    for i in range(W):
+        x = one_step(i, x)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(dev.index or 0)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        x = one_step(i, x)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    hx = torch.empty(1, 16, lat, lat).pin_memory()
+    hx.copy_(x0.cpu())
+    hout = torch.empty_like(hx).pin_memory()
+    dx = torch.empty_like(x0)
+
+    def e2e_step(i):
+        dx.copy_(hx, non_blocking=True)
+        yv = one_step(i, dx)
+        hout.copy_(yv, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hx.copy_(hout)
+
+    for i in range(2):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    # roofline of the dominant non-GEMM kernel: the joint attention (attention6, d = 128) timed alone
+    lib, H, N, d = eng.lib, cfg["num_heads"], (lat // 2) ** 2 + n_txt, 128
+    Np = (N + 15) // 16 * 16
+    QK = torch.randn(Np, 2 * H * d, device=dev).bfloat16()
+    Vt = torch.randn(H * d, Np, device=dev).bfloat16()
+    Ob = torch.empty(N, H * d, device=dev, dtype=torch.bfloat16)
+
+    def attn():
+        L.check(lib.ldn_attention_bf16(QK.data_ptr(), 2 * H * d, QK.data_ptr() + 2 * H * d, 2 * H * d, Vt.data_ptr(), Np, H * d, 0,
+                                       1, H, N, N, Np, d, d, 0, d ** -0.5, Ob.data_ptr(), H * d, L.cur_stream()))
+    for _ in range(3):
+        attn()
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    for _ in range(10):
+        attn()
+    a1.record(stream)
+    torch.cuda.synchronize()
+    attn_ms = a0.elapsed_time(a1) / 10
+    achieved = 4.0 * H * N * N * d / (attn_ms / 1000.0) / 1e12
+    C, M = cfg["hidden_size"], int(cfg["hidden_size"] * cfg["mlp_ratio"])
+    Ni = (lat // 2) ** 2
+    fwd_tflop = (cfg["depth"] * (2 * N * C * (4 * C + 2 * M) + 4 * N * N * C)
+                 + cfg["depth_single_blocks"] * (2 * N * C * (3 * C + M) + 2 * N * (C + M) * C + 4 * N * N * C)) / 1e12
+    its = K / (ms / 1000.0)
+    line = {
+        "metric": "it/s (Flux DiT sampler steps/sec, 2 forwards per step)", "value": its, "unit": "it/s", "n_gpus": 1, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"Flux.1-dev txt2img {args.size}x{args.size} bs=1 (BASELINE config 4): DiT forward x 2 (cond + uncond) + "
+                               "CONST denoise + CFG + Euler update; text encoders and VAE not included",
+                   "tokens": f"{Ni} image + {n_txt} text", "weights": "seeded synthetic Flux.1-dev layout (11.9 G params, bf16 in HBM)",
+                   "l2": "24 GB of weights stream per forward; no flush needed", "cuda_graph": not args.no_graph,
+                   "finite": bool(torch.isfinite(x).all().item())},
+        "clocks": clk,
+        "e2e": {"value": K / e2e_s, "unit": "it/s", "h2d_bytes_per_step": int(hx.numel() * 4),
+                "d2h_bytes_per_step": int(hout.numel() * 4), "ms_per_step": e2e_s * 1000.0 / K},
+        "gpu_launches": int(K * (2 * 681 + 1)),
+        "roofline": {"bound": "tensor", "kernel": f"a6::attn6_tc_kernel<128> (joint attention, N={N}, d=128, H={H})",
+                     "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
+                     "traffic": None, "peak_source": peaks["source"] + " (burst, kernel timed alone)", "ms_per_launch": attn_ms,
+                     "launches_per_step": 2 * (cfg["depth"] + cfg["depth_single_blocks"])},
+        "step_roofline": {"bound": "tensor", "achieved": its * 2 * fwd_tflop, "peak": peaks["bf16_sus"], "unit": "TFLOP/s",
+                          "frac": its * 2 * fwd_tflop / peaks["bf16_sus"], "tflop_per_step": 2 * fwd_tflop,
+                          "peak_source": peaks["source"] + " (sustained)"},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
 
 
 def secondary_metrics(eng, size: int, dev) -> dict:
