@@ -76,7 +76,8 @@ int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond,
                  float c1, float c2, const float* noise, float* x_out, float* denoised_out, int64_t n, void* stream);
 
 /* ---- VAE decode / CLIP encode */
-/* z: [B,4,h,w] fp32 (already divided by 0.18215); rgb: [B,8h,8w,3] fp32 in [0,1] */
+/* z: [B,zc,h,w] fp32, already un-scaled by the latent format (SD1.x: zc = 4, z / 0.18215; Flux VAE: zc = 16, no
+ * post_quant_conv -- both read off the loaded decoder weights); rgb: [B,8h,8w,3] fp32 in [0,1] */
 int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, int lat_w, void* stream);
 /* pixels: [B,3,H,W] fp32 already mapped to [-1,1] (process_input, VariationalAE.py:601); moments: [B,8,H/8,W/8] fp32
  * (mean | logvar after quant_conv). The reparameterised sample mean + exp(0.5*clamp(logvar,-30,20))*randn stays with the

@@ -196,7 +196,9 @@ void launch_scale_in(const float* x, const float* sigma, int B, int C, int H, in
                      cudaStream_t stream);
 // conv_in: 3x3, Cin=4 (NCHW fp32 input scaled by 1/sqrt(sigma^2+1)), Cout=N -> NHWC bf16
 void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const float* bias, int B, int H, int W,
-                    int Cin, int Cout, bf16* out, cudaStream_t stream, int flags = 0);  // flags: 1 = tanh(x/3)*3 on the input (TAESD Clamp), 2 = ReLU on the output
+                    int Cin, int Cout, bf16* out, cudaStream_t stream, int flags = 0, int ldo = 0);
+// flags: 1 = tanh(x/3)*3 on the input (TAESD Clamp), 2 = ReLU on the output; ldo: output row pitch (0 = Cout) so that a wide
+// layer can be produced in channel slices whose fp32 weights fit in shared memory
 // conv_out: 3x3 Cin -> 4 on NHWC bf16 input; writes denoised = x - eps*sigma (NCHW fp32) and optionally eps
 void launch_conv_out_finish(const float* acc16, const float* bias, const float* x, const float* sigma, int B, int HW,
                             int cout, float* denoised, cudaStream_t stream);

@@ -179,7 +179,7 @@ void launch_small_linear(const float* x, int Bn, int K, const bf16* W, const flo
 // from shared memory feeds 32 FMAs (the one-pixel version sat on the shared-memory bandwidth).
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                const bf16* __restrict__ Wt, const float* __restrict__ bias, int B, int H, int W, int Cin,
-                               int Cout, bf16* __restrict__ out, int flags) {
+                               int Cout, bf16* __restrict__ out, int flags, int ldo) {
   extern __shared__ float s_w[];  // transposed: [9*Cin][Cout] so the 8 output channels of a thread are contiguous
   const int K = 9 * Cin;
   for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) {  // consecutive threads -> consecutive o: conflict-free
@@ -243,15 +243,16 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
         ov.y = pack_bf16x2(acc[px][2], acc[px][3]);
         ov.z = pack_bf16x2(acc[px][4], acc[px][5]);
         ov.w = pack_bf16x2(acc[px][6], acc[px][7]);
-        *reinterpret_cast<uint4*>(out + (((size_t)b * H + y) * W + x0 + px) * Cout + g * 8) = ov;
+        *reinterpret_cast<uint4*>(out + (((size_t)b * H + y) * W + x0 + px) * ldo + g * 8) = ov;
       }
     }
   }
 }
 
 void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const float* bias, int B, int H, int W,
-                    int Cin, int Cout, bf16* out, cudaStream_t stream, int flags) {
+                    int Cin, int Cout, bf16* out, cudaStream_t stream, int flags, int ldo) {
   LDN_CHECK(Cout % 8 == 0, "conv_in: Cout must be a multiple of 8");
+  if (ldo == 0) ldo = Cout;
   const size_t smem = sizeof(float) * Cout * 9 * Cin;
   LDN_CHECK(smem <= 200 * 1024, "conv_in: weights do not fit in shared memory");
   static bool attr = false;
@@ -262,7 +263,7 @@ void launch_conv_in(const float* x, const float* sigma, const bf16* Wt, const fl
   const size_t total = (size_t)B * H * ((W + 3) / 4) * (Cout / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  conv_in_kernel<<<blocks, 256, smem, stream>>>(x, sigma, Wt, bias, B, H, W, Cin, Cout, out, flags);
+  conv_in_kernel<<<blocks, 256, smem, stream>>>(x, sigma, Wt, bias, B, H, W, Cin, Cout, out, flags, ldo);
   LDN_CUDA(cudaGetLastError());
 }
 

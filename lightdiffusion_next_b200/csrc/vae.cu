@@ -20,13 +20,13 @@
 using namespace ldn;
 
 struct ldn_engine::VaeState {
-  int ch = 128, zc = 4, out_ch = 3, num_res = 2;
+  int ch = 128, zc = 4, out_ch = 3, num_res = 2;  // zc is re-read from decoder.conv_in at finalize
   std::vector<int> ch_mult = {1, 2, 4, 4};
   Arena arena;
   float* attn_bias = nullptr;      // decoder mid attention: Wp bv + bp
   float* attn_bias_enc = nullptr;  // encoder mid attention (only when encoder weights were loaded)
   float* quant_w = nullptr;        // quant_conv weight as fp32 [8, 8]
-  bool has_decoder = false, has_encoder = false;
+  bool has_decoder = false, has_encoder = false, has_post_quant = false;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Program>> programs;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Program>> enc_programs;
   std::vector<std::unique_ptr<Arena>> program_arenas;
@@ -40,6 +40,8 @@ void vae_finalize(ldn_engine* e, cudaStream_t stream) {
   auto& V = *e->vae;
   const int C = V.ch * V.ch_mult.back();
   V.has_decoder = e->has(1, "decoder.conv_in.weight");
+  if (V.has_decoder) V.zc = (int)(e->W(1, "decoder.conv_in.weight").shape[1] / 9);  // 4: SD1.x, 16: Flux
+  V.has_post_quant = e->has(1, "post_quant_conv.weight");  // absent in the Flux VAE (AutoencodingEngine flux=True)
   V.has_encoder = e->has(1, "encoder.conv_in.weight");
   LDN_CHECK(V.has_decoder || V.has_encoder, "VAE weights hold neither decoder.* nor encoder.* tensors");
   // attn_bias = proj_out.weight @ v.bias + proj_out.bias  (tiny mat-vec on the device)
@@ -202,24 +204,34 @@ static Program* build_vae_program(ldn_engine* e, int B, int h, int w) {
   prog->out = A.get<float>(out_elems);
 
   const int C = V.ch * V.ch_mult[nlev - 1];
-  // post_quant_conv (1x1 on the fp32 latent), conv_in 4 -> 512
-  {
+  // post_quant_conv (1x1 on the fp32 latent; SD1.x only), conv_in zc -> 512
+  const float* zin = prog->in_x;
+  if (V.has_post_quant) {
     const float* x = prog->in_x;
     const int zc = V.zc, HW = h * w;
-    // post_quant_conv weights are stored bf16 [4,4] by the generic ingest; convert once into fp32 scratch
+    // post_quant_conv weights are stored bf16 [zc,zc] by the generic ingest; convert once into fp32 scratch
     float* wq = A.get<float>(zc * zc);
     launch_convert_to_f32(e->W(1, "post_quant_conv.weight").p, 2, (size_t)zc * zc, wq, 0);
     LDN_CUDA(cudaDeviceSynchronize());
     const float* bq = e->W(1, "post_quant_conv.bias").f();
     vb.add("post_quant_conv", [=](cudaStream_t st) { launch_conv1x1_f32(x, wq, bq, B, zc, zc, HW, zq, st); });
+    zin = zq;
   }
   bf16* hcur = A.get<bf16>((size_t)B * h * w * C);
   {
     const bf16* wt = e->W(1, "decoder.conv_in.weight").b();
     const float* bias = e->W(1, "decoder.conv_in.bias").f();
     const int zc = V.zc;
-    bf16* o = hcur;
-    vb.add("decoder.conv_in", [=](cudaStream_t st) { launch_conv_in(zq, nullptr, wt, bias, B, h, w, zc, C, o, st); });
+    // channel slices so that the slice's fp32 weights (slice * 9 * zc floats) fit in shared memory (16-channel Flux latents)
+    int slice = C;
+    while ((size_t)slice * 9 * zc * sizeof(float) > 160 * 1024 && slice % 16 == 0) slice /= 2;
+    for (int c0 = 0; c0 < C; c0 += slice) {
+      const bf16* wts = wt + (size_t)c0 * 9 * zc;
+      const float* bs = bias + c0;
+      bf16* o = hcur + c0;
+      const int n = std::min(slice, C - c0);
+      vb.add("decoder.conv_in", [=](cudaStream_t st) { launch_conv_in(zin, nullptr, wts, bs, B, h, w, zc, n, o, st, 0, C); });
+    }
   }
   const bf16* x = vb.resnet("decoder.mid.block_1", hcur, h, w, C, C);
   x = vb.attn("decoder.mid.attn_1", x, h, w, C, V.attn_bias);

@@ -457,6 +457,7 @@ def ksample(sd, seed: int, steps: int, cfg: float, sampler: str, scheduler: str,
 # VariationalAE.py:192-221; VAE.decode output mapping :602-604, 690-722)
 # ----------------------------------------------------------------------------------------------------------------
 VAE_CFG = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4, out_ch=3)
+FLUX_VAE_CFG = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16, out_ch=3)  # no (post_)quant_conv
 
 
 def vae_decoder_param_shapes(cfg=VAE_CFG) -> Dict[str, Tuple[int, ...]]:
@@ -480,7 +481,8 @@ def vae_decoder_param_shapes(cfg=VAE_CFG) -> Dict[str, Tuple[int, ...]]:
             conv(p + ".nin_shortcut", cout, cin, 1)
 
     ch, mult, nres = cfg["ch"], cfg["ch_mult"], cfg["num_res_blocks"]
-    conv("post_quant_conv", cfg["z_channels"], cfg["z_channels"], 1)
+    if cfg["z_channels"] == 4:  # the 16-channel Flux VAE has no post_quant_conv
+        conv("post_quant_conv", cfg["z_channels"], cfg["z_channels"], 1)
     block_in = ch * mult[-1]
     conv("decoder.conv_in", block_in, cfg["z_channels"], 3)
     res("decoder.mid.block_1", block_in, block_in)
@@ -511,7 +513,9 @@ def _vae_res(sd, p, x):
 def vae_decode(sd: Dict[str, Tensor], z: Tensor, cfg=VAE_CFG) -> Tensor:
     """z [B,4,h,w] fp32 -> image [B,8h,8w,3] fp32 in [0,1] (what VAEDecode returns)."""
     mult, nres = cfg["ch_mult"], cfg["num_res_blocks"]
-    h = _conv(sd, "post_quant_conv", z.float(), padding=0)
+    h = z.float()
+    if "post_quant_conv.weight" in sd:  # absent in the Flux VAE (AutoencodingEngine flux=True, VariationalAE.py:103-145)
+        h = _conv(sd, "post_quant_conv", h, padding=0)
     h = _conv(sd, "decoder.conv_in", h)
     h = _vae_res(sd, "decoder.mid.block_1", h)
     # AttnBlock: single head over all pixels, d = C

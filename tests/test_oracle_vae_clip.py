@@ -69,3 +69,17 @@ def test_oracle_taesd_decoder_matches_reference_golden():
         ref = gold[f"dec_{name}"]
         assert y.shape == ref.shape
         assert ((y - ref).norm() / ref.norm()).item() < 1e-5
+
+
+def test_oracle_flux_vae_decoder_matches_reference_golden():
+    """16-channel Flux VAE decoder (no post_quant_conv): oracle vs the reference's AutoencodingEngine(flux=True)."""
+    import os
+    import torch
+    from oracle import sd15_oracle as O
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "flux_vae_small.pt"))
+    sd = O.synth_state_dict(O.vae_decoder_param_shapes(O.FLUX_VAE_CFG), seed=9753)
+    assert "post_quant_conv.weight" not in sd
+    for name in ("a", "b"):
+        img = O.vae_decode(sd, gold[f"z_{name}"])
+        ref = gold[f"img_{name}"]
+        assert img.shape == ref.shape and ((img - ref).norm() / ref.norm()).item() < 1e-4
