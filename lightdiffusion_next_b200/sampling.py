@@ -21,7 +21,7 @@ from .engine import Engine
 from .schedule import calculate_sigmas, get_ancestral_step, max_denoise
 
 LATENT_SCALE = 0.18215  # src/Utilities/Latent.py:41-62
-SAMPLERS = ("dpmpp_2m_cfgpp", "euler_ancestral_cfgpp", "dpmpp_sde_cfgpp")
+SAMPLERS = ("dpmpp_2m_cfgpp", "euler_ancestral_cfgpp", "dpmpp_sde_cfgpp", "euler_cfgpp")
 
 
 def prepare_noise(latent: torch.Tensor, seed: int) -> torch.Tensor:
@@ -116,6 +116,40 @@ def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.
         x, loop.x_next = loop.x_next, x
         if callback is not None:
             callback({"x": x, "i": i, "sigma": sig[i], "denoised": den})
+    return x
+
+
+def sample_euler_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float, cfg_scale: float = 7.5,
+                       cfg_min: float = 1.0, callback: Optional[Callable] = None) -> torch.Tensor:
+    """`euler_cfgpp` = sample_euler_dy_cfg_pp as the reference executes it (samplers.py:470-608, the sampler of its Flux
+    pipeline, also selectable for SD1.5): a plain Euler step on the guider's CFG result (the sampler's own CFG++ bookkeeping
+    is reset to None every step, :548-550), plus -- while i // 2 == 1 and sigma_{i+1} > 0 -- the dynamic step
+    dy_sampling_step_cfg_pp (:362-466): the (1,1) pixel of every 2x2 block is denoised again at half resolution, at sigma_i,
+    with the CFG result extrapolated once more from the true uncond by current_cfg = cfg_scale + (cfg_min - cfg_scale) i / n
+    (the sampler's own default cfg_scale = 7.5, not the user's cfg), i.e. uncond + cfg * current_cfg * (cond - uncond)."""
+    B, _, H, W = x.shape
+    sig = sigmas.float().cpu()
+    n = len(sig) - 1
+    loop = SamplerLoop(engine, B, H, W)
+    half = None
+    den = torch.empty_like(x)
+    for i in range(n):
+        du, dc = loop.denoise_pair(x, float(sig[i]))
+        engine.cfg_step(x, du, dc, cfg, 1, c0=float(sig[i + 1] - sig[i]), c1=0.0, c2=float(sig[i]), noise=None,
+                        x_out=loop.x_next, denoised_out=den)
+        x, loop.x_next = loop.x_next, x
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sig[i], "denoised": den})
+        if sig[i + 1] > 0 and i // 2 == 1:
+            m, k = H // 2, W // 2
+            if half is None:
+                half = SamplerLoop(engine, B, m, k)
+            sub = x[:, :, 1:2 * m:2, 1:2 * k:2].contiguous()
+            du2, dc2 = half.denoise_pair(sub, float(sig[i]))
+            current_cfg = cfg_scale + (cfg_min - cfg_scale) * (i / n)
+            engine.cfg_step(sub, du2, dc2, cfg * current_cfg, 1, c0=float(sig[i + 1] - sig[i]), c1=0.0, c2=float(sig[i]),
+                            noise=None, x_out=half.x_next, denoised_out=None)
+            x[:, :, 1:2 * m:2, 1:2 * k:2] = half.x_next
     return x
 
 
@@ -237,6 +271,8 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
     elif sampler_name == "dpmpp_sde_cfgpp":
         x = sample_dpmpp_sde_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, seed=seed,
                                    enable_multiscale=enable_multiscale, callback=callback)
+    elif sampler_name == "euler_cfgpp":
+        x = sample_euler_cfgpp(engine, x, sigmas, cfg, callback=callback)
     else:
         x = sample_euler_ancestral_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, callback=callback)
     out = (x / LATENT_SCALE).to(torch.float32).cpu()

@@ -446,9 +446,43 @@ def ksample(sd, seed: int, steps: int, cfg: float, sampler: str, scheduler: str,
         x = sample_euler_ancestral(denoise, x, sigmas, lambda t: torch.randn_like(t))
     elif sampler == "dpmpp_2m_cfgpp":
         x = sample_dpmpp_2m(denoise, x, sigmas, multiscale=multiscale)
+    elif sampler == "euler_cfgpp":
+        def denoise_pair(xx, ss):
+            b = xx.shape[0]
+            o = model(torch.cat([xx, xx]), torch.cat([ss, ss]), torch.cat([uncond.expand(b, -1, -1), cond.expand(b, -1, -1)]))
+            return o[:b], o[b:]
+        x = sample_euler_cfgpp(denoise_pair, x, sigmas, cfg)
     else:
         raise ValueError(sampler)
     return x / LATENT_SCALE
+
+
+def sample_euler_cfgpp(denoise_pair: Callable[[Tensor, Tensor], Tuple[Tensor, Tensor]], x: Tensor, sigmas: Tensor, cfg: float,
+                       cfg_scale: float = 7.5, cfg_min: float = 1.0) -> Tensor:
+    """sample_euler_dy_cfg_pp AS EXECUTED (samplers.py:470-608). The sampler's own `uncond_denoised` bookkeeping is reset to
+    None on every step by its manual post_cfg_function call (:548-550), so the main update is a plain Euler step on the
+    guider's CFG result; what remains of "CFG++" is the extra dynamic step (dy_sampling_step_cfg_pp, :362-466) run while
+    i // 2 == 1: the (1,1) pixel of every 2x2 block is denoised once more at HALF resolution -- at sigma_i although x has
+    already been stepped to sigma_{i+1} -- with the guider's result extrapolated AGAIN from the true uncond by the sampler's
+    own schedule current_cfg = cfg_scale + (cfg_min - cfg_scale) i / n (cfg_scale = 7.5 by default, not the user's cfg)."""
+    n = len(sigmas) - 1
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(n):
+        current_cfg = cfg_scale + (cfg_min - cfg_scale) * (i / n)
+        u, c = denoise_pair(x, sigmas[i] * s_in)
+        den = u + (c - u) * cfg
+        x = x + (x - den) / sigmas[i] * (sigmas[i + 1] - sigmas[i])
+        if sigmas[i + 1] > 0 and i // 2 == 1:
+            B, C, hh, ww = x.shape
+            m, k = hh // 2, ww // 2
+            sub = x[:, :, 1:2 * m:2, 1:2 * k:2].clone()  # a_list[:, :, :, 1, 1] of the 2x2 unfold
+            u2, c2 = denoise_pair(sub, sigmas[i] * s_in)
+            den2 = u2 + (c2 - u2) * cfg
+            den2 = u2 + (den2 - u2) * current_cfg
+            sub = sub + (sub - den2) / sigmas[i] * (sigmas[i + 1] - sigmas[i])
+            x = x.clone()
+            x[:, :, 1:2 * m:2, 1:2 * k:2] = sub
+    return x
 
 
 # ----------------------------------------------------------------------------------------------------------------

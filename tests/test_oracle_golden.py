@@ -85,3 +85,19 @@ def test_all_scheduler_names_bit_exact():
         name, steps = key.rsplit("_", 1)
         assert torch.equal(O.calculate_sigmas(name, int(steps)), ref), key
         assert torch.equal(S.calculate_sigmas(ms, name, int(steps)), ref), key
+
+
+def test_oracle_euler_cfgpp_vs_reference(unet_sd):
+    """The reference's 4th named sampler (euler_cfgpp = sample_euler_dy_cfg_pp with its dynamic half-resolution steps):
+    oracle trajectory vs full reference KSampler runs (tests/golden/make_golden_euler_cfgpp.py)."""
+    import os
+    import torch
+    from oracle import sd15_oracle as O
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "euler_cfgpp_small.pt"))
+    for name in ("a", "b"):
+        a = gold[f"{name}_args"]
+        out = O.ksample(unet_sd, 42, a["steps"], a["cfg"], "euler_cfgpp", a["scheduler"], gold["ctx_pos"], gold["ctx_neg"],
+                        torch.zeros(1, 4, a["hw"], a["hw"]))
+        ref = gold[f"{name}_final"]
+        err = ((out - ref).norm() / ref.norm()).item()
+        assert err < 1e-4, (name, err)
