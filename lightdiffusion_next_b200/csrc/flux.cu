@@ -26,6 +26,13 @@ struct ldn_engine::FluxState {
   bool guidance = false;
   Arena arena;
   std::vector<float*> proj_bias_img, proj_bias_txt, lin2_bias;  // projection biases with the v bias folded in
+  // every Modulation.lin / adaLN weight stacked into one [mod_total, C] matrix: all of them are functions of the same
+  // conditioning vector, so ONE weight-streaming mat-vec at the start of the forward replaces 77 launches
+  bf16* mod_w = nullptr;
+  float* mod_b = nullptr;
+  long long mod_total = 0;
+  std::vector<long long> mod_off_img, mod_off_txt, mod_off_single;
+  long long mod_off_final = 0;
   std::map<std::tuple<int, int>, std::unique_ptr<Program>> programs;
   std::vector<std::unique_ptr<Arena>> arenas;
   // per-program I/O (indexed like programs)
@@ -70,6 +77,37 @@ static void flux_finalize(ldn_engine* e, cudaStream_t stream) {
     launch_small_linear(e->W(4, p + ".linear1.bias").f() + 2 * C, 1, C, e->W(4, p + ".linear2.weight").b(),
                         e->W(4, p + ".linear2.bias").f(), C, false, false, dst, stream, (long long)C + F.M);
     F.lin2_bias.push_back(dst);
+  }
+  {
+    std::vector<std::pair<std::string, long long>> parts;  // key, rows
+    for (int b = 0; b < F.depth; ++b) {
+      const std::string p = "double_blocks." + std::to_string(b);
+      F.mod_off_img.push_back(F.mod_total);
+      parts.push_back({p + ".img_mod.lin", 6LL * C});
+      F.mod_total += 6LL * C;
+      F.mod_off_txt.push_back(F.mod_total);
+      parts.push_back({p + ".txt_mod.lin", 6LL * C});
+      F.mod_total += 6LL * C;
+    }
+    for (int b = 0; b < F.depth_single; ++b) {
+      F.mod_off_single.push_back(F.mod_total);
+      parts.push_back({"single_blocks." + std::to_string(b) + ".modulation.lin", 3LL * C});
+      F.mod_total += 3LL * C;
+    }
+    F.mod_off_final = F.mod_total;
+    parts.push_back({"final_layer.adaLN_modulation.1", 2LL * C});
+    F.mod_total += 2LL * C;
+    F.mod_w = F.arena.get<bf16>((size_t)F.mod_total * C);
+    F.mod_b = F.arena.get<float>((size_t)F.mod_total);
+    long long off = 0;
+    for (auto& pr : parts) {
+      const DevTensor& w = e->W(4, pr.first + ".weight");
+      LDN_CHECK((long long)w.shape[0] == pr.second && (int)w.shape[1] == C, "Flux: unexpected modulation weight shape: " + pr.first);
+      LDN_CUDA(cudaMemcpyAsync(F.mod_w + (size_t)off * C, w.p, (size_t)pr.second * C * sizeof(bf16), cudaMemcpyDeviceToDevice, stream));
+      LDN_CUDA(cudaMemcpyAsync(F.mod_b + off, e->W(4, pr.first + ".bias").p, (size_t)pr.second * sizeof(float),
+                               cudaMemcpyDeviceToDevice, stream));
+      off += pr.second;
+    }
   }
   LDN_CUDA(cudaStreamSynchronize(stream));
   e->finalized[4] = true;
@@ -120,8 +158,7 @@ static Program* build_flux_program(ldn_engine* e, int Ni, int Nt, ldn_engine::Fl
   float* te = A.get<float>(256);
   float* h1 = A.get<float>(C);
   float *v_t = A.get<float>(C), *v_g = A.get<float>(C), *v_y = A.get<float>(C), *vec = A.get<float>(C);
-  float* mod_i = A.get<float>(6 * C);
-  float* mod_t = A.get<float>(6 * C);
+  float* mod_all = A.get<float>((size_t)F.mod_total);
 
   // ---- conditioning vector (Flux.py:676-689): time_in(temb(t)) [+ guidance_in(temb(g))] + vector_in(y)
   add("temb.t", [=](cudaStream_t st) { launch_flux_temb(io.t, 1, te, st); });
@@ -137,6 +174,12 @@ static Program* build_flux_program(ldn_engine* e, int Ni, int Nt, ldn_engine::Fl
   {
     const float* g = F.guidance ? v_g : nullptr;
     add("vec", [=](cudaStream_t st) { launch_vec_add3(v_t, g, v_y, C, vec, st); });
+  }
+  {
+    const bf16* mw = F.mod_w;
+    const float* mb = F.mod_b;
+    const int total = (int)F.mod_total;
+    add("modulation.all", [=](cudaStream_t st) { launch_small_linear(vec, 1, C, mw, mb, total, true, false, mod_all, st); });
   }
   // ---- img_in / txt_in into the two row ranges of X
   bf16* Xt = X;
@@ -188,8 +231,8 @@ static Program* build_flux_program(ldn_engine* e, int Ni, int Nt, ldn_engine::Fl
   // ---- double-stream blocks
   for (int b = 0; b < F.depth; ++b) {
     const std::string p = "double_blocks." + std::to_string(b);
-    small(p + ".img_mod", vec, C, p + ".img_mod.lin", 6 * C, true, false, mod_i);
-    small(p + ".txt_mod", vec, C, p + ".txt_mod.lin", 6 * C, true, false, mod_t);
+    float* mod_i = mod_all + F.mod_off_img[b];
+    float* mod_t = mod_all + F.mod_off_txt[b];
     // image rows must write v^T after the text rows (a text range that is not a multiple of 16 zero-pads into the image columns)
     add(p + ".txt.ln1", [=](cudaStream_t st) { launch_modln(Xt, Nt, C, mod_t, mod_t + C, sA, st); });
     qkv(p + ".txt", p + ".txt_attn.qkv", 0, Nt, p + ".txt_attn.norm");
@@ -222,7 +265,7 @@ static Program* build_flux_program(ldn_engine* e, int Ni, int Nt, ldn_engine::Fl
   // ---- single-stream blocks over the whole buffer
   for (int b = 0; b < F.depth_single; ++b) {
     const std::string p = "single_blocks." + std::to_string(b);
-    small(p + ".mod", vec, C, p + ".modulation.lin", 3 * C, true, false, mod_i);
+    float* mod_i = mod_all + F.mod_off_single[b];
     add(p + ".ln", [=](cudaStream_t st) { launch_modln(X, N, C, mod_i, mod_i + C, sA, st); });
     qkv(p, p + ".linear1", 0, N, p + ".norm");
     {
@@ -239,7 +282,7 @@ static Program* build_flux_program(ldn_engine* e, int Ni, int Nt, ldn_engine::Fl
     gemm(p + ".linear2", l2);
   }
   // ---- LastLayer on the image rows (Flux.py:458-471): shift, scale = adaLN(silu(vec)).chunk(2)
-  small("final.adaLN", vec, C, "final_layer.adaLN_modulation.1", 2 * C, true, false, mod_i);
+  float* mod_i = mod_all + F.mod_off_final;
   add("final.ln", [=](cudaStream_t st) { launch_modln(Xi, Ni, C, mod_i, mod_i + C, sA, st); });
   {
     GemmArgs a;
