@@ -120,36 +120,43 @@ def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.
 
 
 def sample_euler_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float, cfg_scale: float = 7.5,
-                       cfg_min: float = 1.0, callback: Optional[Callable] = None) -> torch.Tensor:
+                       cfg_min: float = 1.0, callback: Optional[Callable] = None,
+                       pair_fn: Optional[Callable] = None) -> torch.Tensor:
     """`euler_cfgpp` = sample_euler_dy_cfg_pp as the reference executes it (samplers.py:470-608, the sampler of its Flux
     pipeline, also selectable for SD1.5): a plain Euler step on the guider's CFG result (the sampler's own CFG++ bookkeeping
     is reset to None every step, :548-550), plus -- while i // 2 == 1 and sigma_{i+1} > 0 -- the dynamic step
     dy_sampling_step_cfg_pp (:362-466): the (1,1) pixel of every 2x2 block is denoised again at half resolution, at sigma_i,
     with the CFG result extrapolated once more from the true uncond by current_cfg = cfg_scale + (cfg_min - cfg_scale) i / n
-    (the sampler's own default cfg_scale = 7.5, not the user's cfg), i.e. uncond + cfg * current_cfg * (cond - uncond)."""
+    (the sampler's own default cfg_scale = 7.5, not the user's cfg), i.e. uncond + cfg * current_cfg * (cond - uncond).
+    pair_fn(x, sigma) -> (denoised_uncond, denoised_cond) replaces the SD1.5 UNet call (used by the Flux path)."""
     B, _, H, W = x.shape
     sig = sigmas.float().cpu()
     n = len(sig) - 1
-    loop = SamplerLoop(engine, B, H, W)
+    loop = SamplerLoop(engine, B, H, W) if pair_fn is None else None
     half = None
+    x_next = torch.empty_like(x)
     den = torch.empty_like(x)
     for i in range(n):
-        du, dc = loop.denoise_pair(x, float(sig[i]))
+        du, dc = loop.denoise_pair(x, float(sig[i])) if pair_fn is None else pair_fn(x, float(sig[i]))
         engine.cfg_step(x, du, dc, cfg, 1, c0=float(sig[i + 1] - sig[i]), c1=0.0, c2=float(sig[i]), noise=None,
-                        x_out=loop.x_next, denoised_out=den)
-        x, loop.x_next = loop.x_next, x
+                        x_out=x_next, denoised_out=den)
+        x, x_next = x_next, x
         if callback is not None:
             callback({"x": x, "i": i, "sigma": sig[i], "denoised": den})
         if sig[i + 1] > 0 and i // 2 == 1:
             m, k = H // 2, W // 2
-            if half is None:
-                half = SamplerLoop(engine, B, m, k)
             sub = x[:, :, 1:2 * m:2, 1:2 * k:2].contiguous()
-            du2, dc2 = half.denoise_pair(sub, float(sig[i]))
+            if pair_fn is None:
+                if half is None:
+                    half = SamplerLoop(engine, B, m, k)
+                du2, dc2 = half.denoise_pair(sub, float(sig[i]))
+            else:
+                du2, dc2 = pair_fn(sub, float(sig[i]))
             current_cfg = cfg_scale + (cfg_min - cfg_scale) * (i / n)
+            sub_next = torch.empty_like(sub)
             engine.cfg_step(sub, du2, dc2, cfg * current_cfg, 1, c0=float(sig[i + 1] - sig[i]), c1=0.0, c2=float(sig[i]),
-                            noise=None, x_out=half.x_next, denoised_out=None)
-            x[:, :, 1:2 * m:2, 1:2 * k:2] = half.x_next
+                            noise=None, x_out=sub_next, denoised_out=None)
+            x[:, :, 1:2 * m:2, 1:2 * k:2] = sub_next
     return x
 
 

@@ -36,6 +36,30 @@ class DiscreteSchedule:
         return ((1 - w) * self.log_sigmas[low] + w * self.log_sigmas[high]).exp()
 
 
+class FluxSchedule:
+    """ModelSamplingFlux (src/sample/sampling.py:172-218): flow-matching time shift sigma(t) = e^mu / (e^mu + (1/t - 1)),
+    mu = shift = 1.15 by default, tabulated at t = 1/10000 ... 1; the model's timestep IS sigma. Duck-types
+    DiscreteSchedule for calculate_sigmas (the reference's Flux pipeline uses the `beta` scheduler)."""
+
+    def __init__(self, shift: float = 1.15, timesteps: int = 10000):
+        self.shift = shift
+        self.sigmas = self.sigma(torch.arange(1, timesteps + 1, 1) / timesteps)
+
+    @property
+    def sigma_min(self) -> torch.Tensor:
+        return self.sigmas[0]
+
+    @property
+    def sigma_max(self) -> torch.Tensor:
+        return self.sigmas[-1]
+
+    def timestep(self, sigma: torch.Tensor) -> torch.Tensor:
+        return sigma
+
+    def sigma(self, timestep: torch.Tensor) -> torch.Tensor:
+        return math.exp(self.shift) / (math.exp(self.shift) + (1 / timestep - 1) ** 1.0)
+
+
 def get_sigmas_karras(n: int, sigma_min: float, sigma_max: float, rho: float = 7.0) -> torch.Tensor:
     ramp = torch.linspace(0, 1, n)
     min_inv_rho = sigma_min ** (1 / rho)

@@ -19,4 +19,9 @@ for name in ("karras", "normal", "simple", "beta"):
     for steps in (1, 4, 10, 20, 30, 50):
         out[f"{name}_{steps}"] = ksampler_util.calculate_sigmas(ms, name, steps).clone()
         print(name, steps, tuple(out[f"{name}_{steps}"].shape))
+fm = sampling.ModelSamplingFlux()
+out["flux_sigmas"] = fm.sigmas.clone()
+for name in ("simple", "beta"):  # ModelSamplingFlux has no sigma_min: karras / normal raise in the reference itself
+    for steps in (4, 20, 28):
+        out[f"flux__{name}_{steps}"] = ksampler_util.calculate_sigmas(fm, name, steps).clone()
 torch.save(out, os.path.join(HERE, "schedules.pt"))

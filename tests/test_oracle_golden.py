@@ -81,7 +81,15 @@ def test_all_scheduler_names_bit_exact():
     from lightdiffusion_next_b200 import schedule as S
     gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "schedules.pt"))
     ms = S.DiscreteSchedule()
+    fm = S.FluxSchedule()
+    assert torch.equal(fm.sigmas, gold["flux_sigmas"])  # ModelSamplingFlux table (shift 1.15, 10000 entries)
     for key, ref in gold.items():
+        if key == "flux_sigmas":
+            continue
+        if key.startswith("flux__"):
+            name, steps = key[len("flux__"):].rsplit("_", 1)
+            assert torch.equal(S.calculate_sigmas(fm, name, int(steps)), ref), key
+            continue
         name, steps = key.rsplit("_", 1)
         assert torch.equal(O.calculate_sigmas(name, int(steps)), ref), key
         assert torch.equal(S.calculate_sigmas(ms, name, int(steps)), ref), key
