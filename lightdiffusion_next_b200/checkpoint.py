@@ -38,6 +38,8 @@ _LORA_CLIP_MAP = {
 
 def load_state_dict_file(path: str) -> Dict[str, torch.Tensor]:
     """Read a checkpoint container into a flat `{key: cpu tensor}` dict."""
+    if path.endswith(".gguf"):
+        return load_gguf(path, handle_prefix=None)
     if path.endswith((".safetensors", ".sft")):
         from safetensors.torch import load_file
 
@@ -46,6 +48,46 @@ def load_state_dict_file(path: str) -> Dict[str, torch.Tensor]:
     if isinstance(sd, dict) and "state_dict" in sd and isinstance(sd["state_dict"], dict):
         sd = sd["state_dict"]
     return sd
+
+
+def load_gguf(path: str, handle_prefix: Optional[str] = "model.diffusion_model.", dtype: torch.dtype = torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """GGUF container (Flux / SD checkpoints quantised by llama.cpp-style tools) -> plain `{key: cpu tensor}`.
+
+    The reference keeps Q8_0 weights packed and dequantises them inside every Linear call (GGMLOps,
+    src/Quantize/Quantizer.py:352-390; gguf_sd_loader :581-666; dequantize_blocks_Q8_0 :94-104). Here the blocks are
+    dequantised ONCE at ingest -- w = d * q with d the block's fp16 scale and q its 32 int8 values, exactly the reference's
+    arithmetic -- and stored as bf16 in HBM (a B200 holds the 24 GB of Flux.1-dev in bf16 eight times over). F32 / F16 / BF16
+    tensors pass through; other quantisation types are rejected, as the reference's dequantize table only knows Q8_0.
+    Uses the same third-party `gguf` reader the reference depends on (requirements: gguf)."""
+    import gguf
+    import numpy as np
+
+    reader = gguf.GGUFReader(path)
+    names = [t.name for t in reader.tensors]
+    strip = len(handle_prefix) if handle_prefix and any(n.startswith(handle_prefix) for n in names) else 0
+    out: Dict[str, torch.Tensor] = {}
+    Q = gguf.GGMLQuantizationType
+    for t in reader.tensors:
+        if strip and not t.name.startswith(handle_prefix):
+            continue
+        key = t.name[strip:]
+        shape = tuple(int(v) for v in reversed(t.shape))  # GGUF stores dimensions innermost-first
+        data = np.asarray(t.data)
+        if t.tensor_type == Q.F32:
+            w = torch.from_numpy(data.copy()).view(torch.float32).reshape(shape)
+        elif t.tensor_type == Q.F16:
+            w = torch.from_numpy(data.copy()).view(torch.float16).reshape(shape)
+        elif t.tensor_type == Q.BF16:
+            w = torch.from_numpy(data.copy()).view(torch.bfloat16).reshape(shape)
+        elif t.tensor_type == Q.Q8_0:
+            blocks = torch.from_numpy(data.copy()).view(torch.uint8).reshape(-1, 34)  # 2-byte fp16 scale + 32 int8
+            d = blocks[:, :2].contiguous().view(torch.float16).to(torch.float32)
+            q = blocks[:, 2:].contiguous().view(torch.int8).to(torch.float32)
+            w = (d * q).reshape(shape).to(dtype)
+        else:
+            raise ValueError(f"GGUF tensor {t.name!r} has unsupported type {t.tensor_type!r} (F32, F16, BF16, Q8_0 are handled)")
+        out[key] = w
+    return out
 
 
 def _strip(sd: Mapping[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:

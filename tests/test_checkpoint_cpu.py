@@ -129,3 +129,40 @@ def test_merge_lora_matches_reference_formula():
     # zero strength is a no-op
     again = {p: {k: v.clone() for k, v in d.items()} for p, d in ref.items()}
     assert C.merge_lora(again, lora, 0.0, 0.0) == 0
+
+
+def test_gguf_q8_0_ingest(tmp_path):
+    """GGUF reader: Q8_0 blocks are dequantised once (w = d * q, the reference's dequantize_blocks_Q8_0 arithmetic), F32 /
+    F16 pass through, the model prefix is stripped like gguf_sd_loader does, unknown quantisations are rejected."""
+    import gguf
+    import numpy as np
+    rng = np.random.default_rng(0)
+    w_q = rng.standard_normal((48, 64)).astype(np.float32)          # rows of 64 = 2 Q8_0 blocks each
+    w_h = rng.standard_normal((8, 16)).astype(np.float16)
+    b_f = rng.standard_normal((48,)).astype(np.float32)
+    path = str(tmp_path / "tiny.gguf")
+    wr = gguf.GGUFWriter(path, "flux")
+    q = gguf.quants.quantize(w_q, gguf.GGMLQuantizationType.Q8_0)
+    wr.add_tensor("model.diffusion_model.double_blocks.0.img_attn.proj.weight", q, raw_dtype=gguf.GGMLQuantizationType.Q8_0)
+    wr.add_tensor("model.diffusion_model.img_in.weight", w_h)
+    wr.add_tensor("model.diffusion_model.img_in.bias", b_f)
+    wr.add_tensor("some.other.tensor", b_f)
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    sd = C.load_gguf(path)
+    assert set(sd) == {"double_blocks.0.img_attn.proj.weight", "img_in.weight", "img_in.bias"}
+    ref = torch.from_numpy(gguf.quants.dequantize(q, gguf.GGMLQuantizationType.Q8_0))
+    got = sd["double_blocks.0.img_attn.proj.weight"]
+    assert got.dtype == torch.bfloat16 and got.shape == (48, 64)
+    assert torch.equal(got, ref.to(torch.bfloat16))                 # same d * q product, one rounding to bf16
+    assert (got.float() - torch.from_numpy(w_q)).abs().max() < 0.05  # and it is the quantised original
+    assert torch.equal(sd["img_in.weight"], torch.from_numpy(w_h)) and sd["img_in.weight"].dtype == torch.float16
+    assert torch.equal(sd["img_in.bias"], torch.from_numpy(b_f))
+    # through the generic entry point (no prefix handling) every tensor is returned
+    assert len(C.load_state_dict_file(path)) == 4
+    # an unsupported quantisation is refused loudly
+    p2 = str(tmp_path / "q4.gguf")
+    wr = gguf.GGUFWriter(p2, "flux")
+    wr.add_tensor("w", gguf.quants.quantize(w_q, gguf.GGMLQuantizationType.Q4_0), raw_dtype=gguf.GGMLQuantizationType.Q4_0)
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    with pytest.raises(ValueError, match="unsupported type"):
+        C.load_gguf(p2)
