@@ -22,21 +22,27 @@ class Pipeline:
         self.e = engine
 
     # ---------------------------------------------------------------- CLIPTextEncode (src/clip/Clip.py:574-589)
-    def encode(self, tokens: Sequence[Sequence[Tuple[int, float]]]) -> torch.Tensor:
+    def encode(self, tokens: Sequence[Sequence[Tuple[int, float]]], return_pooled: bool = False):
         """tokens: k chunks of 77 (id, weight) pairs -> conditioning [1, 77*k, 768] (layer -2 + final LN).
-        Prompt weights: per-token lerp against the empty-prompt encoding (ClipTokenWeightEncoder, SDClip.py:54-76)."""
+        Prompt weights: per-token lerp against the empty-prompt encoding (ClipTokenWeightEncoder, SDClip.py:54-76).
+        return_pooled: also return the pooled vector [1, 768] of the first chunk -- the last layer's final-LN state at the
+        first end-of-text token (CLIPTextModel_.forward, src/clip/CLIPTextModel.py:95-105; the `y` input of Flux)."""
         ids = torch.tensor([[t for t, _ in row] for row in tokens], dtype=torch.int64)
         wts = torch.tensor([[w for _, w in row] for row in tokens], dtype=torch.float32)
         has_w = bool((wts != 1.0).any())
         if has_w:
             ids = torch.cat([ids, torch.tensor([EMPTY_TOKENS], dtype=torch.int64)])
-        pen, _ = self.e.clip_encode(ids)
+        pen, last = self.e.clip_encode(ids)
+        if return_pooled:
+            eos = int((ids[0] == EMPTY_TOKENS[-1]).int().argmax())
+            pooled = last[0:1, eos].clone()
         if has_w:
             z_empty = pen[-1]
             pen = pen[:-1]
             w = wts.to(pen.device)[:, :, None]
             pen = (pen - z_empty) * w + z_empty
-        return pen.reshape(1, -1, pen.shape[-1])
+        cond = pen.reshape(1, -1, pen.shape[-1])
+        return (cond, pooled) if return_pooled else cond
 
     # ---------------------------------------------------------------- KSampler (src/sample/sampling.py:773-887)
     def sample(self, positive: torch.Tensor, negative: torch.Tensor, width: int, height: int, batch: int = 1,
