@@ -30,6 +30,11 @@ def test_pipeline_tokens_to_image(unet_sd):
     cond = pipe.encode(toks)
     assert cond.shape == (1, 77, 768) and rel(cond, g["weighted_cond"]) < 2e-2
     plain = [[(t, 1.0) for t in g["plain_ids"][0].tolist()]]
+    # pooled vector (Flux `y`): last layer + final LN at the first end-of-text token (CLIPTextModel.py:95-105)
+    cond_p, pooled = pipe.encode(plain, return_pooled=True)
+    _, last = O.clip_encode(csd, g["plain_ids"])
+    eos = int((g["plain_ids"][0] == 49407).int().argmax())
+    assert pooled.shape == (1, 768) and rel(pooled, last[0:1, eos]) < 2e-2
     # full path: 2 images, 3 steps, 256x256; compared with the oracle run on the same tokens / seed
     img = pipe(plain, None, width=256, height=256, batch=2, seed=7, steps=3, cfg=7.0)
     assert img.shape == (2, 256, 256, 3) and torch.isfinite(img).all()
