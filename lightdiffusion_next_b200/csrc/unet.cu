@@ -374,7 +374,7 @@ struct Builder {
     const long long Mm = a.conv ? (long long)a.B * a.H * a.W : a.M;
     const long long Kk = a.conv ? 9LL * a.Cin : (long long)a.K0 + a.K1;
     add(name + " [M=" + std::to_string(Mm) + " N=" + std::to_string(a.N) + " K=" + std::to_string(Kk) + "]",
-        [plan](cudaStream_t st) { launch_gemm(plan, st); });
+        [plan](cudaStream_t st) { launch_gemm(plan, st); }, plan.p.splits > 1 ? 2 : 1);  // split-K adds its reduce kernel
   }
   void groupnorm(const std::string& name, const bf16* x0, int C0, const bf16* x1, int C1, int HW, float eps,
                  const std::string& wprefix, bool silu, bf16* out) {
@@ -382,7 +382,7 @@ struct Builder {
     const float* b = e->W(0, wprefix + ".bias").f();
     float* ws = gn_ws;
     int Bn = B;
-    add(name, [=](cudaStream_t st) { launch_groupnorm(x0, C0, x1, C1, Bn, HW, 32, eps, g, b, silu, out, ws, st); }, 3);
+    add(name, [=](cudaStream_t st) { launch_groupnorm(x0, C0, x1, C1, Bn, HW, 32, eps, g, b, silu, out, ws, st); }, 2);  // stats + apply
   }
   void layernorm(const std::string& name, const bf16* x, int rows, int C, const std::string& wprefix, bf16* out) {
     const float* g = e->W(0, wprefix + ".weight").f();

@@ -91,7 +91,7 @@ struct VB {
     const float* b = e->W(1, wp + ".bias").f();
     float* ws = gn_ws;
     const int Bn = B;
-    add(name, [=](cudaStream_t st) { launch_groupnorm(x, C, nullptr, 0, Bn, HW, 32, 1e-6f, g, b, silu, out, ws, st); }, 3);
+    add(name, [=](cudaStream_t st) { launch_groupnorm(x, C, nullptr, 0, Bn, HW, 32, 1e-6f, g, b, silu, out, ws, st); }, 2);
   }
   void conv(const std::string& name, const std::string& wp, const bf16* x, int H, int W, int Cin, int Cout,
             const bf16* residual, bf16* out) {
