@@ -82,6 +82,7 @@ struct GemmPlan {
   int pgrid = 0;  // CTAs of the persistent kernel (<= SM count)
   bool pair = false;  // CTA-pair kernel (gemm_pair.cu); pgrid is then an even CTA count
   int pair_smem_bytes = 0;
+  bool pair_occ2 = false;  // one tile per CTA pair, two CTAs per SM (single accumulator stage)
 };
 
 struct GemmArgs {

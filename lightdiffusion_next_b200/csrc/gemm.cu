@@ -564,20 +564,31 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   static const int pair_mode = getenv("LDN_GEMM_PAIR") ? atoi(getenv("LDN_GEMM_PAIR")) : 0;
   // 1: every eligible GEMM; 2: only those that would otherwise run the one-tile-per-CTA kernel (long K: convs)
   const bool pair_ok = BN >= 32 && BN % 16 == 0 && plan.grid.y >= 2 && !force_v1;
-  plan.pair = pair_ok && (pair_mode == 1 || (pair_mode == 2 && !plan.persistent) || (pair_mode == 3 && plan.persistent));
+  plan.pair = pair_ok && (pair_mode == 1 || (pair_mode == 2 && !plan.persistent) || (pair_mode == 3 && plan.persistent) ||
+                          (pair_mode == 4 && !plan.persistent));
   if (plan.pair) {
     p.tmB2 = make_tmap_2d(a.Wt, a.wt_rows > 0 ? a.wt_rows : a.N, K, a.wt_ld > 0 ? a.wt_ld : K, BN / 2);
     int acc_stride = 32;
     while (acc_stride < BN) acc_stride <<= 1;
-    p.tmem_cols = 2 * acc_stride;
     const int stage2 = kBM * kBK * 2 + (BN / 2) * kBK * 2;
-    int pst = (225 * 1024 - 2048) / stage2;
-    if (pst > 10) pst = 10;
-    p.stages = pst;
-    plan.pair_smem_bytes = pst * stage2 + 1024 + 512;
     const int m_pairs = ((int)plan.grid.y + 1) / 2;
     const int total_pairs = (int)plan.grid.x * m_pairs * (int)plan.grid.z;
-    plan.pgrid = 2 * (total_pairs < 74 ? total_pairs : 74);
+    plan.pair_occ2 = pair_mode == 4;
+    if (plan.pair_occ2) {
+      p.tmem_cols = acc_stride;  // <= 256: two CTAs per SM share the 512 columns
+      int pst = (113 * 1024 - 1024 - 512) / stage2;
+      if (pst > p.chunks_per_split) pst = p.chunks_per_split;
+      p.stages = pst;
+      plan.pair_smem_bytes = pst * stage2 + 1024 + 512;
+      plan.pgrid = 2 * total_pairs;
+    } else {
+      p.tmem_cols = 2 * acc_stride;
+      int pst = (225 * 1024 - 2048) / stage2;
+      if (pst > 10) pst = 10;
+      p.stages = pst;
+      plan.pair_smem_bytes = pst * stage2 + 1024 + 512;
+      plan.pgrid = 2 * (total_pairs < 74 ? total_pairs : 74);
+    }
   }
   return plan;
 }

@@ -21,7 +21,10 @@
 
 namespace ldn {
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+// kOcc = 1: persistent (one pair per TPC walks a tile list, two accumulator stages); kOcc = 2: one tile per pair, two CTAs
+// (of different pairs) per SM overlap each other's epilogue and main loop -- the arrangement that wins for long-K convs.
+template <int kOcc>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
     gemm_tc_pair_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -38,7 +41,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   uint64_t* tfull_bar = empty_bar + stages;   // [2] accumulator ready (both CTAs)
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained (leader only: 16 arrivals, 8 per CTA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const uint32_t acc_stride = (uint32_t)p.tmem_cols / 2;
+  const uint32_t acc_stride = kOcc == 1 ? (uint32_t)p.tmem_cols / 2 : 0u;  // kOcc = 2: a single accumulator stage
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA0);
@@ -210,10 +213,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 void launch_gemm_pair(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr = true;
   }
-  gemm_tc_pair_kernel<<<plan.pgrid, kGemmThreads, plan.pair_smem_bytes, stream>>>(plan.p);
+  if (plan.pair_occ2)
+    gemm_tc_pair_kernel<2><<<plan.pgrid, kGemmThreads, plan.pair_smem_bytes, stream>>>(plan.p);
+  else
+    gemm_tc_pair_kernel<1><<<plan.pgrid, kGemmThreads, plan.pair_smem_bytes, stream>>>(plan.p);
   LDN_CUDA(cudaGetLastError());
 }
 
