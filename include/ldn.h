@@ -15,6 +15,7 @@
  *   ldn_flux_forward   <- Flux3.forward_orig                src/BlackForest/Flux.py:658-730
  *   ldn_taesd_decode   <- TAESD.decode (preview)           src/AutoEncoders/taesd.py:104-136,190-197
  *   ldn_clip_encode    <- CLIPTextModel_.forward          src/clip/CLIPTextModel.py:51-107
+ *   ldn_t5_encode      <- T5.forward (Flux text encoder)  src/clip/FluxClip.py:457-562
  *   op-level entries   <- the torch library calls of      src/cond/cast.py:107,174,241,281 and
  *                         optimized_attention             src/Attention/Attention.py:34-41
  */
@@ -97,6 +98,13 @@ int ldn_taesd_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h,
 /* ids: [S,77] int64 (device); out_last: [S,77,768] fp32 final-LN of last layer (may be NULL);
  * out_penultimate: [S,77,768] fp32 final-LN of layer -2 (what SD1.5 uses) */
 int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultimate, float* out_last, void* stream);
+/* T5 text encoder of the Flux path (T5.forward / T5Stack.forward, src/clip/FluxClip.py:457-562; no attention mask, layer
+ * "last" + final RMS norm as T5XXLModel configures SDClipModel, :565-590).  ids: [S,n] int64 (device), any n >= 1;
+ * rel_buckets: [2n-1] int32 (device), the reference's relative-position bucket (T5Attention._relative_position_bucket,
+ * :153-205) of every distance key - query = -(n-1) .. n-1, computed by the host mirror with the reference's own fp32
+ * arithmetic; out: [S,n,d_model] fp32.  Weights: ldn_load_weights(which = 5) with the state-dict keys of the reference's
+ * T5 module (shared.weight, encoder.block.N.layer.{0,1}.*, encoder.final_layer_norm.weight); heads must be 64 wide. */
+int ldn_t5_encode(ldn_handle h, const int64_t* ids, const int32_t* rel_buckets, int S, int n, float* out, void* stream);
 
 /* ---- op-level entries (used by the parity tests; same kernels the engine runs) */
 /* out[M,N] = [A0 | A1][M,K0+K1] * Wt[N,K]^T (+bias) (+rowbias[row / rows_per_batch]) (+residual); bf16 in/out.

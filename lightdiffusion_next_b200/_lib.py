@@ -51,6 +51,7 @@ SIGNATURES = {
     "ldn_taesd_decode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_flux_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "ldn_clip_encode": [_p, _p, _i, _p, _p, _p],
+    "ldn_t5_encode": [_p, _p, _p, _i, _i, _p, _p],
     "ldn_gemm_bf16": [_p, _l, _i, _p, _l, _i, _p, _i, _i, _p, _p, _i, _i, _p, _l, _p, _l, _p, _i, _i, _i, _i, _p],
     "ldn_conv3x3_bf16": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
     "ldn_attention_bf16": [_p, _l, _p, _l, _p, _l, _l, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _l, _p],

@@ -32,7 +32,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-template <int DV>
+// kBias: an additive logit bias (fp32, already multiplied by log2 e, [heads, bias_rows, bias_ld], padded to whole
+// 128 x 128 tiles so every read of a tile is in range) is added to scale * q.k before the softmax -- T5's relative
+// position bias (t5.cu).  The kBias = false instantiations are unchanged.
+template <int DV, bool kBias = false>
 __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -183,12 +186,25 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
       const bool need_mask = limit < kTileK;
       // pass 1: row max
       float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
+      const float* brow = nullptr;
+      if constexpr (kBias) brow = p.bias + ((long long)h * p.bias_rows + q_idx) * p.bias_ld + kbase;
 #pragma unroll
       for (int c = 0; c < kTileK; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_s + lane_off + (uint32_t)c, v);
         tmem_ld_wait();
-        if (need_mask) {
+        if constexpr (kBias) {  // max of the biased, scaled logits
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(brow + c + i);
+            const float t0 = fmaf(__uint_as_float(v[i]), sc, bv.x), t1 = fmaf(__uint_as_float(v[i + 1]), sc, bv.y);
+            const float t2 = fmaf(__uint_as_float(v[i + 2]), sc, bv.z), t3 = fmaf(__uint_as_float(v[i + 3]), sc, bv.w);
+            if (c + i < limit) mxa[0] = fmaxf(mxa[0], t0);
+            if (c + i + 1 < limit) mxa[1] = fmaxf(mxa[1], t1);
+            if (c + i + 2 < limit) mxa[2] = fmaxf(mxa[2], t2);
+            if (c + i + 3 < limit) mxa[3] = fmaxf(mxa[3], t3);
+          }
+        } else if (need_mask) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (c + i < limit) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v[i]));
@@ -198,7 +214,7 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
         }
       }
       const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-      const float m_new = fmaxf(m_run, mx * sc);
+      const float m_new = fmaxf(m_run, kBias ? mx : mx * sc);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = fast_exp2(m_run - m_use);   // m_run = -inf -> 0
       float rsa[4] = {0.f, 0.f, 0.f, 0.f};
@@ -211,8 +227,14 @@ __global__ void __launch_bounds__(kAttnThreads, (DV <= 80) ? 2 : 1) attn_tc_kern
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, -m_use));
-          float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -m_use));
+          float sh0 = -m_use, sh1 = -m_use;
+          if constexpr (kBias) {
+            const float2 bv = *reinterpret_cast<const float2*>(brow + c + i);
+            sh0 += bv.x;
+            sh1 += bv.y;
+          }
+          float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, sh0));
+          float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, sh1));
           if (need_mask) {
             if (c + i >= limit) p0 = 0.f;
             if (c + i + 1 >= limit) p1 = 0.f;
@@ -299,6 +321,15 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.out = a.out;
   p.ldo = a.ldo;
+  p.bias = a.bias;
+  p.bias_rows = a.bias_rows;
+  p.bias_ld = a.bias_ld;
+  if (a.bias) {
+    LDN_CHECK(a.d == 64 && !a.causal && a.vt_head_stride == 0, "attention: logit bias needs d = 64, no causal mask, plain V^T");
+    LDN_CHECK(a.bias_rows >= (a.Nq + kTileQ - 1) / kTileQ * kTileQ && a.bias_ld >= (a.Nk + kTileK - 1) / kTileK * kTileK &&
+                  a.bias_ld % 4 == 0,
+              "attention: logit bias must be padded to whole 128 x 128 tiles");
+  }
   p.tmQ = make_tmap_2d(a.Q, (uint64_t)a.B * a.Nq, (uint64_t)a.heads * a.slot, a.ldq, 128);
   p.tmK = make_tmap_2d(a.K, (uint64_t)a.B * p.k_batch_stride, (uint64_t)a.heads * a.slot, a.ldk, 128);
   p.tmVt = make_tmap_2d(a.Vt, (uint64_t)a.vt_rows, (uint64_t)a.B * a.nk_pad, a.ldvt, a.vt_head_stride > 0 ? a.vt_head_stride : dp);
@@ -336,19 +367,19 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
     finish_attn6_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // generation 6 at d = 128 (Flux): row sum in registers
   } else {
     LDN_CHECK(p.vt_head_stride == a.d, "attention: vt_head_stride is only supported as 48 (d = 40) or 96 (d = 80)");
-    if (dp <= 64 && !force_v1) finish_attn2_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+    if (dp <= 64 && !force_v1 && !a.bias) finish_attn2_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   }
   return plan;
 }
 
-template <int DV>
+template <int DV, bool kBias = false>
 static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDN_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DV, kBias>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  attn_tc_kernel<DV><<<plan.grid, kAttnThreads, plan.smem_bytes, stream>>>(plan.p);
+  attn_tc_kernel<DV, kBias><<<plan.grid, kAttnThreads, plan.smem_bytes, stream>>>(plan.p);
   LDN_CUDA(cudaGetLastError());
 }
 
@@ -356,6 +387,10 @@ void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
   if (plan.p.variant == 6) return launch_attn6(plan, stream);
   if (plan.p.variant == 5) return launch_attn5(plan, stream);
   if (plan.p.variant == 2) return launch_attn2(plan, stream);
+  if (plan.p.bias) {
+    LDN_CHECK(plan.p.dv == 64, "attention: the logit-bias variant is built for head dim 64 only");
+    return launch_attn_t<64, true>(plan, stream);
+  }
   switch (plan.p.dv) {
     case 48: launch_attn_t<48>(plan, stream); break;
     case 64: launch_attn_t<64>(plan, stream); break;

@@ -146,6 +146,8 @@ struct AttnParams {
   int poly_mod;      // variant 2: every poly_mod-th group of 8 exponentials runs on the FMA pipes (0 = all MUFU)
   bf16* out;         // [B*Nq, heads*d]
   long long ldo;
+  const float* bias; // variant 1 only: additive logit bias * log2(e), [heads, bias_rows, bias_ld] (nullptr = none)
+  int bias_rows, bias_ld;
 };
 struct AttnPlan {
   AttnParams p;
@@ -167,6 +169,8 @@ struct AttnArgs {
   float scale;
   bf16* out;
   long long ldo;
+  const float* bias = nullptr;  // additive logit bias * log2(e), fp32 [heads, bias_rows, bias_ld], shared by all batches; rows / columns padded to multiples of 128 (d = 64, non-causal only)
+  int bias_rows = 0, bias_ld = 0;
 };
 AttnPlan make_attn_plan(const AttnArgs& a);
 void finish_attn2_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);

@@ -157,7 +157,7 @@ void ldn_destroy(ldn_handle h) {
 
 int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream_) {
   LDN_API_BEGIN
-  LDN_CHECK(h && tensors && which >= 0 && which < 5, "ldn_load_weights: bad argument");
+  LDN_CHECK(h && tensors && which >= 0 && which < 6, "ldn_load_weights: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   for (int i = 0; i < n; ++i) {
     const ldn_tensor& t = tensors[i];
@@ -166,7 +166,8 @@ int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, 
     DevTensor d;
     size_t numel = 1;
     for (int k = 0; k < t.ndim; ++k) numel *= (size_t)t.shape[k];
-    const bool keep_f32 = t.ndim == 1 || name.find("embedding") != std::string::npos;
+    const bool keep_f32 = t.ndim == 1 || name.find("embedding") != std::string::npos ||
+                          name.find("relative_attention_bias") != std::string::npos;  // T5 logit-bias table [32, heads]
     if (keep_f32) {
       d.is_bf16 = false;
       d.shape.assign(t.shape, t.shape + t.ndim);
@@ -268,6 +269,14 @@ int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultim
   LDN_CHECK(h && ids, "ldn_clip_encode: bad argument");
   if (!h->finalized[2]) clip_finalize(h, (cudaStream_t)stream);
   clip_encode(h, ids, S, out_penultimate, out_last, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_t5_encode(ldn_handle h, const int64_t* ids, const int32_t* rel_buckets, int S, int n, float* out, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && ids && rel_buckets && out, "ldn_t5_encode: bad argument");
+  LDN_CHECK(!h->w[5].empty(), "ldn_t5_encode: T5 weights not loaded");
+  t5_encode(h, ids, rel_buckets, S, n, out, (cudaStream_t)stream);
   LDN_API_END
 }
 

@@ -62,8 +62,8 @@ struct Arena {
 struct ldn_engine {
   ldn_config cfg;
   ldn::Arena weights_arena;
-  std::unordered_map<std::string, ldn::DevTensor> w[5];  // 0 unet, 1 vae, 2 clip, 3 taesd (preview decoder), 4 flux DiT
-  bool finalized[5] = {false, false, false, false, false};
+  std::unordered_map<std::string, ldn::DevTensor> w[6];  // 0 unet, 1 vae, 2 clip, 3 taesd (preview decoder), 4 flux DiT, 5 T5 text encoder
+  bool finalized[6] = {false, false, false, false, false, false};
   float* log_sigmas = nullptr;
   int n_sigmas = 0;
 
@@ -79,6 +79,8 @@ struct ldn_engine {
   std::shared_ptr<TaesdState> taesd;
   struct FluxState;
   std::shared_ptr<FluxState> flux;
+  struct T5State;
+  std::shared_ptr<T5State> t5;
 
   ldn_engine();
   ~ldn_engine();
@@ -103,4 +105,5 @@ void flux_forward(ldn_engine* e, const float* img, const float* ctx, const float
 void taesd_decode(ldn_engine* e, const float* z, float* rgb, int B, int h, int w, cudaStream_t stream);
 void clip_finalize(ldn_engine* e, cudaStream_t stream);
 void clip_encode(ldn_engine* e, const int64_t* ids, int S, float* out_pen, float* out_last, cudaStream_t stream);
+void t5_encode(ldn_engine* e, const int64_t* ids, const int32_t* rel_buckets, int S, int n, float* out, cudaStream_t stream);
 }  // namespace ldn

@@ -14,7 +14,7 @@ from . import _lib as L
 from .schedule import DiscreteSchedule
 
 _DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
-UNET, VAE, CLIP, TAESD, FLUX = 0, 1, 2, 3, 4
+UNET, VAE, CLIP, TAESD, FLUX, T5 = 0, 1, 2, 3, 4, 5
 
 
 class Engine:
@@ -92,6 +92,12 @@ class Engine:
         """Flux.1 DiT weights (Flux3 state-dict keys, src/BlackForest/Flux.py:548-656)."""
         self.load_weights(FLUX, state_dict)
         self._flux_pe = {}
+
+    def load_t5(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """T5 text-encoder weights (state-dict keys of the reference's T5 module, src/clip/FluxClip.py:501-531; see
+        t5.t5_shapes).  Heads must be 64 wide (T5-XXL: 4096 / 64)."""
+        self.load_weights(T5, state_dict)
+        self._t5_width = int(state_dict["shared.weight"].shape[1])
 
     def load_checkpoint(self, path: str, lora_path: Optional[str] = None, strength_model: float = 1.0,
                         strength_clip: float = 1.0) -> Dict[str, int]:
@@ -208,3 +214,21 @@ class Engine:
             L.check(self.lib.ldn_clip_encode(self.h, ids.data_ptr(), S, pen.data_ptr(), last.data_ptr(),
                                              L.cur_stream()))
         return pen, last
+
+    def t5_encode(self, ids: torch.Tensor) -> torch.Tensor:
+        """ids [S,n] int64 -> final-RMS-norm of the last T5 block's states, [S,n,d_model] fp32 (T5.forward without a mask,
+        src/clip/FluxClip.py:457-562)."""
+        from . import t5 as T5H
+
+        width = getattr(self, "_t5_width", None)
+        if width is None:
+            raise L.LdnError("T5 weights not loaded (Engine.load_t5)")
+        ids = ids.to(self.device, torch.int64).contiguous()
+        S, n = ids.shape
+        buckets = T5H.relative_position_buckets(n).to(self.device)
+        with torch.cuda.device(self.device):
+            out = torch.empty(S, n, width, device=self.device, dtype=torch.float32)
+            L.check(self.lib.ldn_t5_encode(self.h, ids.data_ptr(), buckets.data_ptr(), S, n, out.data_ptr(), L.cur_stream()))
+        self._keep = [ids, buckets]
+        return out
+
