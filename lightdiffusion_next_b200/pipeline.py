@@ -93,3 +93,50 @@ def hires_fix(pipe: "Pipeline", samples: torch.Tensor, positive: torch.Tensor, n
 
     up = latent_upscale({"samples": samples}, width * 2, height * 2)
     return S.sample(pipe.e, seed, steps, cfg, sampler_name, scheduler, positive, negative, up, denoise=denoise)[0]["samples"]
+
+
+class FluxPipeline:
+    """The Flux branch of `pipeline()` (src/user/pipeline.py:218-275) on one engine holding the Flux DiT (load_flux), the
+    T5-XXL and CLIP-L text encoders (load_t5 / load_clip) and the 16-channel autoencoder (load_vae):
+    CLIPTextEncodeFlux -> ConditioningZeroOut -> KSampler(euler_cfgpp, beta, cfg 1, flux=True) -> VAEDecode(flux=True).
+    Tokenisation stays with the caller: `clip_tokens` as for `Pipeline.encode`, `t5_tokens` = the T5 tokenizer's rows of
+    (id, weight) (t5.pad_tokens builds one from sentencepiece ids)."""
+
+    def __init__(self, engine: Engine):
+        self.e = engine
+        self._clip = Pipeline(engine)
+
+    def encode(self, clip_tokens, t5_tokens, guidance: float = 3.0) -> Dict[str, object]:
+        """CLIPTextEncodeFlux.encode (src/Quantize/Quantizer.py:960-990): FluxClipModel.encode_token_weights returns the T5
+        states as the conditioning and CLIP-L's pooled vector (src/clip/FluxClip.py:704-718)."""
+        from . import t5 as T5H
+
+        _, pooled = self._clip.encode(clip_tokens, return_pooled=True)
+        return {"cond": T5H.encode_token_weights(self.e, t5_tokens), "pooled_output": pooled, "guidance": float(guidance)}
+
+    @staticmethod
+    def zero_out(conditioning: Dict[str, object]) -> Dict[str, object]:
+        """ConditioningZeroOut.zero_out (src/Quantize/Quantizer.py:993-1012): the negative of the Flux branch."""
+        return {"cond": torch.zeros_like(conditioning["cond"]), "pooled_output": torch.zeros_like(conditioning["pooled_output"]),
+                "guidance": conditioning["guidance"]}
+
+    def sample(self, positive: Dict[str, object], negative: Dict[str, object], width: int, height: int, batch: int = 1,
+               seed: int = 0, steps: int = 20, cfg: float = 1.0, scheduler: str = "beta") -> torch.Tensor:
+        """EmptyLatentImage (4 zero channels, repeated to the model's 16 by fix_empty_latent_channels,
+        src/Utilities/Latent.py:192-204) -> the Flux KSampler call of pipeline.py:251-264."""
+        from . import flux_sampling as FS
+
+        latent = {"samples": torch.zeros(batch, 16, height // 8, width // 8)}
+        return FS.sample_flux(self.e, seed, steps, (positive["cond"], positive["pooled_output"]),
+                              (negative["cond"], negative["pooled_output"]), latent, cfg=cfg,
+                              guidance=float(positive["guidance"]), scheduler=scheduler)[0]["samples"]
+
+    def decode(self, samples: torch.Tensor) -> torch.Tensor:
+        """VAEDecode(flux=True): latents in the autoencoder's space (process_out applied by the sampler) -> [B,H,W,3] in [0,1]."""
+        return self.e.vae_decode(samples).cpu()
+
+    def __call__(self, clip_tokens, t5_tokens, width: int = 1024, height: int = 1024, batch: int = 1, seed: int = 0,
+                 steps: int = 20, guidance: float = 3.0) -> torch.Tensor:
+        pos = self.encode(clip_tokens, t5_tokens, guidance)
+        return self.decode(self.sample(pos, self.zero_out(pos), width, height, batch, seed, steps))
+
