@@ -50,6 +50,10 @@ for k in sd:
         over[k] = (1.0 + 0.1 * torch.randn(sd[k].shape, generator=g)).half().float()
     elif k.endswith("relative_attention_bias.weight"):  # logit biases of order 1 so the buckets matter
         over[k] = torch.randn(sd[k].shape, generator=g).half().float()
+    elif k.endswith("SelfAttention.q.weight"):
+        # T5 applies no 1/sqrt(d) logit scale; trained checkpoints carry it in q. Unit-variance q and k over 64 dims would give
+        # logits of std 8 -- a softmax so peaked that fp32-vs-bf16 differences of ANY implementation are amplified.
+        over[k] = (sd[k] * 0.125).half().float()
     elif k == "shared.weight":
         over[k] = torch.randn(sd[k].shape, generator=g).half().float()
 sd.update(over)
