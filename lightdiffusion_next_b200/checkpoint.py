@@ -90,6 +90,31 @@ def load_gguf(path: str, handle_prefix: Optional[str] = "model.diffusion_model."
     return out
 
 
+# llama.cpp tensor names of a T5 encoder -> state-dict keys of the reference's T5 module, applied as successive substring
+# replacements in this order (clip_sd_map / gguf_clip_loader, src/Quantize/Quantizer.py:815-858).
+T5_GGUF_KEY_MAP = (
+    ("enc.", "encoder."), (".blk.", ".block."), ("token_embd", "shared"), ("output_norm", "final_layer_norm"),
+    ("attn_q", "layer.0.SelfAttention.q"), ("attn_k", "layer.0.SelfAttention.k"), ("attn_v", "layer.0.SelfAttention.v"),
+    ("attn_o", "layer.0.SelfAttention.o"), ("attn_norm", "layer.0.layer_norm"),
+    ("attn_rel_b", "layer.0.SelfAttention.relative_attention_bias"), ("ffn_up", "layer.1.DenseReluDense.wi_1"),
+    ("ffn_down", "layer.1.DenseReluDense.wo"), ("ffn_gate", "layer.1.DenseReluDense.wi_0"), ("ffn_norm", "layer.1.layer_norm"),
+)
+
+
+def load_t5_gguf(path: str, dtype: torch.dtype = torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """`t5-v1_1-xxl-encoder-Q8_0.gguf` (the Flux text encoder the reference's pipeline loads, src/user/pipeline.py:233-237)
+    -> the T5 state dict `Engine.load_t5` takes.  Like the reference, a file without encoder feed-forward tensors is refused."""
+    raw = load_gguf(path, handle_prefix=None, dtype=dtype)
+    if not any(k.startswith("enc.blk.") and k.endswith(".ffn_up.weight") for k in raw):
+        raise ValueError(f"{path}: not a T5 encoder GGUF (no enc.blk.N.ffn_up.weight tensors)")
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in raw.items():
+        for a, b in T5_GGUF_KEY_MAP:
+            k = k.replace(a, b)
+        out[k] = v
+    return out
+
+
 def _strip(sd: Mapping[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
     n = len(prefix)
     return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}

@@ -77,5 +77,17 @@ z, _ = model.encode_token_weights([rowd])
 out["weights_d"], out["out_d"] = [w for _, w in rowd], z.float().clone()
 print("c/d", tuple(z.shape), float((out["out_d"] - out["out_c"]).abs().max()), flush=True)
 out["buckets_300"] = RC.T5Attention._relative_position_bucket(torch.arange(300)[None, :] - torch.arange(300)[:, None]).to(torch.uint8)
+# the reference's GGUF name map (clip_sd_map, src/Quantize/Quantizer.py:815-858) applied to llama.cpp's T5 encoder names
+from src.Quantize import Quantizer as RQ  # noqa: E402
+names = ["token_embd.weight", "enc.output_norm.weight"] + [
+    f"enc.blk.{i}.{n}.weight" for i in (0, 23) for n in ("attn_q", "attn_k", "attn_v", "attn_o", "attn_norm", "attn_rel_b",
+                                                         "ffn_up", "ffn_down", "ffn_gate", "ffn_norm")]
+mapped = {}
+for k in names:
+    m = k
+    for a, b in RQ.clip_sd_map.items():
+        m = m.replace(a, b)
+    mapped[k] = m
+out["gguf_name_map"] = mapped
 torch.save(out, os.path.join(HERE, "t5_small.pt"))
 print("wrote t5_small.pt", os.path.getsize(os.path.join(HERE, "t5_small.pt")))

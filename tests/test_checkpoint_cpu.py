@@ -1,5 +1,7 @@
 """Host-side checkpoint ingest (lightdiffusion_next_b200/checkpoint.py): container read, SD1.5 prefix split + layout
 validation, LoRA merge arithmetic (reference: Loader.py:11-111, SD15.py:32-69, LoRas.py:15-121, ModelPatcher.py:621-650)."""
+import os
+
 import pytest
 import torch
 
@@ -166,3 +168,60 @@ def test_gguf_q8_0_ingest(tmp_path):
     wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
     with pytest.raises(ValueError, match="unsupported type"):
         C.load_gguf(p2)
+
+
+def test_t5_gguf_key_map(tmp_path):
+    """llama.cpp T5 encoder names -> the reference's T5 state-dict keys (clip_sd_map, Quantizer.py:815-858): the mapped dict
+    has exactly the layout Engine.load_t5 expects; Q8_0 matrices are dequantised once, F32 norms pass through."""
+    import gguf
+    import numpy as np
+    from lightdiffusion_next_b200 import t5 as T5H
+    shapes = T5H.t5_shapes(d_model=64, d_ff=96, num_heads=1, num_layers=2, vocab_size=40)
+    inv = {"shared": "token_embd", "encoder.final_layer_norm": "enc.output_norm"}
+    sub = {"layer.0.SelfAttention.q": "attn_q", "layer.0.SelfAttention.k": "attn_k", "layer.0.SelfAttention.v": "attn_v",
+           "layer.0.SelfAttention.o": "attn_o", "layer.0.layer_norm": "attn_norm",
+           "layer.0.SelfAttention.relative_attention_bias": "attn_rel_b", "layer.1.DenseReluDense.wi_1": "ffn_up",
+           "layer.1.DenseReluDense.wo": "ffn_down", "layer.1.DenseReluDense.wi_0": "ffn_gate", "layer.1.layer_norm": "ffn_norm"}
+    rng = np.random.default_rng(1)
+    path = str(tmp_path / "t5.gguf")
+    wr = gguf.GGUFWriter(path, "t5encoder")
+    want = {}
+    for key, shape in shapes.items():
+        stem = key[:-len(".weight")]
+        if stem in inv:
+            name = inv[stem]
+        else:
+            blk, rest = stem[len("encoder.block."):].split(".", 1)
+            name = f"enc.blk.{blk}.{sub[rest]}"
+        w = rng.standard_normal(shape).astype(np.float32)
+        if len(shape) == 2 and shape[1] % 32 == 0:
+            q = gguf.quants.quantize(w, gguf.GGMLQuantizationType.Q8_0)
+            wr.add_tensor(name + ".weight", q, raw_dtype=gguf.GGMLQuantizationType.Q8_0)
+            want[key] = torch.from_numpy(gguf.quants.dequantize(q, gguf.GGMLQuantizationType.Q8_0)).to(torch.bfloat16)
+        else:
+            wr.add_tensor(name + ".weight", w)
+            want[key] = torch.from_numpy(w)
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    sd = C.load_t5_gguf(path)
+    assert {k: tuple(v.shape) for k, v in sd.items()} == shapes
+    for k in shapes:
+        assert torch.equal(sd[k], want[k]), k
+    # a GGUF that is not a T5 encoder is refused (the reference asserts on enc.blk.23.ffn_up.weight)
+    p2 = str(tmp_path / "other.gguf")
+    wr = gguf.GGUFWriter(p2, "flux")
+    wr.add_tensor("img_in.bias", rng.standard_normal((8,)).astype(np.float32))
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    with pytest.raises(ValueError, match="not a T5 encoder"):
+        C.load_t5_gguf(p2)
+
+
+def test_t5_gguf_key_map_matches_reference_map():
+    """Every llama.cpp T5 name maps exactly as the reference's own clip_sd_map maps it (fixture from make_golden_t5.py)."""
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "t5_small.pt"))
+    from lightdiffusion_next_b200 import t5 as T5H
+    xxl = T5H.t5_shapes()
+    for name, want in gold["gguf_name_map"].items():
+        got = name
+        for a, b in C.T5_GGUF_KEY_MAP:
+            got = got.replace(a, b)
+        assert got == want and want in xxl, (name, got, want)
