@@ -47,3 +47,18 @@ def test_unequal_context_lengths_are_tiled_to_lcm(unet_sd):
     S.sample(eng, 1, 1, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, {"samples": torch.zeros(1, 4, 16, 16)})
     assert eng.ctx.shape == (2, 154, 768)
     assert torch.equal(eng.ctx[0, :77], neg[0]) and torch.equal(eng.ctx[0, 77:], neg[0]) and torch.equal(eng.ctx[1], pos[0])
+
+
+def test_inpaint_noise_mask_is_inert_like_the_reference(unet_sd):
+    """`latent["noise_mask"]` (SetLatentNoiseMask -> common_ksampler, sampling.py:1203-1221): the reference hands it to
+    KSamplerX0Inpaint, whose __call__ forwards to the model without blending (sampling.py:363-378), so for the SD1.5 UNet a
+    mask changes nothing -- recorded from a reference run by tests/golden/make_golden_mask.py.  The engine's sample() takes
+    the same latent dict and reproduces the reference's result bit for bit in behaviour: the mask is accepted and inert."""
+    from fake_engine import FakeEngine
+    from lightdiffusion_next_b200 import sampling as S
+    g = torch.load(os.path.join(GOLDEN, "hires_small.pt"))
+    m = torch.load(os.path.join(GOLDEN, "mask_small.pt"))
+    assert m["equals_unmasked"] and torch.equal(m["masked_final"], g["hires_final"])
+    e = S.sample(FakeEngine(unet_sd), 43, 4, 8.0, "dpmpp_2m_cfgpp", "normal", g["ctx_pos"], g["ctx_neg"],
+                 {"samples": g["up"][:1], "noise_mask": m["mask"]}, denoise=0.45)[0]["samples"]
+    assert rel(e, m["masked_final"]) < 1e-4
