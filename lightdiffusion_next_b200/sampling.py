@@ -62,8 +62,11 @@ class SamplerLoop:
 
 def sample_dpmpp_2m_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
                           enable_multiscale: bool = True, multiscale_factor: float = 0.5,
-                          callback: Optional[Callable] = None) -> torch.Tensor:
-    """x <- (sigma_{i+1}/sigma_i) x - expm1(-h_i) * lerp(uncond, cond, cfg)  (first order, as the reference executes)."""
+                          callback: Optional[Callable] = None, multiscale_fullres_start: int = 5,
+                          multiscale_fullres_end: int = 8, multiscale_intermittent_fullres: bool = True) -> torch.Tensor:
+    """x <- (sigma_{i+1}/sigma_i) x - expm1(-h_i) * lerp(uncond, cond, cfg)  (first order, as the reference executes).
+    The multiscale_* options are the sampler's own keyword arguments (samplers.py:768-773), reachable in the reference
+    through `ksampler(name, extra_options=...)`; the defaults are what `KSampler.sample` always runs with."""
     B, _, oh, ow = x.shape
     sh = int(max(8, ((oh * multiscale_factor) // 8) * 8)) if enable_multiscale else oh
     sw = int(max(8, ((ow * multiscale_factor) // 8) * 8)) if enable_multiscale else ow
@@ -79,7 +82,8 @@ def sample_dpmpp_2m_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor,
     low = SamplerLoop(engine, B, sh, sw) if active else None
     den = torch.empty_like(x)
     for i in range(n):
-        if (not active) or _multiscale_fullres(i, n):
+        if (not active) or _multiscale_fullres(i, n, multiscale_fullres_start, multiscale_fullres_end,
+                                               multiscale_intermittent_fullres):
             du, dc = full.denoise_pair(x, float(sig[i]))
             engine.cfg_step(x, du, dc, cfg, 0, c0=float(ratios[i]), c1=float(hexp[i]), x_out=full.x_next,
                             denoised_out=den)
@@ -241,8 +245,11 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
 def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str, scheduler: str,
            positive: torch.Tensor, negative: torch.Tensor, latent_image: Dict[str, torch.Tensor],
            denoise: float = 1.0, enable_multiscale: bool = True, noise: Optional[torch.Tensor] = None,
-           callback: Optional[Callable] = None, noise_sampler: Optional[Callable] = None) -> Tuple[Dict[str, torch.Tensor]]:
+           callback: Optional[Callable] = None, noise_sampler: Optional[Callable] = None,
+           sampler_options: Optional[Dict[str, object]] = None) -> Tuple[Dict[str, torch.Tensor]]:
     """Drop-in for KSampler.sample on the measured path. positive / negative: [1 or B, 77k, 768] conditioning tensors.
+    sampler_options: the `extra_options` of the reference's `ksampler(name, extra_options)` seam (sampling.py:500-534) for
+    dpmpp_2m_cfgpp: multiscale_factor / multiscale_fullres_start / multiscale_fullres_end / multiscale_intermittent_fullres.
     Returns ({"samples": latents / 0.18215 on the CPU},) like the reference node."""
     if sampler_name not in SAMPLERS:
         raise ValueError(f"sampler {sampler_name!r} is not built (have {SAMPLERS})")
@@ -274,7 +281,11 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
     ctx = torch.cat([negative.expand(B, -1, -1), positive.expand(B, -1, -1)]).to(dev)  # rows: uncond first
     engine.set_context(ctx)
     if sampler_name == "dpmpp_2m_cfgpp":
-        x = sample_dpmpp_2m_cfgpp(engine, x, sigmas, cfg, enable_multiscale=enable_multiscale, callback=callback)
+        opts = dict(sampler_options or {})
+        unknown = set(opts) - {"multiscale_factor", "multiscale_fullres_start", "multiscale_fullres_end", "multiscale_intermittent_fullres"}
+        if unknown:
+            raise ValueError(f"unknown dpmpp_2m_cfgpp options {sorted(unknown)}")
+        x = sample_dpmpp_2m_cfgpp(engine, x, sigmas, cfg, enable_multiscale=enable_multiscale, callback=callback, **opts)
     elif sampler_name == "dpmpp_sde_cfgpp":
         x = sample_dpmpp_sde_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, seed=seed,
                                    enable_multiscale=enable_multiscale, callback=callback)

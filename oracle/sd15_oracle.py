@@ -394,7 +394,8 @@ def multiscale_fullres(step: int, n_steps: int, start: int = 5, end: int = 8, in
 
 
 def sample_dpmpp_2m(denoise: Callable[[Tensor, Tensor], Tensor], x: Tensor, sigmas: Tensor,
-                    multiscale: bool = True, factor: float = 0.5) -> Tensor:
+                    multiscale: bool = True, factor: float = 0.5, start: int = 5, end: int = 8,
+                    intermittent: bool = True) -> Tensor:
     """sample_dpmpp_2m_cfgpp as executed (samplers.py:755-962): first-order exponential integrator
     x <- (sigma_{i+1}/sigma_i) x - expm1(-h) denoised, with the log->exp round trip of the reference, and the
     default-on multiscale schedule: low-res steps run the model on a bilinearly down-sampled x."""
@@ -409,7 +410,7 @@ def sample_dpmpp_2m(denoise: Callable[[Tensor, Tensor], Tensor], x: Tensor, sigm
     n = len(sigmas) - 1
     s_in = x.new_ones([x.shape[0]])
     for i in range(n):
-        full = (not active) or multiscale_fullres(i, n)
+        full = (not active) or multiscale_fullres(i, n, start, end, intermittent)
         xp = x if full else F.interpolate(x, size=(sh, sw), mode="bilinear", align_corners=False)
         den = denoise(xp, sigmas[i] * s_in)
         if not full:
@@ -425,7 +426,7 @@ def prepare_noise(shape, seed: int) -> Tensor:
 
 
 def ksample(sd, seed: int, steps: int, cfg: float, sampler: str, scheduler: str, cond: Tensor, uncond: Tensor,
-            latent: Tensor, multiscale: bool = True) -> Tensor:
+            latent: Tensor, multiscale: bool = True, ms_options: Optional[dict] = None) -> Tensor:
     """KSampler.sample -> common_ksampler -> CFGGuider.sample -> KSAMPLER.sample for denoise=1.0 and an empty
     latent (sampling.py:773-887,1142-1233,445-497; CFG.py:266-294): returns samples / 0.18215."""
     tables = make_sigma_tables()
@@ -445,7 +446,7 @@ def ksample(sd, seed: int, steps: int, cfg: float, sampler: str, scheduler: str,
     if sampler == "euler_ancestral_cfgpp":
         x = sample_euler_ancestral(denoise, x, sigmas, lambda t: torch.randn_like(t))
     elif sampler == "dpmpp_2m_cfgpp":
-        x = sample_dpmpp_2m(denoise, x, sigmas, multiscale=multiscale)
+        x = sample_dpmpp_2m(denoise, x, sigmas, multiscale=multiscale, **(ms_options or {}))
     elif sampler == "euler_cfgpp":
         def denoise_pair(xx, ss):
             b = xx.shape[0]

@@ -9,6 +9,8 @@ import sys
 import pytest
 import torch
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -153,3 +155,29 @@ def test_synth_shape_tables_match_oracle():
     assert synth.clip_shapes() == O.clip_param_shapes()
     assert synth.vae_encoder_shapes() == O.vae_encoder_param_shapes()
     assert synth.taesd_decoder_shapes() == O.taesd_decoder_param_shapes()
+
+
+@pytest.mark.parametrize("name", ["perf", "block"])
+def test_dpmpp_2m_multiscale_options_match_reference(unet_sd, name):
+    """Non-default multiscale options of sample_dpmpp_2m_cfgpp (factor 0.25 / contiguous low-resolution block / other
+    full-resolution margins), as injected through the reference's `ksampler(name, extra_options)` seam
+    (tests/golden/make_golden_msopts.py): oracle and the product's host loop vs the reference's final latents."""
+    from fake_engine import FakeEngine
+    from lightdiffusion_next_b200 import sampling as S
+    from oracle import sd15_oracle as O
+    g = torch.load(os.path.join(GOLDEN, "msopts_small.pt"))
+    a = g[f"{name}_args"]
+    lat = torch.zeros(1, 4, a["hw"], a["hw"])
+    o = a["opts"]
+    ref = g[f"{name}_final"]
+    orc = O.ksample(unet_sd, 42, a["steps"], 7.0, "dpmpp_2m_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], lat,
+                    ms_options=dict(factor=o["multiscale_factor"], start=o["multiscale_fullres_start"],
+                                    end=o["multiscale_fullres_end"], intermittent=o["multiscale_intermittent_fullres"]))
+    assert float((orc - ref).norm() / ref.norm()) < 1e-4
+    eng = FakeEngine(unet_sd)
+    e = S.sample(eng, 42, a["steps"], 7.0, "dpmpp_2m_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], {"samples": lat},
+                 sampler_options=o)[0]["samples"]
+    assert float((e - ref).norm() / ref.norm()) < 1e-4
+    with pytest.raises(ValueError, match="unknown dpmpp_2m_cfgpp options"):
+        S.sample(eng, 42, 1, 7.0, "dpmpp_2m_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], {"samples": lat},
+                 sampler_options={"multiscale_typo": 1})
