@@ -42,8 +42,8 @@ g = torch.Generator().manual_seed(1234)
 ctx_pos = torch.randn(1, 77, 768, generator=g); ctx_neg = torch.randn(1, 77, 768, generator=g)
 out = {"ctx_pos": ctx_pos, "ctx_neg": ctx_neg}
 cases = {
-    # "performance" preset values (factor 0.25) on a 32x32 latent: low-res steps at 8x8
-    "perf": (8, 32, dict(multiscale_factor=0.25, multiscale_fullres_start=2, multiscale_fullres_end=2, multiscale_intermittent_fullres=True)),
+    # "performance" preset values (factor 0.25) on a 24x24 latent: low-res steps at 8x8
+    "perf": (6, 24, dict(multiscale_factor=0.25, multiscale_fullres_start=2, multiscale_fullres_end=2, multiscale_intermittent_fullres=True)),
     # contiguous low-res block (no intermittent full-res steps), "quality"-like late start
     "block": (7, 16, dict(multiscale_factor=0.5, multiscale_fullres_start=3, multiscale_fullres_end=1, multiscale_intermittent_fullres=False)),
 }
