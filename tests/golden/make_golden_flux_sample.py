@@ -45,7 +45,8 @@ t5_pos = torch.randn(1, nt, cfg["context_in_dim"], generator=g)
 y_pos = torch.randn(1, cfg["vec_in_dim"], generator=g)
 out = {"t5_pos": t5_pos, "y_pos": y_pos}
 # negative = ConditioningZeroOut of the positive (pipeline.py:247-249): zero states, zero pooled vector
-for name, steps, h, w, cfg_scale, guidance, zero_neg in (("a", 6, 16, 16, 1.0, 3.0, True), ("b", 5, 12, 20, 2.5, 3.5, False)):
+for name, steps, h, w, cfg_scale, guidance, zero_neg, batch in (("a", 6, 16, 16, 1.0, 3.0, True, 1), ("b", 5, 12, 20, 2.5, 3.5, False, 1),
+                                                             ("c", 4, 8, 12, 1.0, 3.0, True, 2)):
     if zero_neg:
         t5_neg, y_neg = torch.zeros_like(t5_pos), torch.zeros_like(y_pos)
     else:
@@ -54,9 +55,9 @@ for name, steps, h, w, cfg_scale, guidance, zero_neg in (("a", 6, 16, 16, 1.0, 3
         model=mp.clone(), seed=42, steps=steps, cfg=cfg_scale, sampler_name="euler_cfgpp", scheduler="beta", denoise=1.0,
         positive=[[t5_pos, {"pooled_output": y_pos, "guidance": guidance}]],
         negative=[[t5_neg, {"pooled_output": y_neg, "guidance": guidance}]],
-        latent_image={"samples": torch.zeros(1, 16, h, w)}, pipeline=True, flux=True)
+        latent_image={"samples": torch.zeros(batch, 16, h, w)}, pipeline=True, flux=True)
     out[f"{name}_final"] = res[0]["samples"].clone()
-    out[f"{name}_args"] = dict(steps=steps, h=h, w=w, cfg=cfg_scale, guidance=guidance)
+    out[f"{name}_args"] = dict(steps=steps, h=h, w=w, cfg=cfg_scale, guidance=guidance, batch=batch)
     out[f"{name}_t5_neg"], out[f"{name}_y_neg"] = t5_neg, y_neg
     print(name, tuple(res[0]["samples"].shape), float(res[0]["samples"].mean()), float(res[0]["samples"].std()), flush=True)
 torch.save(out, os.path.join(HERE, "flux_sample_small.pt"))
