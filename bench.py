@@ -34,8 +34,10 @@ def load_peaks():
     if os.path.exists(p):
         try:
             d = json.load(open(p))
+            have = [k for k in ("bf16_tflops", "bf16_tflops_sustained", "hbm_gbs") if k in d]
+            source = "measured" if len(have) == 3 else ("measured (" + ", ".join(have) + "), fallback for the rest" if have else "fallback")
             return dict(bf16=float(d.get("bf16_tflops", 1590.0)), bf16_sus=float(d.get("bf16_tflops_sustained", 1400.0)),
-                        hbm=float(d.get("hbm_gbs", 6650.0)), source="measured")
+                        hbm=float(d.get("hbm_gbs", 6650.0)), source=source)
         except Exception:
             pass
     return dict(bf16=1590.0, bf16_sus=1400.0, hbm=6650.0, source="fallback")
