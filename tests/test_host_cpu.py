@@ -181,3 +181,28 @@ def test_dpmpp_2m_multiscale_options_match_reference(unet_sd, name):
     with pytest.raises(ValueError, match="unknown dpmpp_2m_cfgpp options"):
         S.sample(eng, 42, 1, 7.0, "dpmpp_2m_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], {"samples": lat},
                  sampler_options={"multiscale_typo": 1})
+
+
+def test_entry_points_reject_null_arguments_with_an_error_code():
+    """Error convention of include/ldn.h: non-zero return + ldn_last_error() message, never a crash -- checked on the
+    argument validation every engine entry runs before touching the device (no compute call is made)."""
+    from lightdiffusion_next_b200 import _lib
+    lib = _lib.load()
+    calls = {
+        "ldn_load_weights": (None, 0, None, 0, None),
+        "ldn_set_context": (None, None, 2, 77, None),
+        "ldn_unet_denoise": (None, None, None, None, 2, 32, 32, None),
+        "ldn_vae_decode": (None, None, None, 1, 8, 8, None),
+        "ldn_vae_encode": (None, None, None, 1, 64, 64, None),
+        "ldn_taesd_decode": (None, None, None, 1, 8, 8, None),
+        "ldn_flux_forward": (None, None, None, None, None, None, None, None, 1, 16, 16, None),
+        "ldn_clip_encode": (None, None, 1, None, None, None),
+        "ldn_t5_encode": (None, None, None, 1, 16, None, None),
+    }
+    for name, args in calls.items():
+        rc = getattr(lib, name)(*args)
+        assert rc != 0, name
+        msg = lib.ldn_last_error()
+        assert msg and b"bad argument" in msg, (name, msg)
+        with pytest.raises(_lib.LdnError, match="bad argument"):
+            _lib.check(rc)
