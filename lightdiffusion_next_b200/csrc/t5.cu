@@ -132,7 +132,7 @@ static Program* build_t5_program(ldn_engine* e, int S, int n) {
   Arena& A = *T.program_arenas.back();
   prog->arena = &A;
   const int W = T.width, H = T.heads, d = 64, slot = 64, F = T.ff, M = S * n;
-  const int Mld = (M + 15) / 16 * 16;
+  const int Mld = (M + 63) / 64 * 64;  // V^T row length: a multiple of 64 so that the v^T GEMM has whole N tiles only
   const int nk_pad = (n + 7) / 8 * 8;
   const int bias_rows = (n + 127) / 128 * 128, bias_ld = bias_rows;
   const auto key = std::make_pair(S, n);
