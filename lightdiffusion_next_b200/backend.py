@@ -74,3 +74,57 @@ def install(model_patcher, engine: Optional[Engine] = None, max_rows: int = 2, m
     m = model_patcher.clone()
     m.set_model_unet_function_wrapper(EngineWrapper(engine))
     return m
+
+
+class EngineVAE:
+    """Coarser seam: stands in for the reference's `VAE` object (src/AutoEncoders/VariationalAE.py:570-760) wherever nodes
+    call `vae.decode(samples)` / `vae.encode(pixels)` (VAEDecode / VAEEncode, :771-801).  Same arguments, layouts and
+    devices: decode takes latents [B,C,h,w] (4 channels, or 16 with the Flux autoencoder loaded) and returns [B,8h,8w,3] fp32 in
+    [0,1] on the CPU; encode takes [B,H,W,3] in [0,1] and returns a posterior sample [B,C,H/8,W/8] fp32 on the CPU.  `flux`
+    is accepted like the reference's keyword; which autoencoder runs is decided by the weights that were loaded."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+
+    def decode(self, samples_in: torch.Tensor, flux: bool = False) -> torch.Tensor:
+        return self.engine.vae_decode(samples_in).cpu()
+
+    def encode(self, pixel_samples: torch.Tensor, flux: bool = False) -> torch.Tensor:
+        return self.engine.vae_encode(pixel_samples)
+
+
+class EngineCLIP:
+    """Coarser seam: stands in for the reference's `CLIP` object (src/clip/Clip.py:297-446) for `clip.tokenize(text)` +
+    `clip.encode_from_tokens(tokens, return_pooled, return_dict, flux_enabled)` (CLIPTextEncode :574-589, CLIPTextEncodeFlux
+    src/Quantize/Quantizer.py:960-990).  Tokenisation is delegated to the reference's own tokenizer object (host Python with
+    its vocabulary files); everything after the token ids runs on the engine.  SD1.5: tokens = list of 77-long (id, weight)
+    rows -> cond [1, 77k, 768] (layer -2 + final LN, as CLIPSetLastLayer(-2) configures the reference's pipeline).  Flux:
+    tokens = {"l": rows, "t5xxl": rows} -> cond = T5 states, pooled = CLIP-L's pooled vector (FluxClip.py:704-718)."""
+
+    def __init__(self, engine: Engine, tokenizer=None):
+        from .pipeline import Pipeline
+
+        self.engine = engine
+        self.tokenizer = tokenizer
+        self._pipe = Pipeline(engine)
+
+    def tokenize(self, text: str, return_word_ids: bool = False):
+        if self.tokenizer is None:
+            raise RuntimeError("EngineCLIP was built without a tokenizer (pass the reference's SD1Tokenizer / FluxTokenizer)")
+        return self.tokenizer.tokenize_with_weights(text, return_word_ids)
+
+    def encode_from_tokens(self, tokens, return_pooled: bool = False, return_dict: bool = False, flux_enabled: bool = False):
+        if isinstance(tokens, dict) and "t5xxl" in tokens:
+            from . import t5 as T5H
+
+            cond = T5H.encode_token_weights(self.engine, tokens["t5xxl"])
+            _, pooled = self._pipe.encode(tokens["l"], return_pooled=True)
+        else:
+            rows = tokens["l"] if isinstance(tokens, dict) else tokens
+            cond, pooled = self._pipe.encode(rows, return_pooled=True)
+        cond, pooled = cond.cpu(), pooled.cpu()  # Device.intermediate_device()
+        if return_dict:
+            return {"cond": cond, "pooled_output": pooled}
+        if return_pooled:
+            return cond, pooled
+        return cond
