@@ -128,3 +128,51 @@ class EngineCLIP:
         if return_pooled:
             return cond, pooled
         return cond
+
+
+def engine_sampler_function(engine: Engine, sampler_name: str):
+    """Coarser seam: a sampler function for the reference's registry -- what `sampling.ksampler(name)` wraps in `KSAMPLER`
+    (src/sample/sampling.py:500-534) and `KSAMPLER.sample` calls as
+    `fn(model_k, x, sigmas, extra_args=, callback=, disable=, pipeline=, **extra_options) -> x` (:445-497).  `model_k` is the
+    reference's `KSamplerX0Inpaint` around its `CFGGuider`; the contexts and the cfg scale are read off the guider
+    (`.conds["positive" / "negative"][0]["model_conds"]["c_crossattn"].cond`, `.cfg`; CFG.py:164-235, cond.py:74-147) and
+    the whole loop -- model calls, CFG, solver update -- then runs on the engine instead of calling `model_k` per step.
+    x arrives already noise-scaled on the load device and is returned in the model's latent space, as the reference's
+    samplers do.  Use: `KSAMPLER(engine_sampler_function(engine, "dpmpp_2m_cfgpp"), extra_options)`."""
+    from . import sampling as S
+
+    if sampler_name not in S.SAMPLERS:
+        raise ValueError(f"sampler {sampler_name!r} is not built (have {S.SAMPLERS})")
+
+    def _ctx(conds) -> torch.Tensor:
+        if conds is None or len(conds) != 1:
+            raise NotImplementedError("the B200 engine samples one positive and one negative conditioning (no areas / masks)")
+        c = conds[0]["model_conds"]["c_crossattn"]
+        return c.cond if hasattr(c, "cond") else c
+
+    def fn(model, x, sigmas, extra_args=None, callback=None, disable=None, pipeline=False, **extra_options):
+        guider = model.inner_model
+        dev = engine.device
+        S.set_contexts(engine, _ctx(guider.conds.get("positive")), _ctx(guider.conds.get("negative")), x.shape[0])
+        xs = x.to(dev, torch.float32).contiguous()
+        cfg = float(guider.cfg)
+        opts = dict(extra_options)
+        if sampler_name == "dpmpp_2m_cfgpp":
+            allowed = {"enable_multiscale", "multiscale_factor", "multiscale_fullres_start", "multiscale_fullres_end",
+                       "multiscale_intermittent_fullres"}
+        elif sampler_name == "dpmpp_sde_cfgpp":
+            allowed = {"noise_sampler", "enable_multiscale", "multiscale_factor", "eta", "r"}
+            opts.setdefault("seed", (extra_args or {}).get("seed"))
+            allowed.add("seed")
+        elif sampler_name == "euler_ancestral_cfgpp":
+            allowed = {"noise_sampler"}
+        else:
+            allowed = {"cfg_scale", "cfg_min"}
+        unknown = set(opts) - allowed
+        if unknown:
+            raise ValueError(f"unknown {sampler_name} options {sorted(unknown)}")
+        run = {"dpmpp_2m_cfgpp": S.sample_dpmpp_2m_cfgpp, "dpmpp_sde_cfgpp": S.sample_dpmpp_sde_cfgpp,
+               "euler_ancestral_cfgpp": S.sample_euler_ancestral_cfgpp, "euler_cfgpp": S.sample_euler_cfgpp}[sampler_name]
+        return run(engine, xs, sigmas, cfg, callback=callback, **opts).to(x.device)
+
+    return fn

@@ -242,6 +242,19 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
     return x
 
 
+def set_contexts(engine: Engine, positive: torch.Tensor, negative: torch.Tensor, batch: int) -> None:
+    """Uploads the cross-attention contexts of a CFG pair for `batch` images: rows [uncond.., cond..] (cond.py:194);
+    contexts of unequal token length are tiled to their least common multiple before batching (cond.py:100-126)."""
+    tn, tp = negative.shape[1], positive.shape[1]
+    if tn != tp:
+        import math
+        lcm = tn * tp // math.gcd(tn, tp)
+        negative = negative.repeat(1, lcm // tn, 1)
+        positive = positive.repeat(1, lcm // tp, 1)
+    ctx = torch.cat([negative.expand(batch, -1, -1), positive.expand(batch, -1, -1)]).to(engine.device)
+    engine.set_context(ctx)
+
+
 def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str, scheduler: str,
            positive: torch.Tensor, negative: torch.Tensor, latent_image: Dict[str, torch.Tensor],
            denoise: float = 1.0, enable_multiscale: bool = True, noise: Optional[torch.Tensor] = None,
@@ -271,15 +284,7 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
     else:
         x = noise * sigmas[0]
     x = (x + lat).to(dev, torch.float32).contiguous()
-    # contexts of unequal token length are tiled to their least common multiple before batching (cond.py:100-126)
-    tn, tp = negative.shape[1], positive.shape[1]
-    if tn != tp:
-        import math
-        lcm = tn * tp // math.gcd(tn, tp)
-        negative = negative.repeat(1, lcm // tn, 1)
-        positive = positive.repeat(1, lcm // tp, 1)
-    ctx = torch.cat([negative.expand(B, -1, -1), positive.expand(B, -1, -1)]).to(dev)  # rows: uncond first
-    engine.set_context(ctx)
+    set_contexts(engine, positive, negative, B)
     if sampler_name == "dpmpp_2m_cfgpp":
         opts = dict(sampler_options or {})
         unknown = set(opts) - {"multiscale_factor", "multiscale_fullres_start", "multiscale_fullres_end", "multiscale_intermittent_fullres"}

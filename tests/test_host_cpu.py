@@ -206,3 +206,33 @@ def test_entry_points_reject_null_arguments_with_an_error_code():
         assert msg and b"bad argument" in msg, (name, msg)
         with pytest.raises(_lib.LdnError, match="bad argument"):
             _lib.check(rc)
+
+
+def test_sampler_registry_seam_function(unet_sd):
+    """backend.engine_sampler_function: the reference's sampler-function signature (KSAMPLER.sample -> fn(model_k, x, sigmas,
+    extra_args=, callback=, disable=, pipeline=, **extra_options), sampling.py:445-534) driven the way KSAMPLER.sample drives it
+    -- noise-scaled x in, latent-space x out -- reproduces the reference's final latents (golden of the dpmpp_2m run)."""
+    import types
+    from fake_engine import FakeEngine
+    from lightdiffusion_next_b200 import backend, sampling as S
+    from lightdiffusion_next_b200.schedule import calculate_sigmas
+    g = torch.load(os.path.join(GOLDEN, "msopts_small.pt"))
+    a = g["block_args"]
+    eng = FakeEngine(unet_sd)
+    cond = lambda t: [{"model_conds": {"c_crossattn": types.SimpleNamespace(cond=t)}}]
+    guider = types.SimpleNamespace(conds={"positive": cond(g["ctx_pos"]), "negative": cond(g["ctx_neg"])}, cfg=7.0)
+    model_k = types.SimpleNamespace(inner_model=guider)
+    lat = torch.zeros(1, 4, a["hw"], a["hw"])
+    sigmas = calculate_sigmas(eng.schedule, "karras", a["steps"])
+    x = S.prepare_noise(lat, 42) * torch.sqrt(1.0 + sigmas[0] ** 2.0)       # noise_scaling at max denoise (KSAMPLER.sample)
+    fn = backend.engine_sampler_function(eng, "dpmpp_2m_cfgpp")
+    seen = []
+    out = fn(model_k, x, sigmas, extra_args={"seed": 42}, callback=lambda d: seen.append(d["i"]), disable=True, pipeline=True,
+             **a["opts"])
+    ref = g["block_final"]                                                    # process_latent_out applied by the reference
+    assert float((out / S.LATENT_SCALE - ref).norm() / ref.norm()) < 1e-4
+    assert seen == list(range(a["steps"]))
+    with pytest.raises(ValueError, match="unknown dpmpp_2m_cfgpp options"):
+        fn(model_k, x, sigmas, bogus=1)
+    with pytest.raises(ValueError, match="not built"):
+        backend.engine_sampler_function(eng, "euler")
