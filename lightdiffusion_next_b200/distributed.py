@@ -113,3 +113,28 @@ def sample_sharded(engine, seed: int, steps: int, cfg: float, sampler_name: str,
         out = torch.empty((0,) + tuple(latent.shape[1:]), device=dev)
     full = gather_rows(out, B)
     return ({"samples": full.cpu()} if full is not None else None,)
+
+
+def sample_flux_sharded(engine, seed: int, steps: int, positive, negative, latent_image: Dict[str, torch.Tensor], **kw):
+    """flux_sampling.sample_flux for a batch of latents sharded over the ranks (same scheme as sample_sharded: rank 0 draws
+    the full-batch noise as the reference does, slices travel point to point, no collective inside the loop, latents are
+    gathered on rank 0).  positive / negative: (T5 states [1,Nt,C], pooled vector [1,V]) on every rank.  `euler_cfgpp`
+    is deterministic given the noise, so the sharded batch reproduces the single-process batch."""
+    from . import flux_sampling as FS
+    from . import sampling as S
+
+    latent = latent_image["samples"]
+    B = latent.shape[0]
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(B, rank, world)
+    noise_full = S.prepare_noise(latent, seed) if rank == 0 else None
+    dev = engine.device
+    noise = scatter_rows(noise_full, tuple(latent.shape[1:]), B, dev)
+    if hi > lo:
+        res = FS.sample_flux(engine, seed, steps, positive, negative, {"samples": latent[lo:hi]}, noise=noise.cpu(), **kw)
+        out = res[0]["samples"].to(dev)
+    else:
+        out = torch.empty((0,) + tuple(latent.shape[1:]), device=dev)
+    full = gather_rows(out, B)
+    return ({"samples": full.cpu()} if full is not None else None,)
