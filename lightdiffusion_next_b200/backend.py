@@ -130,7 +130,7 @@ class EngineCLIP:
         return cond
 
 
-def engine_sampler_function(engine: Engine, sampler_name: str):
+def engine_sampler_function(engine: Engine, sampler_name: str, interrupt=None):
     """Coarser seam: a sampler function for the reference's registry -- what `sampling.ksampler(name)` wraps in `KSAMPLER`
     (src/sample/sampling.py:500-534) and `KSAMPLER.sample` calls as
     `fn(model_k, x, sigmas, extra_args=, callback=, disable=, pipeline=, **extra_options) -> x` (:445-497).  `model_k` is the
@@ -138,7 +138,9 @@ def engine_sampler_function(engine: Engine, sampler_name: str):
     (`.conds["positive" / "negative"][0]["model_conds"]["c_crossattn"].cond`, `.cfg`; CFG.py:164-235, cond.py:74-147) and
     the whole loop -- model calls, CFG, solver update -- then runs on the engine instead of calling `model_k` per step.
     x arrives already noise-scaled on the load device and is returned in the model's latent space, as the reference's
-    samplers do.  Use: `KSAMPLER(engine_sampler_function(engine, "dpmpp_2m_cfgpp"), extra_options)`."""
+    samplers do.  `interrupt`: a callable polled before every step unless the call is made with pipeline=True -- pass
+    `lambda: app_instance.app.interrupt_flag` to keep the reference's cancel button working (samplers.py:884-889).
+    Use: `KSAMPLER(engine_sampler_function(engine, "dpmpp_2m_cfgpp"), extra_options)`."""
     from . import sampling as S
 
     if sampler_name not in S.SAMPLERS:
@@ -154,7 +156,7 @@ def engine_sampler_function(engine: Engine, sampler_name: str):
         guider = model.inner_model
         dev = engine.device
         S.set_contexts(engine, _ctx(guider.conds.get("positive")), _ctx(guider.conds.get("negative")), x.shape[0])
-        xs = x.to(dev, torch.float32).contiguous()
+        xs = x.detach().to(dev, torch.float32, copy=True).contiguous()  # the loops ping-pong between buffers: never the caller's
         cfg = float(guider.cfg)
         opts = dict(extra_options)
         if sampler_name == "dpmpp_2m_cfgpp":
@@ -173,6 +175,6 @@ def engine_sampler_function(engine: Engine, sampler_name: str):
             raise ValueError(f"unknown {sampler_name} options {sorted(unknown)}")
         run = {"dpmpp_2m_cfgpp": S.sample_dpmpp_2m_cfgpp, "dpmpp_sde_cfgpp": S.sample_dpmpp_sde_cfgpp,
                "euler_ancestral_cfgpp": S.sample_euler_ancestral_cfgpp, "euler_cfgpp": S.sample_euler_cfgpp}[sampler_name]
-        return run(engine, xs, sigmas, cfg, callback=callback, **opts).to(x.device)
+        return run(engine, xs, sigmas, cfg, callback=callback, interrupt=None if pipeline else interrupt, **opts).to(x.device)
 
     return fn

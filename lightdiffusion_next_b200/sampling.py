@@ -39,7 +39,9 @@ def _multiscale_fullres(step: int, n_steps: int, start: int = 5, end: int = 8, i
 
 
 class SamplerLoop:
-    """Reusable loop state for one (batch, resolution): device buffers are allocated once."""
+    """Reusable loop state for one (batch, resolution): device buffers are allocated once.  The sample_* loops below
+    ping-pong between the tensor they are given and `x_next`, i.e. they CONSUME their `x` argument (sample() and the seam
+    functions in backend.py always hand them a private copy)."""
 
     def __init__(self, engine: Engine, batch: int, lat_h: int, lat_w: int):
         self.e = engine
@@ -63,7 +65,8 @@ class SamplerLoop:
 def sample_dpmpp_2m_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
                           enable_multiscale: bool = True, multiscale_factor: float = 0.5,
                           callback: Optional[Callable] = None, multiscale_fullres_start: int = 5,
-                          multiscale_fullres_end: int = 8, multiscale_intermittent_fullres: bool = True) -> torch.Tensor:
+                          multiscale_fullres_end: int = 8, multiscale_intermittent_fullres: bool = True,
+                          interrupt: Optional[Callable[[], bool]] = None) -> torch.Tensor:
     """x <- (sigma_{i+1}/sigma_i) x - expm1(-h_i) * lerp(uncond, cond, cfg)  (first order, as the reference executes).
     The multiscale_* options are the sampler's own keyword arguments (samplers.py:768-773), reachable in the reference
     through `ksampler(name, extra_options=...)`; the defaults are what `KSampler.sample` always runs with."""
@@ -82,6 +85,8 @@ def sample_dpmpp_2m_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor,
     low = SamplerLoop(engine, B, sh, sw) if active else None
     den = torch.empty_like(x)
     for i in range(n):
+        if interrupt is not None and interrupt():
+            return x  # the reference's interrupt_flag poll (samplers.py:884-889): hand back the current latent
         if (not active) or _multiscale_fullres(i, n, multiscale_fullres_start, multiscale_fullres_end,
                                                multiscale_intermittent_fullres):
             du, dc = full.denoise_pair(x, float(sig[i]))
@@ -102,7 +107,8 @@ def sample_dpmpp_2m_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor,
 
 def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
                                  noise_sampler: Optional[Callable] = None,
-                                 callback: Optional[Callable] = None) -> torch.Tensor:
+                                 callback: Optional[Callable] = None,
+                                 interrupt: Optional[Callable[[], bool]] = None) -> torch.Tensor:
     """d = (x - D)/sigma; x += d (sigma_down - sigma); x += randn_like(x) sigma_up   (eta = 1, s_noise = 1)."""
     B = x.shape[0]
     sig = sigmas.float().cpu()
@@ -110,6 +116,8 @@ def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.
     loop = SamplerLoop(engine, B, x.shape[2], x.shape[3])
     den = torch.empty_like(x)
     for i in range(n):
+        if interrupt is not None and interrupt():
+            return x  # the reference's interrupt_flag poll (samplers.py:884-889): hand back the current latent
         du, dc = loop.denoise_pair(x, float(sig[i]))
         sd, su = get_ancestral_step(sig[i], sig[i + 1])
         noise = None
@@ -125,7 +133,7 @@ def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.
 
 def sample_euler_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float, cfg_scale: float = 7.5,
                        cfg_min: float = 1.0, callback: Optional[Callable] = None,
-                       pair_fn: Optional[Callable] = None) -> torch.Tensor:
+                       pair_fn: Optional[Callable] = None, interrupt: Optional[Callable[[], bool]] = None) -> torch.Tensor:
     """`euler_cfgpp` = sample_euler_dy_cfg_pp as the reference executes it (samplers.py:470-608, the sampler of its Flux
     pipeline, also selectable for SD1.5): a plain Euler step on the guider's CFG result (the sampler's own CFG++ bookkeeping
     is reset to None every step, :548-550), plus -- while i // 2 == 1 and sigma_{i+1} > 0 -- the dynamic step
@@ -141,6 +149,8 @@ def sample_euler_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cf
     x_next = torch.empty_like(x)
     den = torch.empty_like(x)
     for i in range(n):
+        if interrupt is not None and interrupt():
+            return x  # the reference's interrupt_flag poll (samplers.py:884-889): hand back the current latent
         du, dc = loop.denoise_pair(x, float(sig[i])) if pair_fn is None else pair_fn(x, float(sig[i]))
         engine.cfg_step(x, du, dc, cfg, 1, c0=float(sig[i + 1] - sig[i]), c1=0.0, c2=float(sig[i]), noise=None,
                         x_out=x_next, denoised_out=den)
@@ -195,7 +205,8 @@ class BrownianIntervalNoise:
 def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
                            noise_sampler: Optional[Callable] = None, seed: Optional[int] = None, eta: float = 1.0,
                            r: float = 0.5, enable_multiscale: bool = False, multiscale_factor: float = 0.5,
-                           callback: Optional[Callable] = None) -> torch.Tensor:
+                           callback: Optional[Callable] = None,
+                           interrupt: Optional[Callable[[], bool]] = None) -> torch.Tensor:
     """DPM-Solver++ (SDE) as the reference executes it (samplers.py:966-1254): two CFG-batched UNet evaluations per
     step (at sigma_i and at the midpoint in log-sigma), ancestral noise from `noise_sampler(sigma, sigma_next)`."""
     B, _, oh, ow = x.shape
@@ -220,6 +231,8 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
         return d if fullres else F.interpolate(d, size=(oh, ow), mode="bilinear", align_corners=False)
 
     for i in range(n):
+        if interrupt is not None and interrupt():
+            return x  # the reference's interrupt_flag poll (samplers.py:884-889): hand back the current latent
         fullres = (not active) or (i < 5 or i >= n - 8)  # sampler defaults: start 5, end 8, not intermittent
         den = denoised_at(x, float(sig[i]), fullres)
         if sig[i + 1] == 0:
@@ -259,10 +272,13 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
            positive: torch.Tensor, negative: torch.Tensor, latent_image: Dict[str, torch.Tensor],
            denoise: float = 1.0, enable_multiscale: bool = True, noise: Optional[torch.Tensor] = None,
            callback: Optional[Callable] = None, noise_sampler: Optional[Callable] = None,
-           sampler_options: Optional[Dict[str, object]] = None) -> Tuple[Dict[str, torch.Tensor]]:
+           sampler_options: Optional[Dict[str, object]] = None,
+           interrupt: Optional[Callable[[], bool]] = None) -> Tuple[Dict[str, torch.Tensor]]:
     """Drop-in for KSampler.sample on the measured path. positive / negative: [1 or B, 77k, 768] conditioning tensors.
     sampler_options: the `extra_options` of the reference's `ksampler(name, extra_options)` seam (sampling.py:500-534) for
     dpmpp_2m_cfgpp: multiscale_factor / multiscale_fullres_start / multiscale_fullres_end / multiscale_intermittent_fullres.
+    interrupt: polled before every step like the reference polls app.interrupt_flag (samplers.py:884-889); when it returns
+    True the loop stops and the current latent is returned.
     Returns ({"samples": latents / 0.18215 on the CPU},) like the reference node."""
     if sampler_name not in SAMPLERS:
         raise ValueError(f"sampler {sampler_name!r} is not built (have {SAMPLERS})")
@@ -290,13 +306,15 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
         unknown = set(opts) - {"multiscale_factor", "multiscale_fullres_start", "multiscale_fullres_end", "multiscale_intermittent_fullres"}
         if unknown:
             raise ValueError(f"unknown dpmpp_2m_cfgpp options {sorted(unknown)}")
-        x = sample_dpmpp_2m_cfgpp(engine, x, sigmas, cfg, enable_multiscale=enable_multiscale, callback=callback, **opts)
+        x = sample_dpmpp_2m_cfgpp(engine, x, sigmas, cfg, enable_multiscale=enable_multiscale, callback=callback,
+                                  interrupt=interrupt, **opts)
     elif sampler_name == "dpmpp_sde_cfgpp":
         x = sample_dpmpp_sde_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, seed=seed,
-                                   enable_multiscale=enable_multiscale, callback=callback)
+                                   enable_multiscale=enable_multiscale, callback=callback, interrupt=interrupt)
     elif sampler_name == "euler_cfgpp":
-        x = sample_euler_cfgpp(engine, x, sigmas, cfg, callback=callback)
+        x = sample_euler_cfgpp(engine, x, sigmas, cfg, callback=callback, interrupt=interrupt)
     else:
-        x = sample_euler_ancestral_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, callback=callback)
+        x = sample_euler_ancestral_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, callback=callback,
+                                         interrupt=interrupt)
     out = (x / LATENT_SCALE).to(torch.float32).cpu()
     return ({"samples": out},)

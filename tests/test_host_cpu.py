@@ -257,3 +257,32 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1"})
     assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
+
+
+def test_interrupt_poll_returns_the_current_latent(unet_sd):
+    """The reference's samplers poll app.interrupt_flag before every step (unless pipeline=True) and hand back the current x
+    (samplers.py:884-889).  Same contract here: `interrupt()` is polled before each step; stopping before step k returns
+    exactly the latent an uninterrupted run holds after step k - 1; pipeline=True at the registry seam disables the poll."""
+    import types
+    from fake_engine import FakeEngine
+    from lightdiffusion_next_b200 import backend, sampling as S
+    g = torch.load(os.path.join(GOLDEN, "msopts_small.pt"))
+    lat = torch.zeros(1, 4, 16, 16)
+    states = []
+    S.sample(FakeEngine(unet_sd), 42, 3, 7.0, "euler_ancestral_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], {"samples": lat},
+             noise_sampler=lambda x: torch.zeros_like(x), callback=lambda d: states.append(d["x"].clone()))
+    polls = []
+    eng = FakeEngine(unet_sd)
+    out = S.sample(eng, 42, 3, 7.0, "euler_ancestral_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], {"samples": lat},
+                   noise_sampler=lambda x: torch.zeros_like(x), interrupt=lambda: (polls.append(1), len(polls) > 2)[1])[0]["samples"]
+    assert len(polls) == 3 and eng.denoise_calls == 2           # stopped before the third step
+    assert torch.equal(out, states[1] / S.LATENT_SCALE)
+    # registry seam: polled when pipeline=False, ignored when pipeline=True (as in the reference)
+    cond = lambda t: [{"model_conds": {"c_crossattn": types.SimpleNamespace(cond=t)}}]
+    model_k = types.SimpleNamespace(inner_model=types.SimpleNamespace(
+        conds={"positive": cond(g["ctx_pos"]), "negative": cond(g["ctx_neg"])}, cfg=7.0))
+    sig = torch.tensor([2.0, 1.0, 0.0])
+    x0 = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(0))
+    fn = backend.engine_sampler_function(FakeEngine(unet_sd), "dpmpp_2m_cfgpp", interrupt=lambda: True)
+    assert torch.equal(fn(model_k, x0, sig, pipeline=False), x0)
+    assert not torch.equal(fn(model_k, x0, sig, pipeline=True), x0)
