@@ -42,7 +42,8 @@ def flux_pair_fn(engine: Engine, ctx_neg: torch.Tensor, ctx_pos: torch.Tensor, y
 def sample_flux(engine: Engine, seed: int, steps: int, positive: Tuple[torch.Tensor, torch.Tensor],
                 negative: Tuple[torch.Tensor, torch.Tensor], latent_image: Dict[str, torch.Tensor], cfg: float = 1.0,
                 guidance: float = 3.5, scheduler: str = "beta", shift: float = 1.15,
-                noise: Optional[torch.Tensor] = None, callback: Optional[Callable] = None) -> Tuple[Dict[str, torch.Tensor]]:
+                noise: Optional[torch.Tensor] = None, callback: Optional[Callable] = None,
+                interrupt: Optional[Callable[[], bool]] = None) -> Tuple[Dict[str, torch.Tensor]]:
     """positive / negative: (T5 states [1,Nt,4096], pooled CLIP vector [1,768]); latent_image {"samples": [B,16,h,w]}.
     Returns ({"samples": latents in the VAE's space (process_out applied), fp32 on the CPU},)."""
     latent = latent_image["samples"]
@@ -52,6 +53,6 @@ def sample_flux(engine: Engine, seed: int, steps: int, positive: Tuple[torch.Ten
     lat = (latent - LATENT_SHIFT) * LATENT_SCALE if torch.count_nonzero(latent) > 0 else latent  # process_in (CFG.py:266-269)
     x = (sigmas[0] * noise + (1.0 - sigmas[0]) * lat).to(engine.device, torch.float32).contiguous()  # CONST.noise_scaling
     fn = flux_pair_fn(engine, negative[0], positive[0], negative[1], positive[1], guidance)
-    x = S.sample_euler_cfgpp(engine, x, sigmas, cfg, callback=callback, pair_fn=fn)
+    x = S.sample_euler_cfgpp(engine, x, sigmas, cfg, callback=callback, pair_fn=fn, interrupt=interrupt)
     out = (x / LATENT_SCALE + LATENT_SHIFT).to(torch.float32).cpu()  # process_out
     return ({"samples": out},)
