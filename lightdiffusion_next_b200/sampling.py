@@ -122,7 +122,8 @@ def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.
         sd, su = get_ancestral_step(sig[i], sig[i + 1])
         noise = None
         if sig[i + 1] > 0:
-            noise = noise_sampler(x) if noise_sampler is not None else torch.randn_like(x)
+            # the reference's convention (samplers.py:633-636, 732): noise_sampler(sigma, sigma_next) -> noise like x
+            noise = noise_sampler(sig[i], sig[i + 1]).to(x.device) if noise_sampler is not None else torch.randn_like(x)
         engine.cfg_step(x, du, dc, cfg, 1, c0=float(sd - sig[i]), c1=float(su), c2=float(sig[i]), noise=noise,
                         x_out=loop.x_next, denoised_out=den)
         x, loop.x_next = loop.x_next, x

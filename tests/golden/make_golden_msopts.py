@@ -56,4 +56,23 @@ for name, (steps, hw, opts) in cases.items():
                           latent_image=lat, seed=42, pipeline=True)
     out[f"{name}_final"] = res.clone(); out[f"{name}_args"] = dict(steps=steps, hw=hw, opts=opts)
     print(name, tuple(res.shape), float(res.std()), flush=True)
+
+
+class SeqNoise:
+    """n-th call returns the n-th draw of a seeded CPU generator; records the (sigma, sigma_next) it was called with."""
+    def __init__(self, shape, seed): self.g = torch.Generator().manual_seed(seed); self.shape = shape; self.calls = []
+    def __call__(self, sigma, sigma_next):
+        self.calls.append((float(sigma), float(sigma_next)))
+        return torch.randn(self.shape, generator=self.g)
+
+
+# euler_ancestral_cfgpp with an injected noise sampler (extra_options={"noise_sampler": f}; samplers.py:621-636, 732)
+lat = torch.zeros(1, 4, 16, 16)
+ns = SeqNoise(lat.shape, 7)
+sampler = sampling.ksampler("euler_ancestral_cfgpp", extra_options={"noise_sampler": ns})
+sigmas = ksampler_util.calculate_sigmas(model.model_sampling, "karras", 3)
+res = sampling.sample(mp, ksampler_util.prepare_noise(lat, 42), [[ctx_pos, {}]], [[ctx_neg, {}]], 7.0, torch.device("cpu"), sampler,
+                      sigmas, latent_image=lat, seed=42, pipeline=True)
+out["anc_final"] = res.clone(); out["anc_calls"] = torch.tensor(ns.calls)
+print("anc", float(res.std()), ns.calls, flush=True)
 torch.save(out, os.path.join(HERE, "msopts_small.pt")); print("wrote msopts_small.pt")

@@ -270,11 +270,11 @@ def test_interrupt_poll_returns_the_current_latent(unet_sd):
     lat = torch.zeros(1, 4, 16, 16)
     states = []
     S.sample(FakeEngine(unet_sd), 42, 3, 7.0, "euler_ancestral_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], {"samples": lat},
-             noise_sampler=lambda x: torch.zeros_like(x), callback=lambda d: states.append(d["x"].clone()))
+             noise_sampler=lambda s0, s1: torch.zeros(1, 4, 16, 16), callback=lambda d: states.append(d["x"].clone()))
     polls = []
     eng = FakeEngine(unet_sd)
     out = S.sample(eng, 42, 3, 7.0, "euler_ancestral_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], {"samples": lat},
-                   noise_sampler=lambda x: torch.zeros_like(x), interrupt=lambda: (polls.append(1), len(polls) > 2)[1])[0]["samples"]
+                   noise_sampler=lambda s0, s1: torch.zeros(1, 4, 16, 16), interrupt=lambda: (polls.append(1), len(polls) > 2)[1])[0]["samples"]
     assert len(polls) == 3 and eng.denoise_calls == 2           # stopped before the third step
     assert torch.equal(out, states[1] / S.LATENT_SCALE)
     # registry seam: polled when pipeline=False, ignored when pipeline=True (as in the reference)
@@ -286,3 +286,28 @@ def test_interrupt_poll_returns_the_current_latent(unet_sd):
     fn = backend.engine_sampler_function(FakeEngine(unet_sd), "dpmpp_2m_cfgpp", interrupt=lambda: True)
     assert torch.equal(fn(model_k, x0, sig, pipeline=False), x0)
     assert not torch.equal(fn(model_k, x0, sig, pipeline=True), x0)
+
+
+def test_euler_ancestral_injected_noise_sampler_matches_reference(unet_sd):
+    """euler_ancestral_cfgpp with the noise sampler injected the way the reference's seam injects it
+    (ksampler(name, extra_options={"noise_sampler": f}); called as f(sigma, sigma_next), samplers.py:732): the product's host
+    loop reproduces the reference's final latent and calls f with the same sigma pairs (not after the last step)."""
+    from fake_engine import FakeEngine
+    from lightdiffusion_next_b200 import sampling as S
+    g = torch.load(os.path.join(GOLDEN, "msopts_small.pt"))
+
+    class SeqNoise:
+        def __init__(self, shape, seed):
+            self.g, self.shape, self.calls = torch.Generator().manual_seed(seed), shape, []
+
+        def __call__(self, sigma, sigma_next):
+            self.calls.append((float(sigma), float(sigma_next)))
+            return torch.randn(self.shape, generator=self.g)
+
+    lat = torch.zeros(1, 4, 16, 16)
+    ns = SeqNoise(lat.shape, 7)
+    e = S.sample(FakeEngine(unet_sd), 42, 3, 7.0, "euler_ancestral_cfgpp", "karras", g["ctx_pos"], g["ctx_neg"], {"samples": lat},
+                 noise_sampler=ns)[0]["samples"]
+    ref = g["anc_final"]
+    assert float((e - ref).norm() / ref.norm()) < 1e-4
+    assert torch.allclose(torch.tensor(ns.calls), g["anc_calls"], rtol=1e-5)
