@@ -96,8 +96,11 @@ class Engine:
     def load_t5(self, state_dict: Dict[str, torch.Tensor]) -> None:
         """T5 text-encoder weights (state-dict keys of the reference's T5 module, src/clip/FluxClip.py:501-531; see
         t5.t5_shapes).  Heads must be 64 wide (T5-XXL: 4096 / 64)."""
-        self.load_weights(T5, state_dict)
-        self._t5_width = int(state_dict["shared.weight"].shape[1])
+        from . import t5 as T5H
+
+        cfg = T5H.validate_state_dict(state_dict)
+        self.load_weights(T5, {k: state_dict[k] for k in T5H.t5_shapes(**cfg)})  # encoder tensors only
+        self._t5_width = cfg["d_model"]
 
     def load_checkpoint(self, path: str, lora_path: Optional[str] = None, strength_model: float = 1.0,
                         strength_clip: float = 1.0) -> Dict[str, int]:

@@ -43,6 +43,32 @@ def t5_shapes(d_model: int = 4096, d_ff: int = 10240, num_heads: int = 64, num_l
     return s
 
 
+def validate_state_dict(sd) -> Dict[str, int]:
+    """Checks a T5 encoder state dict against the layout the engine consumes (names and shapes, decoder / lm_head tensors
+    tolerated and ignored by the caller) and returns its configuration.  Raises ValueError naming what is wrong -- the
+    engine has no fallback for a malformed checkpoint."""
+    if "shared.weight" not in sd or sd["shared.weight"].dim() != 2:
+        raise ValueError("T5 state dict: shared.weight [vocab, d_model] is missing")
+    vocab, d_model = (int(v) for v in sd["shared.weight"].shape)
+    rb = "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"
+    wi = "encoder.block.0.layer.1.DenseReluDense.wi_0.weight"
+    if rb not in sd or wi not in sd:
+        raise ValueError(f"T5 state dict: {rb if rb not in sd else wi} is missing (a gated-activation T5 v1.1 encoder is expected)")
+    heads, d_ff = int(sd[rb].shape[1]), int(sd[wi].shape[0])
+    layers = 0
+    while f"encoder.block.{layers}.layer.0.SelfAttention.q.weight" in sd:
+        layers += 1
+    want = t5_shapes(d_model, d_ff, heads, layers, vocab)
+    missing = sorted(k for k in want if k not in sd)
+    wrong = sorted(k for k in want if k in sd and tuple(sd[k].shape) != want[k])
+    if missing or wrong:
+        raise ValueError(f"T5 state dict does not match the encoder layout: missing {missing[:4]}{'...' if len(missing) > 4 else ''}, "
+                         f"wrong shape {[(k, tuple(sd[k].shape), want[k]) for k in wrong[:3]]}")
+    if d_model % heads != 0 or d_model // heads != 64:
+        raise ValueError(f"T5: head width {d_model / heads:g} is not supported (the engine's logit-bias attention is built for 64)")
+    return dict(vocab_size=vocab, d_model=d_model, d_ff=d_ff, num_heads=heads, num_layers=layers)
+
+
 def relative_position_buckets(n: int) -> torch.Tensor:
     """int32 [2n-1]: bucket of the relative distance (key - query) = -(n-1) .. n-1 (bidirectional, 32 buckets, distances
     >= 128 share the last bucket of their direction).  bias[h, i, j] = table[buckets[j - i + n - 1], h]."""
