@@ -54,7 +54,9 @@ int ldn_create(const ldn_config* cfg, ldn_handle* out);
 void ldn_destroy(ldn_handle h);
 /* which: 0 = UNet ("model.diffusion_model." prefix stripped), 1 = VAE ("first_stage_model." stripped; decoder.* +
  *        post_quant_conv.* and/or encoder.* + quant_conv.*), 2 = CLIP-L text model ("...text_model." stripped),
- *        3 = TAESD preview decoder (keys of taesd_decoder.safetensors), 4 = Flux.1 DiT (Flux3 state-dict keys) */
+ *        3 = TAESD preview decoder (keys of taesd_decoder.safetensors), 4 = Flux.1 DiT (Flux3 state-dict keys),
+ *        5 = T5 text encoder (keys of the reference's T5 module, src/clip/FluxClip.py:501-531).
+ * Matrices are stored as bf16; vectors, embedding tables named "*embedding*" and the T5 relative_attention_bias table as fp32. */
 int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, void* stream);
 /* Discrete schedule tables (ModelSamplingDiscrete.sigmas / .log_sigmas, src/sample/sampling.py:221-356): host
  * pointers, n entries each. log_sigmas is passed separately because the reference computes it in float64. */
