@@ -90,6 +90,9 @@ class Engine:
 
     def load_flux(self, state_dict: Dict[str, torch.Tensor]) -> None:
         """Flux.1 DiT weights (Flux3 state-dict keys, src/BlackForest/Flux.py:548-656)."""
+        from . import flux as FX
+
+        FX.validate_state_dict(state_dict)  # fails loudly on a malformed checkpoint
         self.load_weights(FLUX, state_dict)
         self._flux_pe = {}
 

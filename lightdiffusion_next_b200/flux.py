@@ -83,3 +83,43 @@ def flux_shapes(cfg=FLUX_DEV) -> Dict[str, Tuple[int, ...]]:
     lin("final_layer.linear", cfg["in_channels"] * 4, C)
     lin("final_layer.adaLN_modulation.1", 2 * C, C)
     return s
+
+
+def infer_config(sd) -> Dict[str, object]:
+    """Flux3 hyper-parameters read off a state dict's shapes (what detect_unet_config does for the reference's loader):
+    everything but the rotary axes / theta, which are not stored in the weights."""
+    def need(k):
+        if k not in sd:
+            raise ValueError(f"Flux state dict: {k} is missing")
+        return tuple(int(v) for v in sd[k].shape)
+
+    C, cin4 = need("img_in.weight")
+    hd = need("double_blocks.0.img_attn.norm.query_norm.scale")[0]
+    M = need("double_blocks.0.img_mlp.0.weight")[0]
+    depth = 0
+    while f"double_blocks.{depth}.img_attn.qkv.weight" in sd:
+        depth += 1
+    single = 0
+    while f"single_blocks.{single}.linear1.weight" in sd:
+        single += 1
+    if C % hd != 0 or cin4 % 4 != 0:
+        raise ValueError(f"Flux state dict: hidden size {C} / head width {hd} / patch width {cin4} are inconsistent")
+    return dict(in_channels=cin4 // 4, vec_in_dim=need("vector_in.in_layer.weight")[1], context_in_dim=need("txt_in.weight")[1],
+                hidden_size=C, mlp_ratio=M / C, num_heads=C // hd, depth=depth, depth_single_blocks=single,
+                guidance_embed="guidance_in.in_layer.weight" in sd)
+
+
+def validate_state_dict(sd) -> Dict[str, object]:
+    """Names and shapes of a Flux3 state dict against the layout the engine consumes; returns the inferred configuration.
+    Raises ValueError naming what is wrong (no fallback for a malformed checkpoint).  The joint attention kernel is built
+    for 128-wide heads."""
+    cfg = infer_config(sd)
+    want = flux_shapes(cfg)
+    missing = sorted(k for k in want if k not in sd)
+    wrong = sorted(k for k in want if k in sd and tuple(sd[k].shape) != want[k])
+    if missing or wrong:
+        raise ValueError(f"Flux state dict does not match the Flux3 layout: missing {missing[:4]}{'...' if len(missing) > 4 else ''}, "
+                         f"wrong shape {[(k, tuple(sd[k].shape), want[k]) for k in wrong[:3]]}")
+    if cfg["hidden_size"] // cfg["num_heads"] != 128:
+        raise ValueError(f"Flux: head width {cfg['hidden_size'] // cfg['num_heads']} is not supported (128 expected)")
+    return cfg
