@@ -311,3 +311,38 @@ def test_euler_ancestral_injected_noise_sampler_matches_reference(unet_sd):
     ref = g["anc_final"]
     assert float((e - ref).norm() / ref.norm()) < 1e-4
     assert torch.allclose(torch.tensor(ns.calls), g["anc_calls"], rtol=1e-5)
+
+
+def test_schedules_sweep_product_equals_oracle_and_is_well_formed():
+    """Every scheduler name x 1..40 steps: the product's host schedule equals the (reference-pinned) oracle's bit for bit,
+    starts at or below sigma_max, decreases strictly and ends in exactly 0; same for the Flux table with `beta` / `simple`."""
+    from lightdiffusion_next_b200.schedule import DiscreteSchedule, FluxSchedule, calculate_sigmas
+    from oracle import sd15_oracle as O
+    sched = DiscreteSchedule()
+    for name in ("karras", "normal", "simple", "beta"):
+        for steps in range(1, 41):
+            s = calculate_sigmas(sched, name, steps)
+            assert torch.equal(s, O.calculate_sigmas(name, steps)), (name, steps)
+            assert s[-1] == 0 and s.dtype == torch.float32 and 2 <= len(s) <= steps + 1, (name, steps)
+            assert bool((s[:-1] > s[1:]).all()), (name, steps)
+            assert float(s[0]) <= 14.6147
+    fs = FluxSchedule(1.15)
+    for name in ("beta", "simple"):
+        for steps in (1, 2, 4, 20, 50):
+            s = calculate_sigmas(fs, name, steps)
+            assert s[-1] == 0 and float(s[0]) <= 1.0 and bool((s[:-1] > s[1:]).all()), (name, steps)
+
+
+def test_t5_bucket_properties():
+    """Relative-position buckets: 16 buckets per direction, exact below 8, logarithmic up to 128, saturating beyond; mirrored
+    distances differ by exactly the direction offset; non-decreasing in |distance|."""
+    from lightdiffusion_next_b200 import t5 as T5H
+    n = 700
+    b = T5H.relative_position_buckets(n).long()
+    c = n - 1                                    # index of distance 0
+    assert int(b[c]) == 0 and b.min() == 0 and b.max() == 31
+    d = torch.arange(1, n)
+    assert torch.equal(b[c + d], b[c - d] + 16)  # key after query = same magnitude bucket + 16
+    mag = b[c - d]
+    assert torch.equal(mag[:7], torch.arange(1, 8)) and bool((mag[1:] >= mag[:-1]).all())
+    assert int(mag[89]) == 14 and bool((mag[90:] == 15).all())    # last bucket: |distance| >= 8 * 16^(7/8) = 90.5, incl. everything >= 128
