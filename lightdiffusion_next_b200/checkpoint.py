@@ -229,3 +229,41 @@ def load_sd15(engine, path: str, lora_path: Optional[str] = None, strength_model
     if parts["clip"]:
         engine.load_clip(parts["clip"])
     return {k: len(v) for k, v in parts.items()}
+
+
+def load_flux_files(engine, unet_path: str, ae_path: Optional[str] = None, clip_l_path: Optional[str] = None,
+                    t5_path: Optional[str] = None) -> Dict[str, int]:
+    """The four files of the reference's Flux branch (src/user/pipeline.py:225-237: UnetLoaderGGUF "flux1-dev-Q8_0.gguf",
+    VAELoader "ae.safetensors", DualCLIPLoaderGGUF "clip_l.safetensors" + "t5-v1_1-xxl-encoder-Q8_0.gguf") -> engine.
+    GGUF or safetensors for the DiT and T5; Q8_0 is dequantised once at ingest.  Returns the tensor count loaded per part."""
+    n: Dict[str, int] = {}
+    dit = load_gguf(unet_path) if unet_path.endswith(".gguf") else _strip_optional(load_state_dict_file(unet_path), "model.diffusion_model.")
+    engine.load_flux(dit)
+    n["flux"] = len(dit)
+    if ae_path:
+        ae = {k: v for k, v in load_state_dict_file(ae_path).items() if k.startswith(("decoder.", "encoder."))}
+        if not ae:
+            raise ValueError(f"{ae_path}: no decoder.* / encoder.* tensors (not a Flux autoencoder file)")
+        engine.load_vae(ae)
+        n["vae"] = len(ae)
+    if clip_l_path:
+        sd = load_state_dict_file(clip_l_path)
+        clip = _strip_optional(_strip_optional(sd, "cond_stage_model.transformer."), "text_model.")
+        clip = {k: v for k, v in clip.items() if k.startswith(("embeddings.", "encoder.", "final_layer_norm."))}
+        if "embeddings.token_embedding.weight" not in clip:
+            raise ValueError(f"{clip_l_path}: no text_model.embeddings.token_embedding.weight (not a CLIP-L text encoder file)")
+        clip.pop("embeddings.position_ids", None)
+        engine.load_clip(clip)
+        n["clip"] = len(clip)
+    if t5_path:
+        t5 = load_t5_gguf(t5_path) if t5_path.endswith(".gguf") else load_state_dict_file(t5_path)
+        engine.load_t5(t5)
+        n["t5"] = len(t5)
+    return n
+
+
+def _strip_optional(sd: Mapping[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
+    """Drop `prefix` from the keys that carry it (files come with or without the wrapping module's name)."""
+    if not any(k.startswith(prefix) for k in sd):
+        return dict(sd)
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}

@@ -227,3 +227,52 @@ def test_t5_gguf_key_map_matches_reference_map():
         assert got == want, (name, got, want)
         assert want in xxl or "relative_attention_bias" in want  # only block 0 owns a bias table
 
+
+
+def test_load_flux_files_routes_every_part(tmp_path):
+    """checkpoint.load_flux_files: DiT from GGUF (prefix stripped, Q8_0 dequantised), autoencoder / CLIP-L from safetensors
+    (HF `text_model.` prefix stripped, position_ids dropped), T5 from GGUF (llama.cpp names mapped) -> the engine's loaders."""
+    import gguf
+    import numpy as np
+    from safetensors.torch import save_file
+    rng = np.random.default_rng(2)
+    unet = str(tmp_path / "flux.gguf")
+    wr = gguf.GGUFWriter(unet, "flux")
+    w = rng.standard_normal((8, 64)).astype(np.float32)
+    wr.add_tensor("model.diffusion_model.img_in.weight", gguf.quants.quantize(w, gguf.GGMLQuantizationType.Q8_0),
+                  raw_dtype=gguf.GGMLQuantizationType.Q8_0)
+    wr.add_tensor("model.diffusion_model.img_in.bias", rng.standard_normal((8,)).astype(np.float32))
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    ae = str(tmp_path / "ae.safetensors")
+    save_file({"decoder.conv_in.weight": torch.zeros(4, 16, 3, 3), "encoder.conv_in.bias": torch.zeros(4),
+               "loss.logvar": torch.zeros(1)}, ae)
+    clip = str(tmp_path / "clip_l.safetensors")
+    save_file({"text_model.embeddings.token_embedding.weight": torch.zeros(10, 8), "text_model.embeddings.position_ids": torch.zeros(1, 77),
+               "text_model.encoder.layers.0.mlp.fc1.weight": torch.zeros(4, 8), "text_model.final_layer_norm.bias": torch.zeros(8),
+               "text_projection.weight": torch.zeros(8, 8)}, clip)
+    t5 = str(tmp_path / "t5.gguf")
+    wr = gguf.GGUFWriter(t5, "t5encoder")
+    wr.add_tensor("token_embd.weight", rng.standard_normal((6, 32)).astype(np.float32))
+    wr.add_tensor("enc.blk.0.ffn_up.weight", rng.standard_normal((8, 32)).astype(np.float32))
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+
+    class Rec:
+        def __init__(self):
+            self.got = {}
+
+        def load_flux(self, sd): self.got["flux"] = sd
+        def load_vae(self, sd): self.got["vae"] = sd
+        def load_clip(self, sd): self.got["clip"] = sd
+        def load_t5(self, sd): self.got["t5"] = sd
+
+    e = Rec()
+    n = C.load_flux_files(e, unet, ae, clip, t5)
+    assert n == {"flux": 2, "vae": 2, "clip": 3, "t5": 2}
+    assert set(e.got["flux"]) == {"img_in.weight", "img_in.bias"} and e.got["flux"]["img_in.weight"].dtype == torch.bfloat16
+    assert set(e.got["vae"]) == {"decoder.conv_in.weight", "encoder.conv_in.bias"}
+    assert set(e.got["clip"]) == {"embeddings.token_embedding.weight", "encoder.layers.0.mlp.fc1.weight", "final_layer_norm.bias"}
+    assert set(e.got["t5"]) == {"shared.weight", "encoder.block.0.layer.1.DenseReluDense.wi_1.weight"}
+    with pytest.raises(ValueError, match="not a CLIP-L"):
+        C.load_flux_files(Rec(), unet, clip_l_path=ae)
+    with pytest.raises(ValueError, match="not a Flux autoencoder"):
+        C.load_flux_files(Rec(), unet, ae_path=clip)
