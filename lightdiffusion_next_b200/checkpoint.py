@@ -63,6 +63,13 @@ def load_gguf(path: str, handle_prefix: Optional[str] = "model.diffusion_model."
     import numpy as np
 
     reader = gguf.GGUFReader(path)
+    arch = reader.get_field("general.architecture")
+    if arch is not None:  # same check as gguf_sd_loader (:600-614)
+        if len(arch.types) != 1 or arch.types[0] != gguf.GGUFValueType.STRING:
+            raise TypeError(f"{path}: bad type for GGUF general.architecture: expected string, got {arch.types!r}")
+        arch_str = str(bytes(arch.parts[arch.data[-1]]), encoding="utf-8")
+        if arch_str not in {"flux", "sd1", "sdxl", "t5", "t5encoder"}:
+            raise ValueError(f"{path}: unexpected GGUF architecture {arch_str!r} (flux, sd1, sdxl, t5, t5encoder are accepted)")
     names = [t.name for t in reader.tensors]
     strip = len(handle_prefix) if handle_prefix and any(n.startswith(handle_prefix) for n in names) else 0
     out: Dict[str, torch.Tensor] = {}
@@ -71,7 +78,9 @@ def load_gguf(path: str, handle_prefix: Optional[str] = "model.diffusion_model."
         if strip and not t.name.startswith(handle_prefix):
             continue
         key = t.name[strip:]
-        shape = tuple(int(v) for v in reversed(t.shape))  # GGUF stores dimensions innermost-first
+        shape = _gguf_orig_shape(reader, t.name)  # converters that reshape a tensor for quantisation record the original
+        if shape is None:
+            shape = tuple(int(v) for v in reversed(t.shape))  # GGUF stores dimensions innermost-first
         data = np.asarray(t.data)
         if t.tensor_type == Q.F32:
             w = torch.from_numpy(data.copy()).view(torch.float32).reshape(shape)
@@ -88,6 +97,19 @@ def load_gguf(path: str, handle_prefix: Optional[str] = "model.diffusion_model."
             raise ValueError(f"GGUF tensor {t.name!r} has unsupported type {t.tensor_type!r} (F32, F16, BF16, Q8_0 are handled)")
         out[key] = w
     return out
+
+
+def _gguf_orig_shape(reader, tensor_name: str) -> Optional[Tuple[int, ...]]:
+    """`comfy.gguf.orig_shape.<tensor>` metadata (ARRAY of INT32), as gguf_sd_loader_get_orig_shape reads it (:427-447)."""
+    import gguf
+
+    key = f"comfy.gguf.orig_shape.{tensor_name}"
+    field = reader.get_field(key)
+    if field is None:
+        return None
+    if len(field.types) != 2 or field.types[0] != gguf.GGUFValueType.ARRAY or field.types[1] != gguf.GGUFValueType.INT32:
+        raise TypeError(f"bad original shape metadata for {key}: expected ARRAY of INT32, got {field.types}")
+    return tuple(int(field.parts[i][0]) for i in field.data)
 
 
 # llama.cpp tensor names of a T5 encoder -> state-dict keys of the reference's T5 module, applied as successive substring

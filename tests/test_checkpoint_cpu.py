@@ -276,3 +276,29 @@ def test_load_flux_files_routes_every_part(tmp_path):
         C.load_flux_files(Rec(), unet, clip_l_path=ae)
     with pytest.raises(ValueError, match="not a Flux autoencoder"):
         C.load_flux_files(Rec(), unet, ae_path=clip)
+
+
+def test_gguf_orig_shape_metadata_and_architecture_check(tmp_path):
+    """gguf_sd_loader behaviours (Quantizer.py:427-447, 600-614): `comfy.gguf.orig_shape.<name>` restores a tensor's original
+    shape (converters flatten some tensors to quantise them); an unknown `general.architecture` is refused."""
+    import gguf
+    import numpy as np
+    rng = np.random.default_rng(3)
+    w = rng.standard_normal((4, 64)).astype(np.float32)            # stored flat-ish, really [4, 16, 2, 2]
+    path = str(tmp_path / "shaped.gguf")
+    wr = gguf.GGUFWriter(path, "sd1")
+    wr.add_tensor("model.diffusion_model.input_blocks.0.0.weight", gguf.quants.quantize(w, gguf.GGMLQuantizationType.Q8_0),
+                  raw_dtype=gguf.GGMLQuantizationType.Q8_0)
+    wr.add_array("comfy.gguf.orig_shape.model.diffusion_model.input_blocks.0.0.weight", [4, 16, 2, 2])
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    sd = C.load_gguf(path)
+    got = sd["input_blocks.0.0.weight"]
+    assert got.shape == (4, 16, 2, 2)
+    ref = torch.from_numpy(gguf.quants.dequantize(gguf.quants.quantize(w, gguf.GGMLQuantizationType.Q8_0), gguf.GGMLQuantizationType.Q8_0))
+    assert torch.equal(got, ref.reshape(4, 16, 2, 2).to(torch.bfloat16))
+    p2 = str(tmp_path / "llama.gguf")
+    wr = gguf.GGUFWriter(p2, "llama")
+    wr.add_tensor("w", w)
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    with pytest.raises(ValueError, match="unexpected GGUF architecture"):
+        C.load_gguf(p2)
