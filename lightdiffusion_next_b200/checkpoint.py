@@ -194,13 +194,76 @@ def _squeeze(shape: Iterable[int]) -> Tuple[int, ...]:
     return tuple(int(s) for s in shape if int(s) != 1)
 
 
+_DIFFUSERS_RESNET = {"in_layers.0": "norm1", "in_layers.2": "conv1", "emb_layers.1": "time_emb_proj", "out_layers.0": "norm2",
+                     "out_layers.3": "conv2", "skip_connection": "conv_shortcut"}
+_DIFFUSERS_BASIC = {"input_blocks.0.0": "conv_in", "out.0": "conv_norm_out", "out.2": "conv_out",
+                    "time_embed.0": "time_embedding.linear_1", "time_embed.2": "time_embedding.linear_2"}
+
+
+def diffusers_unet_name(key: str, num_res: int = 2, levels: int = 4) -> Optional[str]:
+    """LDM UNet weight key -> the name the same tensor has in a diffusers `UNet2DConditionModel` (the inverse direction of
+    the reference's unet_to_diffusers table, src/NeuralNetwork/unet.py:85-185), for the SD1.x block layout: every level has
+    `num_res` ResBlocks, a down/upsampler closes each level but the last / first.  None for keys without a counterpart."""
+    stem, _, leaf = key.rpartition(".")
+    if stem in _DIFFUSERS_BASIC:
+        return f"{_DIFFUSERS_BASIC[stem]}.{leaf}"
+    parts = key.split(".")
+    per = num_res + 1
+
+    def inner(sub: str, prefix: str, res_i, att_i) -> Optional[str]:
+        # sub: "0.<resnet member>", "1.<transformer member>", "<j>.op.*" / "<j>.conv.*" handled by the callers
+        j, _, rest = sub.partition(".")
+        if j == "0":
+            mod, _, lf = rest.rpartition(".")
+            return f"{prefix}.resnets.{res_i}.{_DIFFUSERS_RESNET[mod]}.{lf}" if mod in _DIFFUSERS_RESNET else None
+        if j == "1" and not rest.startswith("conv."):
+            return f"{prefix}.attentions.{att_i}.{rest}"
+        return None
+
+    if parts[0] == "input_blocks":
+        n = int(parts[1])
+        x, i = divmod(n - 1, per)
+        sub = ".".join(parts[2:])
+        if i == num_res:  # the level's downsampler
+            return f"down_blocks.{x}.downsamplers.0.conv.{leaf}" if sub.startswith("0.op.") else None
+        return inner(sub, f"down_blocks.{x}", i, i)
+    if parts[0] == "middle_block":
+        j, sub = parts[1], ".".join(parts[2:])
+        if j == "1":
+            return f"mid_block.attentions.0.{sub}"
+        mod, _, lf = sub.rpartition(".")
+        return f"mid_block.resnets.{0 if j == '0' else 1}.{_DIFFUSERS_RESNET[mod]}.{lf}" if mod in _DIFFUSERS_RESNET else None
+    if parts[0] == "output_blocks":
+        n = int(parts[1])
+        x, i = divmod(n, per)
+        sub = ".".join(parts[2:])
+        if len(parts) > 3 and parts[3] == "conv":  # the level's upsampler sits after the ResBlock (and the transformer)
+            return f"up_blocks.{x}.upsamplers.0.conv.{leaf}"
+        return inner(sub, f"up_blocks.{x}", i, i)
+    return None
+
+
 def lora_key_map(parts: Mapping[str, Mapping[str, torch.Tensor]]) -> Dict[str, Tuple[str, str]]:
-    """LoRA module name -> (part, weight key).  UNet: `lora_unet_` + key with dots replaced by underscores
-    (LoRas.py:95-99); CLIP: the three text-encoder spellings of LoRas.py:69-83."""
+    """LoRA module name -> (part, weight key).  UNet (model_lora_keys_unet, LoRas.py:86-121): `lora_unet_` / `lora_prior_unet_`
+    + the LDM key with dots replaced by underscores, the same with the tensor's diffusers name (what kohya-trained SD1.5
+    LoRAs use: `lora_unet_down_blocks_0_attentions_0_transformer_blocks_0_attn1_to_q`), and the diffusers-LoRA spellings
+    (`[unet.]<diffusers name>` with `.to_` -> `.processor.to_`, `to_out.0` -> `to_out`); CLIP: the three text-encoder
+    spellings of LoRas.py:69-83."""
     m: Dict[str, Tuple[str, str]] = {}
     for k in parts.get("unet", {}):
         if k.endswith(".weight"):
-            m["lora_unet_" + k[: -len(".weight")].replace(".", "_")] = ("unet", k)
+            stem = k[: -len(".weight")]
+            m["lora_unet_" + stem.replace(".", "_")] = ("unet", k)
+            m["lora_prior_unet_" + stem.replace(".", "_")] = ("unet", k)
+            d = diffusers_unet_name(k)
+            if d is not None:
+                dstem = d[: -len(".weight")]
+                m["lora_unet_" + dstem.replace(".", "_")] = ("unet", k)
+                proc = dstem.replace(".to_", ".processor.to_")
+                if proc.endswith(".to_out.0"):
+                    proc = proc[:-2]
+                m[proc] = ("unet", k)
+                m["unet." + proc] = ("unet", k)
     for k in parts.get("clip", {}):
         if not (k.startswith("encoder.layers.") and k.endswith(".weight")):
             continue

@@ -302,3 +302,33 @@ def test_gguf_orig_shape_metadata_and_architecture_check(tmp_path):
     wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
     with pytest.raises(ValueError, match="unexpected GGUF architecture"):
         C.load_gguf(p2)
+
+
+def test_lora_unet_key_map_equals_the_reference_map():
+    """Every LoRA name the reference resolves to an existing SD1.5 UNet weight (model_lora_keys_unet incl. the diffusers names
+    kohya LoRAs use; tests/golden/make_golden_lora_keys.py) resolves to the same weight here, and nothing else is claimed;
+    the LDM -> diffusers naming is the exact inverse of the reference's unet_to_diffusers table."""
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lora_keys.pt"))
+    unet_keys = {k[len("diffusion_model."):] for k in gold["unet_keys"]}
+    assert unet_keys == set(synth.unet_shapes())
+    want = {name: tgt[len("diffusion_model."):] for name, tgt in gold["lora_to_unet"].items() if tgt in set(gold["unet_keys"])}
+    got = {name: key for name, (part, key) in C.lora_key_map({"unet": synth.unet_shapes(), "clip": {}}).items() if part == "unet"}
+    assert got == want
+    assert "lora_unet_down_blocks_0_attentions_0_transformer_blocks_0_attn1_to_q" in got
+    assert got["lora_unet_up_blocks_3_resnets_2_conv_shortcut"] == "output_blocks.11.0.skip_connection.weight"
+    inv = {ldm: d for d, ldm in gold["diffusers_map"].items() if ldm in unet_keys}
+    for k in unet_keys:
+        assert C.diffusers_unet_name(k) == inv.get(k), k
+
+
+def test_merge_lora_through_diffusers_names():
+    """A kohya-style SD1.5 LoRA names UNet modules by their diffusers path: the merge lands on the LDM weight the reference's
+    key map points at, with the same arithmetic as for LDM-named modules."""
+    g = torch.Generator().manual_seed(5)
+    k = "output_blocks.4.1.transformer_blocks.0.attn2.to_k.weight"      # = up_blocks.1.attentions.1 in diffusers
+    w0 = torch.randn(16, 24, generator=g).half()
+    parts = {"unet": {k: w0.clone()}, "clip": {}, "vae": {}}
+    m = "lora_unet_up_blocks_1_attentions_1_transformer_blocks_0_attn2_to_k"
+    up, down = torch.randn(16, 2, generator=g), torch.randn(2, 24, generator=g)
+    assert C.merge_lora(parts, {m + ".lora_up.weight": up, m + ".lora_down.weight": down, m + ".alpha": torch.tensor(1.0)}, 0.7) == 1
+    assert torch.equal(parts["unet"][k], w0 + (0.7 * (1.0 / 2) * torch.mm(up, down)).to(w0.dtype))
