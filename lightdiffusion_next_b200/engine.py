@@ -83,6 +83,27 @@ class Engine:
 
     def load_clip(self, state_dict: Dict[str, torch.Tensor]) -> None:
         self.load_weights(CLIP, state_dict)
+        self._clip_tok = state_dict.get("embeddings.token_embedding.weight")  # kept for textual-inversion rows
+        self._clip_ti_key = None
+
+    def clip_vocab(self) -> int:
+        tok = getattr(self, "_clip_tok", None)
+        if tok is None:
+            raise L.LdnError("CLIP weights not loaded (Engine.load_clip)")
+        return int(tok.shape[0])
+
+    def set_clip_extra_embeddings(self, vectors) -> None:
+        """Textual-inversion vectors become rows vocab, vocab + 1, ... of the token-embedding table (what the reference's
+        set_up_textual_embeddings does with a temporary Embedding, src/SD15/SDClip.py:247-259).  The extended table replaces
+        the loaded one (the original rows are unchanged, so plain prompts keep working) and is re-uploaded only when the
+        set of vectors changes."""
+        from .pipeline import extend_token_table
+
+        self.clip_vocab()
+        key = hash(torch.stack([v.detach().float().cpu() for v in vectors]).numpy().tobytes())
+        if key != self._clip_ti_key:
+            self.load_weights(CLIP, {"embeddings.token_embedding.weight": extend_token_table(self._clip_tok, vectors)})
+            self._clip_ti_key = key
 
     def load_taesd(self, state_dict: Dict[str, torch.Tensor]) -> None:
         """TAESD preview decoder weights (keys of `taesd_decoder.safetensors`: nn.Sequential indices, taesd.py:104-136)."""

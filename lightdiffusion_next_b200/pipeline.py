@@ -17,6 +17,41 @@ from .engine import Engine
 EMPTY_TOKENS = [49406] + [49407] * 76  # <|startoftext|>, <|endoftext|> padding: what the SD1 tokenizer emits for ""
 
 
+PAD_TOKEN = 49407
+
+
+def resolve_textual_embeddings(tokens, vocab: int, width: int = 768, pad: int = PAD_TOKEN):
+    """SDClipModel.set_up_textual_embeddings (src/SD15/SDClip.py:213-268): a token row may carry textual-inversion embedding
+    VECTORS in place of ids (what the reference's tokenizer emits for "embedding:name"; its default negative prompt has four,
+    src/user/pipeline.py:98).  Every vector of the right width gets the next id past the vocabulary; a vector of the wrong
+    width is dropped (the ids behind it move up and the row is re-padded at its end -- the weights keep their positions,
+    as in the reference).  Returns (ids [rows, n] int64, weights [rows, n] fp32, [vectors in id order])."""
+    extra: List[torch.Tensor] = []
+    ids_rows, w_rows = [], []
+    for row in tokens:
+        ids = []
+        for t, _ in row:
+            if isinstance(t, torch.Tensor):
+                if t.dim() == 1 and t.shape[0] == width:
+                    ids.append(vocab + len(extra))
+                    extra.append(t)
+                # else: ignored, like the reference (it logs a warning)
+            else:
+                if int(t) < 0:
+                    raise ValueError("negative token ids are not supported")
+                ids.append(int(t))
+        ids += [pad] * (len(row) - len(ids))
+        ids_rows.append(ids)
+        w_rows.append([float(w) for _, w in row])
+    return torch.tensor(ids_rows, dtype=torch.int64), torch.tensor(w_rows, dtype=torch.float32), extra
+
+
+def extend_token_table(base: torch.Tensor, vectors: Sequence[torch.Tensor]) -> torch.Tensor:
+    """The reference builds a new Embedding in the table's own dtype with the vectors appended (SDClip.py:247-259): the
+    vectors are rounded to that dtype (fp16 checkpoints) exactly as there."""
+    return torch.cat([base.cpu(), torch.stack([v.detach().cpu() for v in vectors]).to(base.dtype)])
+
+
 class Pipeline:
     def __init__(self, engine: Engine):
         self.e = engine
@@ -27,8 +62,13 @@ class Pipeline:
         Prompt weights: per-token lerp against the empty-prompt encoding (ClipTokenWeightEncoder, SDClip.py:54-76).
         return_pooled: also return the pooled vector [1, 768] of the first chunk -- the last layer's final-LN state at the
         first end-of-text token (CLIPTextModel_.forward, src/clip/CLIPTextModel.py:95-105; the `y` input of Flux)."""
-        ids = torch.tensor([[t for t, _ in row] for row in tokens], dtype=torch.int64)
-        wts = torch.tensor([[w for _, w in row] for row in tokens], dtype=torch.float32)
+        if any(isinstance(t, torch.Tensor) for row in tokens for t, _ in row):
+            ids, wts, extra = resolve_textual_embeddings(tokens, self.e.clip_vocab())
+            if extra:
+                self.e.set_clip_extra_embeddings(extra)
+        else:
+            ids = torch.tensor([[t for t, _ in row] for row in tokens], dtype=torch.int64)
+            wts = torch.tensor([[w for _, w in row] for row in tokens], dtype=torch.float32)
         has_w = bool((wts != 1.0).any())
         if has_w:
             ids = torch.cat([ids, torch.tensor([EMPTY_TOKENS], dtype=torch.int64)])

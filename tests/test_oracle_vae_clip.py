@@ -83,3 +83,41 @@ def test_oracle_flux_vae_decoder_matches_reference_golden():
         img = O.vae_decode(sd, gold[f"z_{name}"])
         ref = gold[f"img_{name}"]
         assert img.shape == ref.shape and ((img - ref).norm() / ref.norm()).item() < 1e-4
+
+
+def test_textual_inversion_rows_match_reference():
+    """Token rows carrying textual-inversion vectors (the reference pipeline's default negative prompt has four): the
+    product's host handling (pipeline.resolve_textual_embeddings / extend_token_table, Pipeline.encode) with the device call
+    answered by the oracle reproduces the reference's SD1ClipModel.encode_token_weights -- extra ids past the vocabulary,
+    a wrong-width vector dropped with the row re-padded and the weights left in place, vectors rounded to the table's dtype."""
+    from lightdiffusion_next_b200.pipeline import Pipeline, extend_token_table, resolve_textual_embeddings
+    g = torch.load(os.path.join(GOLDEN, "clip_ti_small.pt"))
+    sd = dict(O.synth_state_dict(O.clip_param_shapes(), seed=777))
+    row = [((g["vectors"][t[1]] if t[1] != "bad" else g["bad"]) if isinstance(t, tuple) else t, w) for t, w in g["row_spec"]]
+    ids, wts, extra = resolve_textual_embeddings([row], 49408)
+    assert ids.shape == (1, 77) and ids[0, :6].tolist() == [49406, 320, 49408, 49409, 1125, 49410] and int(ids[0, -1]) == 49407
+    assert len(extra) == 3 and abs(float(wts[0, 3]) - 1.2) < 1e-6 and abs(float(wts[0, 6]) - 0.8) < 1e-6
+
+    class Stand:
+        device = torch.device("cpu")
+
+        def __init__(self):
+            self.sd = dict(sd)
+            self.uploads = 0
+
+        def clip_vocab(self):
+            return 49408
+
+        def set_clip_extra_embeddings(self, vectors):
+            self.sd["embeddings.token_embedding.weight"] = extend_token_table(sd["embeddings.token_embedding.weight"], vectors)
+            self.uploads += 1
+
+        def clip_encode(self, ids):
+            return O.clip_encode(self.sd, ids)
+
+    e = Stand()
+    cond = Pipeline(e).encode([row])
+    assert e.uploads == 1 and e.sd["embeddings.token_embedding.weight"].shape == (49411, 768)
+    assert rel(cond, g["cond"]) < 2e-5
+    plain = Pipeline(e).encode([[(49406, 1.0), (320, 1.0)] + [(49407, 1.0)] * 75])     # the original rows still work
+    assert rel(plain, O.clip_encode(sd, torch.tensor([[49406, 320] + [49407] * 75]))[0]) < 1e-6
