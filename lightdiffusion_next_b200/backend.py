@@ -167,7 +167,7 @@ def engine_sampler_function(engine: Engine, sampler_name: str, interrupt=None):
             opts.setdefault("seed", (extra_args or {}).get("seed"))
             allowed.add("seed")
         elif sampler_name == "euler_ancestral_cfgpp":
-            allowed = {"noise_sampler"}
+            allowed = {"noise_sampler", "eta", "s_noise"}
         else:
             allowed = {"cfg_scale", "cfg_min"}
         unknown = set(opts) - allowed

@@ -108,8 +108,10 @@ def sample_dpmpp_2m_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor,
 def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
                                  noise_sampler: Optional[Callable] = None,
                                  callback: Optional[Callable] = None,
-                                 interrupt: Optional[Callable[[], bool]] = None) -> torch.Tensor:
-    """d = (x - D)/sigma; x += d (sigma_down - sigma); x += randn_like(x) sigma_up   (eta = 1, s_noise = 1)."""
+                                 interrupt: Optional[Callable[[], bool]] = None, eta: float = 1.0,
+                                 s_noise: float = 1.0) -> torch.Tensor:
+    """d = (x - D)/sigma; x += d (sigma_down - sigma); x += noise * s_noise * sigma_up, (sigma_down, sigma_up) =
+    get_ancestral_step(sigma_i, sigma_{i+1}, eta)   (sample_euler_ancestral_dy_cfg_pp as executed, samplers.py:612-740)."""
     B = x.shape[0]
     sig = sigmas.float().cpu()
     n = len(sig) - 1
@@ -119,12 +121,12 @@ def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.
         if interrupt is not None and interrupt():
             return x  # the reference's interrupt_flag poll (samplers.py:884-889): hand back the current latent
         du, dc = loop.denoise_pair(x, float(sig[i]))
-        sd, su = get_ancestral_step(sig[i], sig[i + 1])
+        sd, su = get_ancestral_step(sig[i], sig[i + 1], eta)
         noise = None
         if sig[i + 1] > 0:
             # the reference's convention (samplers.py:633-636, 732): noise_sampler(sigma, sigma_next) -> noise like x
             noise = noise_sampler(sig[i], sig[i + 1]).to(x.device) if noise_sampler is not None else torch.randn_like(x)
-        engine.cfg_step(x, du, dc, cfg, 1, c0=float(sd - sig[i]), c1=float(su), c2=float(sig[i]), noise=noise,
+        engine.cfg_step(x, du, dc, cfg, 1, c0=float(sd - sig[i]), c1=float(su) * s_noise, c2=float(sig[i]), noise=noise,
                         x_out=loop.x_next, denoised_out=den)
         x, loop.x_next = loop.x_next, x
         if callback is not None:

@@ -75,4 +75,11 @@ res = sampling.sample(mp, ksampler_util.prepare_noise(lat, 42), [[ctx_pos, {}]],
                       sigmas, latent_image=lat, seed=42, pipeline=True)
 out["anc_final"] = res.clone(); out["anc_calls"] = torch.tensor(ns.calls)
 print("anc", float(res.std()), ns.calls, flush=True)
+# ... and with eta / s_noise (the sampler's own keyword arguments, samplers.py:619-620)
+ns = SeqNoise(lat.shape, 7)
+sampler = sampling.ksampler("euler_ancestral_cfgpp", extra_options={"noise_sampler": ns, "eta": 0.6, "s_noise": 1.1})
+res = sampling.sample(mp, ksampler_util.prepare_noise(lat, 42), [[ctx_pos, {}]], [[ctx_neg, {}]], 7.0, torch.device("cpu"), sampler,
+                      sigmas, latent_image=lat, seed=42, pipeline=True)
+out["anc_eta_final"] = res.clone()
+print("anc_eta", float(res.std()), flush=True)
 torch.save(out, os.path.join(HERE, "msopts_small.pt")); print("wrote msopts_small.pt")

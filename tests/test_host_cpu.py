@@ -311,6 +311,20 @@ def test_euler_ancestral_injected_noise_sampler_matches_reference(unet_sd):
     ref = g["anc_final"]
     assert float((e - ref).norm() / ref.norm()) < 1e-4
     assert torch.allclose(torch.tensor(ns.calls), g["anc_calls"], rtol=1e-5)
+    # eta / s_noise, through the registry-seam function with the reference's extra_options
+    import types
+    from lightdiffusion_next_b200 import backend
+    from lightdiffusion_next_b200.schedule import calculate_sigmas
+    eng = FakeEngine(unet_sd)
+    cond = lambda t: [{"model_conds": {"c_crossattn": types.SimpleNamespace(cond=t)}}]
+    model_k = types.SimpleNamespace(inner_model=types.SimpleNamespace(
+        conds={"positive": cond(g["ctx_pos"]), "negative": cond(g["ctx_neg"])}, cfg=7.0))
+    sigmas = calculate_sigmas(eng.schedule, "karras", 3)
+    x = S.prepare_noise(lat, 42) * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+    out = backend.engine_sampler_function(eng, "euler_ancestral_cfgpp")(
+        model_k, x, sigmas, pipeline=True, noise_sampler=SeqNoise(lat.shape, 7), eta=0.6, s_noise=1.1)
+    ref = g["anc_eta_final"]
+    assert float((out / S.LATENT_SCALE - ref).norm() / ref.norm()) < 1e-4
 
 
 def test_schedules_sweep_product_equals_oracle_and_is_well_formed():
