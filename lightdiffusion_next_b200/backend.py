@@ -163,7 +163,8 @@ def engine_sampler_function(engine: Engine, sampler_name: str, interrupt=None):
             allowed = {"enable_multiscale", "multiscale_factor", "multiscale_fullres_start", "multiscale_fullres_end",
                        "multiscale_intermittent_fullres"}
         elif sampler_name == "dpmpp_sde_cfgpp":
-            allowed = {"noise_sampler", "enable_multiscale", "multiscale_factor", "eta", "r"}
+            allowed = {"noise_sampler", "enable_multiscale", "multiscale_factor", "eta", "r", "s_noise", "multiscale_fullres_start",
+                       "multiscale_fullres_end", "multiscale_intermittent_fullres"}
             opts.setdefault("seed", (extra_args or {}).get("seed"))
             allowed.add("seed")
         elif sampler_name == "euler_ancestral_cfgpp":

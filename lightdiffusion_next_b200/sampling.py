@@ -209,9 +209,12 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
                            noise_sampler: Optional[Callable] = None, seed: Optional[int] = None, eta: float = 1.0,
                            r: float = 0.5, enable_multiscale: bool = False, multiscale_factor: float = 0.5,
                            callback: Optional[Callable] = None,
-                           interrupt: Optional[Callable[[], bool]] = None) -> torch.Tensor:
+                           interrupt: Optional[Callable[[], bool]] = None, s_noise: float = 1.0,
+                           multiscale_fullres_start: int = 5, multiscale_fullres_end: int = 8,
+                           multiscale_intermittent_fullres: bool = False) -> torch.Tensor:
     """DPM-Solver++ (SDE) as the reference executes it (samplers.py:966-1254): two CFG-batched UNet evaluations per
-    step (at sigma_i and at the midpoint in log-sigma), ancestral noise from `noise_sampler(sigma, sigma_next)`."""
+    step (at sigma_i and at the midpoint in log-sigma), ancestral noise from `noise_sampler(sigma, sigma_next)`.  The
+    keyword defaults are the reference sampler's own (:973-989: multiscale margins 5 / 8, no intermittent full-res steps)."""
     B, _, oh, ow = x.shape
     sh = int(max(8, ((oh * multiscale_factor) // 8) * 8)) if enable_multiscale else oh
     sw = int(max(8, ((ow * multiscale_factor) // 8) * 8)) if enable_multiscale else ow
@@ -236,7 +239,8 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
     for i in range(n):
         if interrupt is not None and interrupt():
             return x  # the reference's interrupt_flag poll (samplers.py:884-889): hand back the current latent
-        fullres = (not active) or (i < 5 or i >= n - 8)  # sampler defaults: start 5, end 8, not intermittent
+        fullres = (not active) or _multiscale_fullres(i, n, multiscale_fullres_start, multiscale_fullres_end,
+                                                      multiscale_intermittent_fullres)
         den = denoised_at(x, float(sig[i]), fullres)
         if sig[i + 1] == 0:
             x = x + (x - den) / float(sig[i]) * float(sig[i + 1] - sig[i])
@@ -246,13 +250,13 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
             sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(s), eta)
             s_ = t_fn(sd)
             n1 = noise_sampler(sigma_fn(t), sigma_fn(s)).to(x.device)
-            x_2 = float(sigma_fn(s_) / sigma_fn(t)) * x - float((t - s_).expm1()) * den + n1 * float(su)
+            x_2 = float(sigma_fn(s_) / sigma_fn(t)) * x - float((t - s_).expm1()) * den + n1 * (float(su) * s_noise)
             den_2 = denoised_at(x_2, float(sigma_fn(s)), fullres)
             sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(t_next), eta)
             t_next_ = t_fn(sd)
             d_mix = (1 - 1 / (2 * r)) * den + (1 / (2 * r)) * den_2
             n2 = noise_sampler(sigma_fn(t), sigma_fn(t_next)).to(x.device)
-            x = float(sigma_fn(t_next_) / sigma_fn(t)) * x - float((t - t_next_).expm1()) * d_mix + n2 * float(su)
+            x = float(sigma_fn(t_next_) / sigma_fn(t)) * x - float((t - t_next_).expm1()) * d_mix + n2 * (float(su) * s_noise)
         if callback is not None:
             callback({"x": x, "i": i, "sigma": sig[i], "denoised": den})
     return x
