@@ -59,9 +59,22 @@ class EngineWrapper:
         return self
 
 
-def unet_state_dict_from_model(base_model) -> Dict[str, torch.Tensor]:
-    """Weights stay owned by BaseModel.diffusion_model; the engine keeps its own repacked bf16 copy."""
-    return {k: v for k, v in base_model.diffusion_model.state_dict().items()}
+def unet_state_dict_from_model(base_model, model_patcher=None) -> Dict[str, torch.Tensor]:
+    """Weights stay owned by BaseModel.diffusion_model; the engine keeps its own repacked bf16 copy.  Weight patches queued
+    on the ModelPatcher (LoRAs -- the reference's default pipeline loads one, src/user/pipeline.py:283-291) are what the
+    reference would apply in patch_model before running the UNet (ModelPatcher.py:267-300, 515-548): they are folded into the
+    copy with the patcher's OWN calculate_weight, on an fp32 temporary rounded once to the storage dtype, exactly as
+    patch_weight_to_device does.  The reference's module is left untouched."""
+    sd = {k: v for k, v in base_model.diffusion_model.state_dict().items()}
+    patches = getattr(model_patcher, "patches", None) if model_patcher is not None else None
+    if patches:
+        pref = "diffusion_model."
+        for key, plist in patches.items():
+            k = key[len(pref):] if key.startswith(pref) else None
+            if k is not None and k in sd:
+                w = sd[k]
+                sd[k] = model_patcher.calculate_weight(plist, w.to(torch.float32, copy=True), key).to(w.dtype)
+    return sd
 
 
 def install(model_patcher, engine: Optional[Engine] = None, max_rows: int = 2, max_h: int = 128, max_w: int = 128,
@@ -70,7 +83,7 @@ def install(model_patcher, engine: Optional[Engine] = None, max_rows: int = 2, m
     ApplyStableFastUnet.apply_stable_fast pattern)."""
     if engine is None:
         engine = Engine(max_rows=max_rows, max_h=max_h, max_w=max_w, max_ctx_tokens=max_ctx_tokens)
-        engine.load_unet(unet_state_dict_from_model(model_patcher.model))
+        engine.load_unet(unet_state_dict_from_model(model_patcher.model, model_patcher))
     m = model_patcher.clone()
     m.set_model_unet_function_wrapper(EngineWrapper(engine))
     return m

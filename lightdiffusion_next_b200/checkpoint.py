@@ -8,7 +8,8 @@ Mirrors the reference's on-disk contract, not its loader classes:
     SD15.process_clip_state_dict does, src/SD15/SD15.py:32-69);
   * LoRA merge: kohya-style `lora_unet_*` / `lora_te_text_model_encoder_layers_*` keys (src/Model/LoRas.py:15-121) folded
     into the weights with `W += strength * (alpha / rank) * (up @ down)` (ModelPatcher.calculate_weight,
-    src/Model/ModelPatcher.py:621-650): fp32 product, rounded to the weight's storage dtype before the add.
+    src/Model/ModelPatcher.py:621-650, applied by patch_weight_to_device :267-300): fp32 product added to an fp32 copy of
+    the weight, rounded once to the weight's storage dtype.
 
 The engine never sees file formats: it takes the resulting `{name: tensor}` dicts through `Engine.load_unet / load_vae /
 load_clip` (C ABI `ldn_load_weights`), which repack to the HBM layout once.
@@ -296,7 +297,8 @@ def merge_lora(parts: Dict[str, Dict[str, torch.Tensor]], lora: Mapping[str, tor
             alpha *= float(lora[a_k].item()) / down.shape[0]
         w = parts[part][wkey]
         delta = (alpha * torch.mm(up.flatten(start_dim=1), down.flatten(start_dim=1))).reshape(w.shape)
-        parts[part][wkey] = w + delta.to(w.dtype)
+        # patch_weight_to_device (ModelPatcher.py:267-300): the sum is formed on an fp32 copy and rounded once
+        parts[part][wkey] = (w.to(torch.float32) + delta).to(w.dtype)
         n += 1
     return n
 

@@ -114,7 +114,7 @@ def test_merge_lora_matches_reference_formula():
 
     def expect(w, up, down, strength, alpha):
         a = strength * (alpha / down.shape[0] if alpha is not None else 1.0)
-        return w + (a * torch.mm(up.float().flatten(1), down.float().flatten(1))).reshape(w.shape).to(w.dtype)
+        return (w.float() + (a * torch.mm(up.float().flatten(1), down.float().flatten(1))).reshape(w.shape)).to(w.dtype)
 
     k = "input_blocks.1.1.transformer_blocks.0.attn1.to_q.weight"
     m = "lora_unet_input_blocks_1_1_transformer_blocks_0_attn1_to_q"
@@ -331,4 +331,40 @@ def test_merge_lora_through_diffusers_names():
     m = "lora_unet_up_blocks_1_attentions_1_transformer_blocks_0_attn2_to_k"
     up, down = torch.randn(16, 2, generator=g), torch.randn(2, 24, generator=g)
     assert C.merge_lora(parts, {m + ".lora_up.weight": up, m + ".lora_down.weight": down, m + ".alpha": torch.tensor(1.0)}, 0.7) == 1
-    assert torch.equal(parts["unet"][k], w0 + (0.7 * (1.0 / 2) * torch.mm(up, down)).to(w0.dtype))
+    assert torch.equal(parts["unet"][k], (w0.float() + 0.7 * (1.0 / 2) * torch.mm(up, down)).to(w0.dtype))
+
+
+def test_lora_application_is_bit_identical_to_the_reference_patcher():
+    """merge_lora (ingest path) and backend.unet_state_dict_from_model (seam path, patches queued on a ModelPatcher) against
+    weights patched by the reference's own LoRas.load_lora + ModelPatcher.add_patches / patch_model
+    (tests/golden/make_golden_lora_apply.py): same module-name resolution, same fp32 sum rounded once to fp16 -- bit for bit."""
+    import types
+    from lightdiffusion_next_b200 import backend
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lora_apply.pt"))
+    keys = list(gold["patched"])
+    base = {k: synth.synth_tensor(k, synth.unet_shapes()[k]) for k in keys}
+    parts = {"unet": {k: v.clone() for k, v in base.items()}, "clip": {}, "vae": {}}
+    assert C.merge_lora(parts, gold["lora"], strength_model=gold["strength"]) == 3
+    for k in keys:
+        assert not torch.equal(parts["unet"][k], base[k])
+        assert torch.equal(parts["unet"][k], gold["patched"][k]), k
+
+    # seam path: a ModelPatcher-like object with queued patches in the reference's own tuple format
+    def calculate_weight(patches, weight, key):                     # stand-in with the reference's signature
+        for strength, (kind, (up, down, alpha, mid, dora)), _ in patches:
+            a = strength * (alpha / down.shape[0] if alpha is not None else 1.0)
+            weight += (a * torch.mm(up.float().flatten(1), down.float().flatten(1))).reshape(weight.shape)
+        return weight
+
+    km = {m: k for m, (p, k) in C.lora_key_map({"unet": synth.unet_shapes(), "clip": {}}).items()}
+    patches = {}
+    for name in {n.rsplit(".lora_up.weight", 1)[0] for n in gold["lora"] if n.endswith(".lora_up.weight")}:
+        al = gold["lora"].get(name + ".alpha")
+        patches["diffusion_model." + km[name]] = [(gold["strength"], ("lora", (gold["lora"][name + ".lora_up.weight"],
+                                                   gold["lora"][name + ".lora_down.weight"], None if al is None else al.item(), None, None)), 1.0)]
+    dm = types.SimpleNamespace(state_dict=lambda: {k: v.clone() for k, v in base.items()})
+    patcher = types.SimpleNamespace(patches=patches, calculate_weight=calculate_weight)
+    sd = backend.unet_state_dict_from_model(types.SimpleNamespace(diffusion_model=dm), patcher)
+    for k in keys:
+        assert torch.equal(sd[k], gold["patched"][k]), k
+    assert all(torch.equal(a, b) for a, b in zip(dm.state_dict().values(), base.values()))   # the source module is untouched
