@@ -65,15 +65,30 @@ def unet_state_dict_from_model(base_model, model_patcher=None) -> Dict[str, torc
     reference would apply in patch_model before running the UNet (ModelPatcher.py:267-300, 515-548): they are folded into the
     copy with the patcher's OWN calculate_weight, on an fp32 temporary rounded once to the storage dtype, exactly as
     patch_weight_to_device does.  The reference's module is left untouched."""
-    sd = {k: v for k, v in base_model.diffusion_model.state_dict().items()}
+    return patched_state_dict(base_model.diffusion_model.state_dict(), model_patcher, "diffusion_model.")
+
+
+def patched_state_dict(state_dict, model_patcher, prefix: str) -> Dict[str, torch.Tensor]:
+    """A copy of `state_dict` with the patches a reference ModelPatcher has queued for keys `prefix + name` applied the way
+    patch_weight_to_device applies them (fp32 temporary, the patcher's own calculate_weight, one rounding)."""
+    sd = {k: v for k, v in state_dict.items()}
     patches = getattr(model_patcher, "patches", None) if model_patcher is not None else None
     if patches:
-        pref = "diffusion_model."
         for key, plist in patches.items():
-            k = key[len(pref):] if key.startswith(pref) else None
+            k = key[len(prefix):] if key.startswith(prefix) else None
             if k is not None and k in sd:
                 w = sd[k]
                 sd[k] = model_patcher.calculate_weight(plist, w.to(torch.float32, copy=True), key).to(w.dtype)
+    return sd
+
+
+def clip_state_dict_from_clip(clip) -> Dict[str, torch.Tensor]:
+    """CLIP-L text-model weights of a reference `CLIP` object (src/clip/Clip.py:297-404) for `Engine.load_clip`, with the
+    patches queued on `clip.patcher` (the CLIP half of a LoRA, keys `clip_l.transformer.text_model.*`, LoRas.py:60-84) folded
+    in like the UNet's."""
+    tm = clip.cond_stage_model.clip_l.transformer.text_model
+    sd = patched_state_dict(tm.state_dict(), getattr(clip, "patcher", None), "clip_l.transformer.text_model.")
+    sd.pop("embeddings.position_ids", None)
     return sd
 
 

@@ -368,3 +368,29 @@ def test_lora_application_is_bit_identical_to_the_reference_patcher():
     for k in keys:
         assert torch.equal(sd[k], gold["patched"][k]), k
     assert all(torch.equal(a, b) for a, b in zip(dm.state_dict().values(), base.values()))   # the source module is untouched
+
+
+def test_clip_patches_are_folded_in_at_the_seam():
+    """backend.clip_state_dict_from_clip: the CLIP half of a LoRA queued on the reference's `clip.patcher` lands on the
+    text-model weights handed to Engine.load_clip (same arithmetic as the UNet path); position_ids is dropped."""
+    import types
+    from lightdiffusion_next_b200 import backend
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(24, 24, generator=g).half()
+    up, down = torch.randn(24, 2, generator=g), torch.randn(2, 24, generator=g)
+
+    def calculate_weight(patches, weight, key):
+        for strength, (kind, (u, d, alpha, mid, dora)), _ in patches:
+            weight += strength * (alpha / d.shape[0]) * torch.mm(u.float(), d.float())
+        return weight
+
+    tm = types.SimpleNamespace(state_dict=lambda: {"encoder.layers.0.self_attn.q_proj.weight": w.clone(),
+                                                   "embeddings.position_ids": torch.arange(77)[None]})
+    clip = types.SimpleNamespace(
+        cond_stage_model=types.SimpleNamespace(clip_l=types.SimpleNamespace(transformer=types.SimpleNamespace(text_model=tm))),
+        patcher=types.SimpleNamespace(calculate_weight=calculate_weight, patches={
+            "clip_l.transformer.text_model.encoder.layers.0.self_attn.q_proj.weight": [(0.7, ("lora", (up, down, 4.0, None, None)), 1.0)],
+            "clip_l.logit_scale": [(1.0, ("lora", (up, down, 1.0, None, None)), 1.0)]}))
+    sd = backend.clip_state_dict_from_clip(clip)
+    assert set(sd) == {"encoder.layers.0.self_attn.q_proj.weight"}
+    assert torch.equal(sd["encoder.layers.0.self_attn.q_proj.weight"], (w.float() + 0.7 * (4.0 / 2) * torch.mm(up, down)).half())
