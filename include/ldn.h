@@ -78,6 +78,11 @@ int ldn_unet_last_launches(ldn_handle h);
 int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
                  float c1, float c2, const float* noise, float* x_out, float* denoised_out, int64_t n, void* stream);
 
+/* Bilinear resample of fp32 planes, src [planes,h,w] -> dst [planes,oh,ow], with the arithmetic of
+ * F.interpolate(mode="bilinear", align_corners=False): the down / up-scaling around the reference's half-resolution
+ * (multiscale) sampler steps, src/sample/samplers.py:821-835 (dpmpp_2m_cfgpp), :1035-1051 (dpmpp_sde_cfgpp). */
+int ldn_resample_bilinear(const float* src, float* dst, int planes, int h, int w, int oh, int ow, void* stream);
+
 /* ---- VAE decode / CLIP encode */
 /* z: [B,zc,h,w] fp32, already un-scaled by the latent format (SD1.x: zc = 4, z / 0.18215; Flux VAE: zc = 16, no
  * post_quant_conv -- both read off the loaded decoder weights); rgb: [B,8h,8w,3] fp32 in [0,1] */
@@ -100,6 +105,10 @@ int ldn_taesd_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h,
 /* ids: [S,77] int64 (device); out_last: [S,77,768] fp32 final-LN of last layer (may be NULL);
  * out_penultimate: [S,77,768] fp32 final-LN of layer -2 (what SD1.5 uses) */
 int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultimate, float* out_last, void* stream);
+/* Textual-inversion vectors for the CLIP token table: vectors [n, 768] fp32 (device) become token ids vocab, vocab + 1, ...
+ * of the loaded table, which itself is untouched (SDClipModel.set_up_textual_embeddings, src/SD15/SDClip.py:213-268).
+ * n <= 256; n = 0 clears them. No re-upload of the table, no program rebuild. */
+int ldn_clip_set_extra_embeddings(ldn_handle h, const float* vectors, int n, void* stream);
 /* T5 text encoder of the Flux path (T5.forward / T5Stack.forward, src/clip/FluxClip.py:457-562; no attention mask, layer
  * "last" + final RMS norm as T5XXLModel configures SDClipModel, :565-590).  ids: [S,n] int64 (device), any n >= 1;
  * rel_buckets: [2n-1] int32 (device), the reference's relative-position bucket (T5Attention._relative_position_bucket,

@@ -46,11 +46,13 @@ SIGNATURES = {
     "ldn_unet_denoise": [_p, _p, _p, _p, _i, _i, _i, _p],
     "ldn_unet_last_launches": [_p],
     "ldn_cfg_step": [_p, _p, _p, _f, _i, _f, _f, _f, _p, _p, _p, _l, _p],
+    "ldn_resample_bilinear": [_p, _p, _i, _i, _i, _i, _i, _p],
     "ldn_vae_decode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_vae_encode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_taesd_decode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_flux_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "ldn_clip_encode": [_p, _p, _i, _p, _p, _p],
+    "ldn_clip_set_extra_embeddings": [_p, _p, _i, _p],
     "ldn_t5_encode": [_p, _p, _p, _i, _i, _p, _p],
     "ldn_gemm_bf16": [_p, _l, _i, _p, _l, _i, _p, _i, _i, _p, _p, _i, _i, _p, _l, _p, _l, _p, _i, _i, _i, _i, _p],
     "ldn_conv3x3_bf16": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],

@@ -52,6 +52,10 @@ void clip_finalize(ldn_engine* e, cudaStream_t stream) {
     C.bqk.push_back(bqk);
     C.out_bias.push_back(ob);
   }
+  if (!e->clip_extra) {
+    e->clip_extra = e->weights_arena.get<float>((size_t)ldn_engine::kClipExtraCap * W, true);
+    e->clip_extra_n = reinterpret_cast<int*>(e->weights_arena.alloc(sizeof(int), true));
+  }
   LDN_CUDA(cudaStreamSynchronize(stream));
   e->finalized[2] = true;
 }
@@ -92,9 +96,13 @@ static Program* build_clip_program(ldn_engine* e, int S) {
     add(name, [plan](cudaStream_t st) { launch_gemm(plan, st); });
   };
   {
-    const float* tok = e->W(2, "embeddings.token_embedding.weight").f();
+    const DevTensor& tokw = e->W(2, "embeddings.token_embedding.weight");
+    const float* tok = tokw.f();
+    const int vocab = (int)tokw.shape[0];
     const float* pos = e->W(2, "embeddings.position_embedding.weight").f();
-    add("embeddings", [=](cudaStream_t st) { launch_clip_embed(ids, tok, pos, M, T, W, X, st); });
+    const float* extra = e->clip_extra;
+    const int* extra_n = e->clip_extra_n;
+    add("embeddings", [=](cudaStream_t st) { launch_clip_embed(ids, tok, vocab, extra, extra_n, pos, M, T, W, X, st); });
   }
   const float scale = 1.0f / sqrtf((float)d);
   for (int i = 0; i < C.layers; ++i) {

@@ -238,15 +238,17 @@ void launch_repack_conv_weight(const void* src, int src_dtype, int O, int I, int
 void launch_cfg_step(const float* x, const float* den_uncond, const float* den_cond, float cfg, int mode, float c0,
                      float c1, float c2, const float* noise, float* x_out, float* denoised_out, size_t n,
                      cudaStream_t stream);
+// F.interpolate(bilinear, align_corners=False) on fp32 [planes, h, w] -> [planes, oh, ow]
+void launch_resample_bilinear(const float* src, float* dst, int planes, int h, int w, int oh, int ow, cudaStream_t stream);
 // rgb[B,H,W,3] fp32 = clamp((conv3x3(h) + 1) / 2, 0, 1)   (VAE conv_out + VAE.process_output)
 void launch_conv_out_rgb(const bf16* h, const bf16* Wt, const float* bias, int B, int H, int W, int Cin, float* rgb,
                          cudaStream_t stream);
 // y[b,o,p] = sum_c W[o,c] x[b,c,p] + bias[o] on fp32 NCHW (VAE post_quant_conv, 4 -> 4 channels)
 void launch_conv1x1_f32(const float* x, const float* W, const float* bias, int B, int Cin, int Cout, int HW, float* y,
                         cudaStream_t stream);
-// out[r, :] = tok_emb[ids[r], :] + pos_emb[r % T, :]  -> bf16
-void launch_clip_embed(const long long* ids, const float* tok_emb, const float* pos_emb, int rows, int T, int C, bf16* out,
-                       cudaStream_t stream);
+// out[r, :] = (ids[r] < vocab ? tok_emb[ids[r], :] : extra[ids[r] - vocab, :]) + pos_emb[r % T, :]  -> bf16
+void launch_clip_embed(const long long* ids, const float* tok_emb, int vocab, const float* extra, const int* extra_n,
+                       const float* pos_emb, int rows, int T, int C, bf16* out, cudaStream_t stream);
 void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
                          cudaStream_t stream);
 

@@ -18,6 +18,16 @@ void* Arena::alloc(size_t bytes, bool zero) {
   total += bytes;
   return p;
 }
+void Arena::free_block(void* p) {
+  for (size_t i = 0; i < blocks.size(); ++i)
+    if (blocks[i] == p) {
+      cudaFree(p);  // implicit device synchronisation: no kernel can still be reading the tensor
+      total -= sizes[i];
+      blocks.erase(blocks.begin() + i);
+      sizes.erase(sizes.begin() + i);
+      return;
+    }
+}
 void Arena::release() {
   for (void* p : blocks) cudaFree(p);
   blocks.clear();
@@ -168,16 +178,34 @@ int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, 
     for (int k = 0; k < t.ndim; ++k) numel *= (size_t)t.shape[k];
     const bool keep_f32 = t.ndim == 1 || name.find("embedding") != std::string::npos ||
                           name.find("relative_attention_bias") != std::string::npos;  // T5 logit-bias table [32, heads]
+    // Re-loading a name (another checkpoint / LoRA into the same engine) reuses the old allocation when the size is
+    // unchanged and frees it otherwise: nothing accumulates in the weight arena across reloads.
+    void* reuse = nullptr;
+    {
+      auto old = h->w[which].find(name);
+      if (old != h->w[which].end()) {
+        const size_t old_bytes = old->second.numel() * (old->second.is_bf16 ? sizeof(bf16) : sizeof(float));
+        const size_t new_bytes = numel * (keep_f32 ? sizeof(float) : sizeof(bf16));
+        if (old_bytes == new_bytes) {
+          LDN_CUDA(cudaStreamSynchronize(stream));
+          reuse = old->second.p;
+        } else {
+          h->weights_arena.free_block(old->second.p);
+        }
+        h->w[which].erase(old);
+      }
+    }
+    auto walloc = [&](size_t bytes) { return reuse ? reuse : h->weights_arena.alloc(bytes); };
     if (keep_f32) {
       d.is_bf16 = false;
       d.shape.assign(t.shape, t.shape + t.ndim);
-      d.p = h->weights_arena.alloc(numel * sizeof(float));
+      d.p = walloc(numel * sizeof(float));
       launch_convert_to_f32(t.data, t.dtype, numel, d.f(), stream);
     } else if (t.ndim == 4 && t.shape[2] * t.shape[3] > 1) {
       // OIHW -> [O, kh*kw*I], K index = (ky*kw + kx)*I + c  (K-major operand of the implicit GEMM)
       d.is_bf16 = true;
       d.shape = {t.shape[0], t.shape[2] * t.shape[3] * t.shape[1]};
-      d.p = h->weights_arena.alloc(numel * sizeof(bf16));
+      d.p = walloc(numel * sizeof(bf16));
       launch_repack_conv_weight(t.data, t.dtype, (int)t.shape[0], (int)t.shape[1], (int)t.shape[2], (int)t.shape[3],
                                 d.b(), stream);
     } else {
@@ -186,7 +214,7 @@ int ldn_load_weights(ldn_handle h, int which, const ldn_tensor* tensors, int n, 
         d.shape = {t.shape[0], t.shape[1]};
       else
         d.shape.assign(t.shape, t.shape + t.ndim);
-      d.p = h->weights_arena.alloc(numel * sizeof(bf16));
+      d.p = walloc(numel * sizeof(bf16));
       launch_convert_to_bf16(t.data, t.dtype, numel, d.b(), stream);
     }
     h->w[which][name] = d;
@@ -233,6 +261,13 @@ int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond,
   LDN_API_END
 }
 
+int ldn_resample_bilinear(const float* src, float* dst, int planes, int h, int w, int oh, int ow, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(src && dst && planes >= 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "ldn_resample_bilinear: bad argument");
+  launch_resample_bilinear(src, dst, planes, h, w, oh, ow, (cudaStream_t)stream);
+  LDN_API_END
+}
+
 int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, int lat_w, void* stream) {
   LDN_API_BEGIN
   LDN_CHECK(h && z && rgb, "ldn_vae_decode: bad argument");
@@ -269,6 +304,21 @@ int ldn_clip_encode(ldn_handle h, const int64_t* ids, int S, float* out_penultim
   LDN_CHECK(h && ids, "ldn_clip_encode: bad argument");
   if (!h->finalized[2]) clip_finalize(h, (cudaStream_t)stream);
   clip_encode(h, ids, S, out_penultimate, out_last, (cudaStream_t)stream);
+  LDN_API_END
+}
+
+int ldn_clip_set_extra_embeddings(ldn_handle h, const float* vectors, int n, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(h && n >= 0 && (n == 0 || vectors), "ldn_clip_set_extra_embeddings: bad argument");
+  LDN_CHECK(!h->w[2].empty(), "ldn_clip_set_extra_embeddings: CLIP weights not loaded");
+  LDN_CHECK(n <= ldn_engine::kClipExtraCap, "ldn_clip_set_extra_embeddings: more than 256 textual-inversion vectors");
+  if (!h->finalized[2]) clip_finalize(h, (cudaStream_t)stream);
+  const int width = (int)h->W(2, "embeddings.token_embedding.weight").shape[1];
+  if (n > 0)
+    LDN_CUDA(cudaMemcpyAsync(h->clip_extra, vectors, (size_t)n * width * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+  LDN_CUDA(cudaMemcpyAsync(h->clip_extra_n, &n, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  LDN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // `n` lives on this stack frame
   LDN_API_END
 }
 

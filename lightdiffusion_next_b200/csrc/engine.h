@@ -49,6 +49,7 @@ struct Arena {
   std::vector<size_t> sizes;
   size_t total = 0;
   void* alloc(size_t bytes, bool zero = false);
+  void free_block(void* p);  // releases one block (a replaced weight tensor)
   template <typename T>
   T* get(size_t n, bool zero = false) {
     return reinterpret_cast<T*>(alloc(n * sizeof(T), zero));
@@ -66,6 +67,10 @@ struct ldn_engine {
   bool finalized[6] = {false, false, false, false, false, false};
   float* log_sigmas = nullptr;
   int n_sigmas = 0;
+  // textual-inversion rows of the CLIP token table (ids vocab, vocab + 1, ...): fixed capacity, graph-stable addresses
+  static constexpr int kClipExtraCap = 256;
+  float* clip_extra = nullptr;   // [kClipExtraCap, 768] fp32
+  int* clip_extra_n = nullptr;   // device scalar: rows in use
 
   // ---- UNet derived weights / context (unet.cu)
   struct UNetState;

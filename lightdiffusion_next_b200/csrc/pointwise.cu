@@ -587,6 +587,39 @@ void launch_cfg_step(const float* x, const float* den_uncond, const float* den_c
   LDN_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------ bilinear resample (multiscale steps)
+// F.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False) on fp32 NCHW planes, the call the reference makes
+// around its half-resolution sampler steps (src/sample/samplers.py:821-835).  Same arithmetic as ATen's
+// upsample_bilinear2d: source index = (in / out) * (dst + 0.5) - 0.5 clamped at 0, truncated; the second tap is clamped to
+// the last row / column; value = h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d).
+__global__ void resample_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int planes, int h, int w,
+                                         int oh, int ow, float rh, float rw) {
+  const size_t total = (size_t)planes * oh * ow;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % ow);
+    const size_t t = i / ow;
+    const int oy = (int)(t % oh);
+    const size_t pl = t / oh;
+    const float sy = fmaxf(rh * (oy + 0.5f) - 0.5f, 0.f);
+    const float sx = fmaxf(rw * (ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int yp = y0 < h - 1 ? 1 : 0, xp = x0 < w - 1 ? 1 : 0;
+    const float h1 = sy - y0, h0 = 1.f - h1, w1 = sx - x0, w0 = 1.f - w1;
+    const float* s = src + pl * (size_t)h * w + (size_t)y0 * w + x0;
+    dst[i] = h0 * (w0 * s[0] + w1 * s[xp]) + h1 * (w0 * s[(size_t)yp * w] + w1 * s[(size_t)yp * w + xp]);
+  }
+}
+void launch_resample_bilinear(const float* src, float* dst, int planes, int h, int w, int oh, int ow,
+                              cudaStream_t stream) {
+  const size_t total = (size_t)planes * oh * ow;
+  if (total == 0) return;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  resample_bilinear_kernel<<<blocks, 256, 0, stream>>>(src, dst, planes, h, w, oh, ow, (float)h / (float)oh,
+                                                       (float)w / (float)ow);
+  LDN_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ row softmax (VAE mid attention, materialised scores)
 // out[r, :] = softmax(in[r, :] * scale); one block per row.
 __global__ void softmax_rows_kernel(const bf16* __restrict__ in, long long ld_in, bf16* __restrict__ out,
@@ -776,20 +809,30 @@ void launch_conv1x1_f32(const float* x, const float* W, const float* bias, int B
   LDN_CUDA(cudaGetLastError());
 }
 
-__global__ void clip_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
-                                  int rows, int T, int C, bf16* __restrict__ out) {
+// Token ids in [0, vocab) read the checkpoint's table; ids vocab, vocab + 1, ... read the small textual-inversion table
+// (SDClipModel.set_up_textual_embeddings appends them to a temporary Embedding, src/SD15/SDClip.py:247-259). The host
+// validates ids before the call; an id that is still out of range reads the last vocabulary row instead of foreign memory.
+__global__ void clip_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok, int vocab,
+                                  const float* __restrict__ extra, const int* __restrict__ extra_n,
+                                  const float* __restrict__ pos, int rows, int T, int C, bf16* __restrict__ out) {
   const size_t total = (size_t)rows * C;
+  const int n_extra = extra_n ? *extra_n : 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const int r = (int)(i / C);
-    out[i] = __float2bfloat16(tok[(size_t)ids[r] * C + c] + pos[(size_t)(r % T) * C + c]);
+    const long long id = ids[r];
+    const float* src;
+    if (id >= 0 && id < vocab) src = tok + (size_t)id * C;
+    else if (id >= vocab && id - vocab < n_extra) src = extra + (size_t)(id - vocab) * C;
+    else src = tok + (size_t)(vocab - 1) * C;
+    out[i] = __float2bfloat16(src[c] + pos[(size_t)(r % T) * C + c]);
   }
 }
-void launch_clip_embed(const long long* ids, const float* tok_emb, const float* pos_emb, int rows, int T, int C, bf16* out,
-                       cudaStream_t stream) {
+void launch_clip_embed(const long long* ids, const float* tok_emb, int vocab, const float* extra, const int* extra_n,
+                       const float* pos_emb, int rows, int T, int C, bf16* out, cudaStream_t stream) {
   const size_t total = (size_t)rows * C;
   int blocks = (int)((total + 255) / 256);
-  clip_embed_kernel<<<blocks, 256, 0, stream>>>(ids, tok_emb, pos_emb, rows, T, C, out);
+  clip_embed_kernel<<<blocks, 256, 0, stream>>>(ids, tok_emb, vocab, extra, extra_n, pos_emb, rows, T, C, out);
   LDN_CUDA(cudaGetLastError());
 }
 

@@ -3,9 +3,9 @@
 The reference has no multi-GPU path; the sampler trajectory of an image depends only on its own noise
 and conditioning, so images shard across ranks with NO per-step collective.  Collectives used, all outside the loop:
   * broadcast of the weights from rank 0 (once),
-  * scatter of the full-batch initial noise drawn on rank 0 exactly as the reference draws it
-    (one CPU generator over [B,4,h,w], src/sample/ksampler_util.py:287-295) so a sharded run reproduces the
-    single-GPU batch result,
+  * none for the noise: every rank replays the reference's full-batch draw (one seeded CPU generator over [B,4,h,w],
+    src/sample/ksampler_util.py:287-295) and keeps its slice, so a sharded run reproduces the single-GPU batch result
+    (scatter_rows / gather_rows remain for data that only rank 0 holds, e.g. per-image prompts or input images),
   * gather of the final latents (256 KB per 1024^2 image) or decoded images.
 Backend: "nccl" on GPUs (NVLink/NVSwitch), "gloo" in the CPU tests.
 """
@@ -90,8 +90,10 @@ def gather_rows(mine: torch.Tensor, batch: int, dst: int = 0) -> Optional[torch.
 def sample_sharded(engine, seed: int, steps: int, cfg: float, sampler_name: str, scheduler: str, positive: torch.Tensor,
                    negative: torch.Tensor, latent_image: Dict[str, torch.Tensor], **kw):
     """KSampler.sample for a batch sharded over the ranks.  positive/negative: [1 or B, T, 768] on every rank.
-    Returns ({"samples": [B,4,h,w]},) on rank 0 and (None,) elsewhere.  Exact w.r.t. the single-process batch result
-    for dpmpp_2m_cfgpp; for ancestral samplers the per-step device noise is drawn per rank (statistically equivalent)."""
+    Returns ({"samples": [B,4,h,w]},) on rank 0 and (None,) elsewhere.  Reproduces the single-process batch result for
+    every sampler: the initial noise is each rank's slice of the same full-batch draw, and the per-step noise of the ancestral
+    / SDE samplers is drawn on every rank for the WHOLE batch from identically seeded generators and sliced (`batch_slice`),
+    so image i gets the noise it would get as row i of the unsharded batch -- never the same noise as another image."""
     from . import sampling as S
 
     latent = latent_image["samples"]
@@ -99,15 +101,18 @@ def sample_sharded(engine, seed: int, steps: int, cfg: float, sampler_name: str,
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_range(B, rank, world)
-    noise_full = S.prepare_noise(latent, seed) if rank == 0 else None
+    # Every rank replays the reference's prepare_noise (ksampler_util.py:274-295) for the FULL batch: one CPU generator
+    # seeded with `seed` (torch.manual_seed also seeds the CUDA generators).  It costs microseconds, needs no scatter, and
+    # leaves every generator of every rank in exactly the state the single-process batch run has at this point -- which is
+    # what makes the per-step noise below shard-invariant.
+    noise = S.prepare_noise(latent, seed)[lo:hi]
     dev = engine.device
-    noise = scatter_rows(noise_full, tuple(latent.shape[1:]), B, dev)
     out = None
     if hi > lo:
         pos = positive if positive.shape[0] == 1 else positive[lo:hi]
         neg = negative if negative.shape[0] == 1 else negative[lo:hi]
         res = S.sample(engine, seed, steps, cfg, sampler_name, scheduler, pos, neg, {"samples": latent[lo:hi]},
-                       noise=noise.cpu(), **kw)
+                       noise=noise, batch_slice=(lo, hi, B), **kw)
         out = res[0]["samples"].to(dev)
     else:
         out = torch.empty((0,) + tuple(latent.shape[1:]), device=dev)

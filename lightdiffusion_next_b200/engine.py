@@ -38,6 +38,8 @@ class Engine:
                                         C.cast(lsig.data_ptr(), C.POINTER(C.c_float)), sig.numel()))
         self._ctx_key = None
         self._keep = []
+        self.weights_epoch: Dict[int, int] = {}
+        self.context_uploads = 0  # ldn_set_context calls (each: pad + 32 K/V projections)
 
     def close(self) -> None:
         if getattr(self, "h", None):
@@ -74,6 +76,7 @@ class Engine:
                 L.check(self.lib.ldn_load_weights(self.h, which, arr, len(part), stream))
                 del keep
         self._ctx_key = None
+        self.weights_epoch[which] = self.weights_epoch.get(which, 0) + 1  # a UNet reload drops the uploaded context
 
     def load_unet(self, state_dict: Dict[str, torch.Tensor]) -> None:
         self.load_weights(UNET, state_dict)
@@ -83,8 +86,9 @@ class Engine:
 
     def load_clip(self, state_dict: Dict[str, torch.Tensor]) -> None:
         self.load_weights(CLIP, state_dict)
-        self._clip_tok = state_dict.get("embeddings.token_embedding.weight")  # kept for textual-inversion rows
+        self._clip_tok = state_dict.get("embeddings.token_embedding.weight")  # dtype / vocabulary size of the table
         self._clip_ti_key = None
+        self._clip_extra_n = 0
 
     def clip_vocab(self) -> int:
         tok = getattr(self, "_clip_tok", None)
@@ -93,17 +97,20 @@ class Engine:
         return int(tok.shape[0])
 
     def set_clip_extra_embeddings(self, vectors) -> None:
-        """Textual-inversion vectors become rows vocab, vocab + 1, ... of the token-embedding table (what the reference's
-        set_up_textual_embeddings does with a temporary Embedding, src/SD15/SDClip.py:247-259).  The extended table replaces
-        the loaded one (the original rows are unchanged, so plain prompts keep working) and is re-uploaded only when the
-        set of vectors changes."""
-        from .pipeline import extend_token_table
-
+        """Textual-inversion vectors become token ids vocab, vocab + 1, ... (what the reference's
+        set_up_textual_embeddings does with a temporary Embedding, src/SD15/SDClip.py:247-259).  They go into a small
+        separate device table (ldn_clip_set_extra_embeddings): the checkpoint's 150 MB token table is neither re-uploaded
+        nor replaced, and no program is rebuilt.  The vectors are rounded to the table's dtype exactly as there."""
         self.clip_vocab()
-        key = hash(torch.stack([v.detach().float().cpu() for v in vectors]).numpy().tobytes())
+        vec = torch.stack([v.detach().cpu() for v in vectors]).to(self._clip_tok.dtype).float().contiguous() \
+            if len(vectors) else torch.zeros(0, self._clip_tok.shape[1])
+        key = hash(vec.numpy().tobytes())
         if key != self._clip_ti_key:
-            self.load_weights(CLIP, {"embeddings.token_embedding.weight": extend_token_table(self._clip_tok, vectors)})
+            dv = vec.to(self.device)
+            with torch.cuda.device(self.device):
+                L.check(self.lib.ldn_clip_set_extra_embeddings(self.h, dv.data_ptr(), int(vec.shape[0]), L.cur_stream()))
             self._clip_ti_key = key
+            self._clip_extra_n = int(vec.shape[0])
 
     def load_taesd(self, state_dict: Dict[str, torch.Tensor]) -> None:
         """TAESD preview decoder weights (keys of `taesd_decoder.safetensors`: nn.Sequential indices, taesd.py:104-136)."""
@@ -142,6 +149,7 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(self.lib.ldn_set_context(self.h, ctx.data_ptr(), rows, tokens, L.cur_stream()))
         self._keep = [ctx]
+        self.context_uploads += 1
 
     def denoise(self, x: torch.Tensor, sigma: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x [rows,4,h,w] fp32, sigma [rows] fp32 -> denoised = x - eps*sigma (BaseModel.apply_model semantics)."""
@@ -162,6 +170,19 @@ class Engine:
             L.check(self.lib.ldn_cfg_step(L.ptr(x), den_uncond.data_ptr(), den_cond.data_ptr(), float(cfg), mode,
                                           float(c0), float(c1), float(c2), L.ptr(noise), L.ptr(x_out),
                                           L.ptr(denoised_out), n, L.cur_stream()))
+
+    def resample_bilinear(self, x: torch.Tensor, size, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """F.interpolate(x, size=size, mode="bilinear", align_corners=False) on fp32 NCHW (the resampling around the
+        reference's half-resolution sampler steps, samplers.py:821-835), as one launch of the engine's own kernel."""
+        assert x.is_cuda and x.dtype == torch.float32
+        x = x.contiguous()
+        B, Cc, h, w = x.shape
+        oh, ow = int(size[0]), int(size[1])
+        if out is None:
+            out = torch.empty(B, Cc, oh, ow, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_resample_bilinear(x.data_ptr(), out.data_ptr(), B * Cc, h, w, oh, ow, L.cur_stream()))
+        return out
 
     # ------------------------------------------------------------------ VAE / CLIP
     def vae_decode(self, z: torch.Tensor) -> torch.Tensor:
@@ -233,6 +254,10 @@ class Engine:
 
     def clip_encode(self, ids: torch.Tensor):
         """ids [S,77] int64 -> (penultimate-layer output after final LN, last-layer output after final LN)."""
+        if not ids.is_cuda:  # token ids come from the host tokenizer: range-check them before they index device memory
+            hi = self.clip_vocab() + getattr(self, "_clip_extra_n", 0)
+            if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= hi):
+                raise L.LdnError(f"CLIP token id outside [0, {hi}) (vocabulary + loaded textual-inversion vectors)")
         ids = ids.to(self.device, torch.int64).contiguous()
         S = ids.shape[0]
         pen = torch.empty(S, 77, 768, device=self.device, dtype=torch.float32)

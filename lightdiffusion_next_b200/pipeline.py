@@ -64,8 +64,7 @@ class Pipeline:
         first end-of-text token (CLIPTextModel_.forward, src/clip/CLIPTextModel.py:95-105; the `y` input of Flux)."""
         if any(isinstance(t, torch.Tensor) for row in tokens for t, _ in row):
             ids, wts, extra = resolve_textual_embeddings(tokens, self.e.clip_vocab())
-            if extra:
-                self.e.set_clip_extra_embeddings(extra)
+            self.e.set_clip_extra_embeddings(extra)
         else:
             ids = torch.tensor([[t for t, _ in row] for row in tokens], dtype=torch.int64)
             wts = torch.tensor([[w for _, w in row] for row in tokens], dtype=torch.float32)
@@ -87,10 +86,11 @@ class Pipeline:
     # ---------------------------------------------------------------- KSampler (src/sample/sampling.py:773-887)
     def sample(self, positive: torch.Tensor, negative: torch.Tensor, width: int, height: int, batch: int = 1,
                seed: int = 0, steps: int = 20, cfg: float = 7.0, sampler_name: str = "dpmpp_2m_cfgpp",
-               scheduler: str = "karras", enable_multiscale: bool = True) -> torch.Tensor:
+               scheduler: str = "karras", enable_multiscale: bool = True,
+               sampler_options: Optional[Dict[str, object]] = None) -> torch.Tensor:
         latent = {"samples": torch.zeros(batch, 4, height // 8, width // 8)}  # EmptyLatentImage (Latent.py:174-190)
         return S.sample(self.e, seed, steps, cfg, sampler_name, scheduler, positive, negative, latent,
-                        enable_multiscale=enable_multiscale)[0]["samples"]
+                        enable_multiscale=enable_multiscale, sampler_options=sampler_options)[0]["samples"]
 
     # ---------------------------------------------------------------- VAEDecode (VariationalAE.py:771-784)
     def decode(self, samples: torch.Tensor) -> torch.Tensor:
@@ -133,6 +133,87 @@ def hires_fix(pipe: "Pipeline", samples: torch.Tensor, positive: torch.Tensor, n
 
     up = latent_upscale({"samples": samples}, width * 2, height * 2)
     return S.sample(pipe.e, seed, steps, cfg, sampler_name, scheduler, positive, negative, up, denoise=denoise)[0]["samples"]
+
+
+_hires_fix_pass = hires_fix  # pipeline() below has a flag of the same name
+
+
+# the reference's default negative prompt (src/user/pipeline.py:98); its four "embedding:" terms are textual-inversion
+# files the tokenizer resolves from its embedding directory (absent files are skipped with a warning, SDToken.py:335-352)
+DEFAULT_NEGATIVE_PROMPT = ("(worst quality, low quality:1.4), (zombie, sketch, interlocked fingers, comic), "
+                           "(embedding:EasyNegative), (embedding:badhandv4), (embedding:lr), (embedding:ng_deepnegative_v1_75t)")
+last_seed = 0  # module state like the reference's `last_seed` (pipeline.py:22, 102-107)
+
+
+def _token_rows(tokenizer, text: str):
+    """SD1Tokenizer.tokenize_with_weights returns {"l": rows}, SDTokenizer returns the rows (SDToken.py:292-396, 425-440)."""
+    t = tokenizer.tokenize_with_weights(text)
+    return t["l"] if isinstance(t, dict) else t
+
+
+def pipeline(engine: Engine, prompt: str, w: int, h: int, number: int = 1, batch: int = 1, hires_fix: bool = False,
+             adetailer: bool = False, enhance_prompt: bool = False, img2img: bool = False, stable_fast: bool = False,
+             reuse_seed: bool = False, flux_enabled: bool = False, prio_speed: bool = False, autohdr: bool = False,
+             realistic_model: bool = False, negative_prompt: Optional[str] = None, multiscale_preset: Optional[str] = None,
+             enable_multiscale: bool = True, multiscale_factor: float = 0.5, multiscale_fullres_start: int = 3,
+             multiscale_fullres_end: int = 8, multiscale_intermittent_fullres: bool = False, *, tokenizer=None,
+             seed: Optional[int] = None, hires_seed: Optional[int] = None) -> List[torch.Tensor]:
+    """`pipeline(prompt, w, h, number, batch, ...)` of the reference (src/user/pipeline.py:31-518), SD1.5 txt2img branch
+    (:278-372), on an engine that already holds the UNet / VAE / CLIP weights (checkpoint + LoRA loading is
+    `Engine.load_checkpoint`): CLIPSetLastLayer(-2) + CLIPTextEncode of prompt and negative prompt -> EmptyLatentImage ->
+    KSampler(20 steps, cfg 7, dpmpp_sde_cfgpp -- dpmpp_2m_cfgpp with prio_speed --, karras, the caller's multiscale options)
+    -> [HiresFix: LatentUpscale x2 + KSampler(10 steps, cfg 8, euler_ancestral_cfgpp, normal, denoise 0.45)] -> VAEDecode.
+
+    Same positional / keyword arguments as the reference.  Differences, all at the edges of the hot path: the images are
+    RETURNED (a list of `number` tensors [batch, H, W, 3] in [0, 1]) instead of being written as PNGs; `tokenizer` is the
+    reference's tokenizer object (SD1Tokenizer / SDTokenizer: host Python + vocabulary files, out of scope) or anything with
+    its `tokenize_with_weights(text)`; `seed` pins the seed the reference draws at random (`reuse_seed` works as there).
+    The flags for subsystems outside SURVEY.md 8 raise instead of being ignored: adetailer, enhance_prompt, autohdr,
+    img2img-from-a-path (use Pipeline.img2img with pixels), flux_enabled (use FluxPipeline).  `stable_fast` and
+    `realistic_model` are accepted and inert: the engine replaces the former, the latter picks a checkpoint file.
+    As in the reference, `enable_multiscale` & co. only reach dpmpp_sde_cfgpp; dpmpp_2m_cfgpp runs its own defaults (fact 9)."""
+    import random
+
+    global last_seed
+    for flag, name in ((adetailer, "adetailer"), (enhance_prompt, "enhance_prompt"), (autohdr, "autohdr"),
+                       (img2img, "img2img"), (flux_enabled, "flux_enabled")):
+        if flag:
+            raise NotImplementedError(f"pipeline({name}=True) is outside the sampler hot path this engine replaces")
+    if tokenizer is None:
+        raise ValueError("pipeline() needs tokenizer= (the reference's SD1Tokenizer, src/SD15/SDToken.py:399-440)")
+    if multiscale_preset is not None:
+        enable_multiscale, multiscale_factor, multiscale_fullres_start, multiscale_fullres_end, \
+            multiscale_intermittent_fullres = MULTISCALE_PRESETS[multiscale_preset]
+    if negative_prompt is None or negative_prompt.strip() == "":
+        negative_prompt = DEFAULT_NEGATIVE_PROMPT
+    if reuse_seed:
+        seed = last_seed
+    elif seed is None:
+        seed = random.randint(1, 2 ** 64)
+    last_seed = seed
+    sampler_name = "dpmpp_sde_cfgpp" if not prio_speed else "dpmpp_2m_cfgpp"
+    pipe = Pipeline(engine)
+    images = []
+    for _ in range(number):
+        pos = pipe.encode(_token_rows(tokenizer, prompt))
+        neg = pipe.encode(_token_rows(tokenizer, negative_prompt))
+        opts = None
+        if sampler_name == "dpmpp_sde_cfgpp":  # the only sampler sample1 forwards these to (sampling.py:949-964)
+            opts = {"multiscale_factor": multiscale_factor, "multiscale_fullres_start": multiscale_fullres_start,
+                    "multiscale_fullres_end": multiscale_fullres_end,
+                    "multiscale_intermittent_fullres": multiscale_intermittent_fullres}
+        lat = pipe.sample(pos, neg, w, h, batch, seed, 20, 7.0, sampler_name, "karras", enable_multiscale=enable_multiscale,
+                          sampler_options=opts)
+        if hires_fix:
+            hs = hires_seed if hires_seed is not None else random.randint(1, 2 ** 64)
+            lat = _hires_fix_pass(pipe, lat, pos, neg, w, h, seed=hs)
+        images.append(pipe.decode(lat))
+    return images
+
+
+# src/sample/multiscale_presets.py:49-86: (enable, factor, fullres_start, fullres_end, intermittent)
+MULTISCALE_PRESETS = {"quality": (True, 0.5, 10, 8, True), "performance": (True, 0.25, 5, 8, True),
+                      "balanced": (True, 0.5, 5, 8, True), "disabled": (False, 1.0, 0, 0, False)}
 
 
 class FluxPipeline:

@@ -15,13 +15,21 @@ from __future__ import annotations
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
-import torch.nn.functional as F
 
 from .engine import Engine
 from .schedule import calculate_sigmas, get_ancestral_step, max_denoise
 
 LATENT_SCALE = 0.18215  # src/Utilities/Latent.py:41-62
 SAMPLERS = ("dpmpp_2m_cfgpp", "euler_ancestral_cfgpp", "dpmpp_sde_cfgpp", "euler_cfgpp")
+_MS = {"enable_multiscale", "multiscale_factor", "multiscale_fullres_start", "multiscale_fullres_end",
+       "multiscale_intermittent_fullres"}
+# keyword arguments of the reference's sampler functions that this engine honours (samplers.py:755-773, 612-631, 966-989,
+# 470-489); everything else is rejected loudly rather than silently dropped
+SAMPLER_OPTIONS = {"dpmpp_2m_cfgpp": set(_MS), "dpmpp_sde_cfgpp": _MS | {"noise_sampler", "eta", "r", "s_noise"},
+                   "euler_ancestral_cfgpp": {"noise_sampler", "eta", "s_noise"}, "euler_cfgpp": {"cfg_scale", "cfg_min"}}
+# what KSampler.sample -> common_ksampler -> sample1 always passes for dpmpp_sde_cfgpp (sampling.py:795-799, 949-964)
+KSAMPLER_SDE_MULTISCALE = {"multiscale_factor": 0.5, "multiscale_fullres_start": 3, "multiscale_fullres_end": 8,
+                           "multiscale_intermittent_fullres": False}
 
 
 def prepare_noise(latent: torch.Tensor, seed: int) -> torch.Tensor:
@@ -94,27 +102,45 @@ def sample_dpmpp_2m_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor,
                             denoised_out=den)
             x, full.x_next = full.x_next, x
         else:
-            xp = F.interpolate(x, size=(sh, sw), mode="bilinear", align_corners=False)
+            # half-resolution step (samplers.py:821-835, 905-930): bilinear down, denoise, bilinear up, same update
+            xp = engine.resample_bilinear(x, (sh, sw))
             du, dc = low.denoise_pair(xp, float(sig[i]))
             d_low = torch.empty_like(xp)
             engine.cfg_step(None, du, dc, cfg, 2, denoised_out=d_low)
-            den = F.interpolate(d_low, size=(oh, ow), mode="bilinear", align_corners=False)
-            x = float(ratios[i]) * x - float(hexp[i]) * den
+            den = engine.resample_bilinear(d_low, (oh, ow), out=den)
+            engine.cfg_step(x, den, den, 1.0, 0, c0=float(ratios[i]), c1=float(hexp[i]), x_out=full.x_next)
+            x, full.x_next = full.x_next, x
         if callback is not None:
             callback({"x": x, "i": i, "sigma": sig[i], "denoised": den})
     return x
+
+
+def default_noise_sampler(x: torch.Tensor, batch_slice: Optional[Tuple[int, int, int]] = None) -> Callable:
+    """sampling_util.default_noise_sampler (src/sample/sampling_util.py:154-165): torch.randn_like(x) from the device's
+    global generator (seeded by prepare_noise's torch.manual_seed, as in the reference).  batch_slice = (lo, hi, total):
+    this process holds images [lo, hi) of a batch of `total` -- the draw is made for the WHOLE batch and sliced, so that
+    every rank of a sharded run consumes the generator exactly like the single-process batch does (each rank must have
+    been seeded alike: distributed.sample_sharded calls torch.manual_seed(seed) on every rank)."""
+    if batch_slice is None:
+        return lambda sigma, sigma_next: torch.randn_like(x)
+    lo, hi, total = batch_slice
+    shape = (total,) + tuple(x.shape[1:])
+    return lambda sigma, sigma_next: torch.randn(shape, dtype=x.dtype, device=x.device)[lo:hi]
 
 
 def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor, cfg: float,
                                  noise_sampler: Optional[Callable] = None,
                                  callback: Optional[Callable] = None,
                                  interrupt: Optional[Callable[[], bool]] = None, eta: float = 1.0,
-                                 s_noise: float = 1.0) -> torch.Tensor:
+                                 s_noise: float = 1.0,
+                                 batch_slice: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
     """d = (x - D)/sigma; x += d (sigma_down - sigma); x += noise * s_noise * sigma_up, (sigma_down, sigma_up) =
     get_ancestral_step(sigma_i, sigma_{i+1}, eta)   (sample_euler_ancestral_dy_cfg_pp as executed, samplers.py:612-740)."""
     B = x.shape[0]
     sig = sigmas.float().cpu()
     n = len(sig) - 1
+    if noise_sampler is None:
+        noise_sampler = default_noise_sampler(x, batch_slice)
     loop = SamplerLoop(engine, B, x.shape[2], x.shape[3])
     den = torch.empty_like(x)
     for i in range(n):
@@ -125,7 +151,7 @@ def sample_euler_ancestral_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.
         noise = None
         if sig[i + 1] > 0:
             # the reference's convention (samplers.py:633-636, 732): noise_sampler(sigma, sigma_next) -> noise like x
-            noise = noise_sampler(sig[i], sig[i + 1]).to(x.device) if noise_sampler is not None else torch.randn_like(x)
+            noise = noise_sampler(sig[i], sig[i + 1]).to(x.device, torch.float32).contiguous()
         engine.cfg_step(x, du, dc, cfg, 1, c0=float(sd - sig[i]), c1=float(su) * s_noise, c2=float(sig[i]), noise=noise,
                         x_out=loop.x_next, denoised_out=den)
         x, loop.x_next = loop.x_next, x
@@ -185,14 +211,18 @@ class BrownianIntervalNoise:
     device; statistically equivalent to the reference's CPU Brownian tree, not sample-identical (inject `noise_sampler`
     for that)."""
 
-    def __init__(self, x: torch.Tensor, seed: Optional[int] = None):
-        self.shape, self.device = x.shape, x.device
+    def __init__(self, x: torch.Tensor, seed: Optional[int] = None, batch_slice: Optional[Tuple[int, int, int]] = None):
+        """batch_slice = (lo, hi, total): x holds images [lo, hi) of a batch of `total`; every draw is made for the whole
+        batch from the same seeded generator and sliced, so the shards of a multi-GPU run get DIFFERENT, and the same,
+        noise as the rows of the single-process batch (one path per image)."""
+        self.lo, self.hi, total = batch_slice if batch_slice is not None else (0, x.shape[0], x.shape[0])
+        self.shape, self.device = (total,) + tuple(x.shape[1:]), x.device
         self.gen = torch.Generator(device=x.device)
         self.gen.manual_seed(0 if seed is None else int(seed))
         self._left = None   # (sigma_hi, sigma_mid, increment over [mid, hi])
 
     def _draw(self, var: float) -> torch.Tensor:
-        return torch.randn(self.shape, generator=self.gen, device=self.device) * (var ** 0.5)
+        return torch.randn(self.shape, generator=self.gen, device=self.device)[self.lo:self.hi] * (var ** 0.5)
 
     def __call__(self, sigma, sigma_next) -> torch.Tensor:
         hi, lo = float(sigma), float(sigma_next)
@@ -211,10 +241,12 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
                            callback: Optional[Callable] = None,
                            interrupt: Optional[Callable[[], bool]] = None, s_noise: float = 1.0,
                            multiscale_fullres_start: int = 5, multiscale_fullres_end: int = 8,
-                           multiscale_intermittent_fullres: bool = False) -> torch.Tensor:
+                           multiscale_intermittent_fullres: bool = False,
+                           batch_slice: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
     """DPM-Solver++ (SDE) as the reference executes it (samplers.py:966-1254): two CFG-batched UNet evaluations per
     step (at sigma_i and at the midpoint in log-sigma), ancestral noise from `noise_sampler(sigma, sigma_next)`.  The
-    keyword defaults are the reference sampler's own (:973-989: multiscale margins 5 / 8, no intermittent full-res steps)."""
+    multiscale margins default to the reference sampler's own (:973-989: 5 / 8, no intermittent full-res steps); note that
+    KSampler.sample always overrides them for this sampler (3 / 8) -- `sample()` below does the same."""
     B, _, oh, ow = x.shape
     sh = int(max(8, ((oh * multiscale_factor) // 8) * 8)) if enable_multiscale else oh
     sw = int(max(8, ((ow * multiscale_factor) // 8) * 8)) if enable_multiscale else ow
@@ -222,7 +254,7 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
     sig = sigmas.float().cpu()
     n = len(sig) - 1
     if noise_sampler is None:
-        noise_sampler = BrownianIntervalNoise(x, seed)
+        noise_sampler = BrownianIntervalNoise(x, seed, batch_slice)
     full = SamplerLoop(engine, B, oh, ow)
     low = SamplerLoop(engine, B, sh, sw) if active else None
     sigma_fn = lambda t: t.neg().exp()
@@ -230,11 +262,11 @@ def sample_dpmpp_sde_cfgpp(engine: Engine, x: torch.Tensor, sigmas: torch.Tensor
 
     def denoised_at(xx: torch.Tensor, sigma: float, fullres: bool) -> torch.Tensor:
         loop = full if fullres else low
-        xin = xx if fullres else F.interpolate(xx, size=(sh, sw), mode="bilinear", align_corners=False)
+        xin = xx if fullres else engine.resample_bilinear(xx, (sh, sw))
         du, dc = loop.denoise_pair(xin, sigma)
         d = torch.empty_like(xin)
         engine.cfg_step(None, du, dc, cfg, 2, denoised_out=d)
-        return d if fullres else F.interpolate(d, size=(oh, ow), mode="bilinear", align_corners=False)
+        return d if fullres else engine.resample_bilinear(d, (oh, ow))
 
     for i in range(n):
         if interrupt is not None and interrupt():
@@ -280,10 +312,13 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
            denoise: float = 1.0, enable_multiscale: bool = True, noise: Optional[torch.Tensor] = None,
            callback: Optional[Callable] = None, noise_sampler: Optional[Callable] = None,
            sampler_options: Optional[Dict[str, object]] = None,
-           interrupt: Optional[Callable[[], bool]] = None) -> Tuple[Dict[str, torch.Tensor]]:
+           interrupt: Optional[Callable[[], bool]] = None,
+           batch_slice: Optional[Tuple[int, int, int]] = None) -> Tuple[Dict[str, torch.Tensor]]:
     """Drop-in for KSampler.sample on the measured path. positive / negative: [1 or B, 77k, 768] conditioning tensors.
-    sampler_options: the `extra_options` of the reference's `ksampler(name, extra_options)` seam (sampling.py:500-534) for
-    dpmpp_2m_cfgpp: multiscale_factor / multiscale_fullres_start / multiscale_fullres_end / multiscale_intermittent_fullres.
+    sampler_options: the `extra_options` of the reference's `ksampler(name, extra_options)` seam (sampling.py:500-534),
+    i.e. keyword arguments of the sampler function (SAMPLER_OPTIONS lists what each sampler takes; anything else raises).
+    batch_slice = (lo, hi, total): this call samples images [lo, hi) of a batch of `total` (multi-GPU sharding) -- the
+    default per-step noise of the ancestral / SDE samplers is then drawn for the whole batch and sliced.
     interrupt: polled before every step like the reference polls app.interrupt_flag (samplers.py:884-889); when it returns
     True the loop stops and the current latent is returned.
     Returns ({"samples": latents / 0.18215 on the CPU},) like the reference node."""
@@ -308,20 +343,29 @@ def sample(engine: Engine, seed: int, steps: int, cfg: float, sampler_name: str,
         x = noise * sigmas[0]
     x = (x + lat).to(dev, torch.float32).contiguous()
     set_contexts(engine, positive, negative, B)
+    opts = dict(sampler_options or {})
+    unknown = set(opts) - SAMPLER_OPTIONS[sampler_name]
+    if unknown:
+        raise ValueError(f"unknown {sampler_name} options {sorted(unknown)} (accepted: {sorted(SAMPLER_OPTIONS[sampler_name])})")
     if sampler_name == "dpmpp_2m_cfgpp":
-        opts = dict(sampler_options or {})
-        unknown = set(opts) - {"multiscale_factor", "multiscale_fullres_start", "multiscale_fullres_end", "multiscale_intermittent_fullres"}
-        if unknown:
-            raise ValueError(f"unknown dpmpp_2m_cfgpp options {sorted(unknown)}")
-        x = sample_dpmpp_2m_cfgpp(engine, x, sigmas, cfg, enable_multiscale=enable_multiscale, callback=callback,
-                                  interrupt=interrupt, **opts)
+        # sample1's multiscale_supported_samplers lists "sample_dpmpp_2m_cfgpp", which never matches this name, so the
+        # reference runs this sampler with the sampler function's OWN defaults (5 / 8 / intermittent)
+        opts.setdefault("enable_multiscale", enable_multiscale)
+        x = sample_dpmpp_2m_cfgpp(engine, x, sigmas, cfg, callback=callback, interrupt=interrupt, **opts)
     elif sampler_name == "dpmpp_sde_cfgpp":
-        x = sample_dpmpp_sde_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, seed=seed,
-                                   enable_multiscale=enable_multiscale, callback=callback, interrupt=interrupt)
+        # ... whereas "dpmpp_sde_cfgpp" IS in that list: KSampler.sample / common_ksampler / sample1 always hand it
+        # extra_options with their own defaults (sampling.py:795-799, 949-964)
+        for k, v in KSAMPLER_SDE_MULTISCALE.items():
+            opts.setdefault(k, v)
+        opts.setdefault("enable_multiscale", enable_multiscale)
+        opts.setdefault("noise_sampler", noise_sampler)
+        x = sample_dpmpp_sde_cfgpp(engine, x, sigmas, cfg, seed=seed, callback=callback, interrupt=interrupt,
+                                   batch_slice=batch_slice, **opts)
     elif sampler_name == "euler_cfgpp":
-        x = sample_euler_cfgpp(engine, x, sigmas, cfg, callback=callback, interrupt=interrupt)
+        x = sample_euler_cfgpp(engine, x, sigmas, cfg, callback=callback, interrupt=interrupt, **opts)
     else:
-        x = sample_euler_ancestral_cfgpp(engine, x, sigmas, cfg, noise_sampler=noise_sampler, callback=callback,
-                                         interrupt=interrupt)
+        opts.setdefault("noise_sampler", noise_sampler)
+        x = sample_euler_ancestral_cfgpp(engine, x, sigmas, cfg, callback=callback, interrupt=interrupt,
+                                         batch_slice=batch_slice, **opts)
     out = (x / LATENT_SCALE).to(torch.float32).cpu()
     return ({"samples": out},)

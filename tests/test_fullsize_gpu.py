@@ -5,7 +5,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-EPS_TOL = 2.5e-2  # bf16 engine vs fp32 reference, per forward (the reference's own bf16 path is at 1.06e-2)
+EPS_TOL = 1.5e-2  # bf16 engine vs fp32 reference, per forward (the reference's own bf16 path is at 1.06e-2)
 
 
 def rel(a, b):

@@ -117,8 +117,10 @@ g = torch.Generator().manual_seed(1234)
 pos = torch.randn(1, 77, 768, generator=g); neg = torch.randn(1, 77, 768, generator=g)
 B = 3  # ragged over 2 ranks
 res = D.sample_sharded(eng, 42, 2, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, {{"samples": torch.zeros(B, 4, 16, 16)}})
+# ancestral sampler: the per-step noise must be the unsharded batch's rows, not the same draw on every rank
+anc = D.sample_sharded(eng, 42, 2, 7.0, "euler_ancestral_cfgpp", "karras", pos, neg, {{"samples": torch.zeros(B, 4, 8, 8)}})
 if rank == 0:
-    torch.save(res[0]["samples"], {out!r})
+    torch.save({{"dpmpp_2m": res[0]["samples"], "euler_a": anc[0]["samples"]}}, {out!r})
 dist.barrier(); dist.destroy_process_group()
 """
 
@@ -142,8 +144,12 @@ def test_two_rank_gloo_sharded_sampling_equals_single_process(tmp_path, unet_sd)
     neg = torch.randn(1, 77, 768, generator=g)
     single = S.sample(FakeEngine(unet_sd), 42, 2, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg,
                       {"samples": torch.zeros(3, 4, 16, 16)})[0]["samples"]
-    assert sharded.shape == single.shape
-    assert rel(sharded, single) < 1e-5
+    assert sharded["dpmpp_2m"].shape == single.shape
+    assert rel(sharded["dpmpp_2m"], single) < 1e-5
+    single_a = S.sample(FakeEngine(unet_sd), 42, 2, 7.0, "euler_ancestral_cfgpp", "karras", pos, neg,
+                        {"samples": torch.zeros(3, 4, 8, 8)})[0]["samples"]
+    assert rel(sharded["euler_a"], single_a) < 1e-5   # exact noise rows: shard-invariant per-step draws
+    assert rel(single_a[0], single_a[1]) > 0.5        # ... and different images get different noise
 
 
 def test_synth_shape_tables_match_oracle():
