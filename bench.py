@@ -9,8 +9,15 @@
 (no checkpoints exist offline).  N > 1: one process per GPU (torchrun), each rank owns its own image(s) for the whole
 trajectory, no data-path collective (weak scaling); value = all ranks' iterations / max-over-ranks device time.
 
---impl reference: the CPU arm.  The reference is Python and cannot travel to the GPU box, so this times the oracle port
-(oracle/sd15_oracle.py, pinned against the reference's own outputs) on the host cores, on a bounded sample.
+Beside the contract keys the line carries (N = 1) `secondary`: whole KSampler runs, pipe() end to end, BASELINE config 3
+(bs = 32) and config 5 (HiresFix 512 -> 2048 + VAE decode), the REAL reference timed on this GPU through its own stock path
+(`gpu_reference`: the comparator north_star names) and the reference's loop driven through the engine seam (`seam`); and
+(N > 1) `sharded`: config 3 and config 5 through distributed.sample_sharded on NCCL with an in-run check that the gathered
+latents equal what one process computes for the same images.
+
+--impl reference: the CPU arm.  The unmodified reference (snapshotted into baseline/_ref by build(), see
+baseline/run_reference.py) runs the same workload through its own sampling stack on all host cores; if the snapshot is
+absent the oracle port (oracle/sd15_oracle.py, pinned against the reference's own outputs) is timed instead.
 """
 from __future__ import annotations
 
@@ -27,6 +34,29 @@ sys.path.insert(0, ROOT)
 
 UNET_TFLOP_1024 = 9.348  # per CFG step bs=1 (B=2), BASELINE.md §2 (measured on the reference module)
 UNET_TFLOP_512 = 1.607
+
+
+def workload_string(size: int, bs: int) -> str:
+    """One string for both arms (the driver compares them)."""
+    return (f"SD1.5 txt2img {size}x{size} dpmpp_2m_cfgpp bs={bs}/GPU (CFG pair, UNet batch {2 * bs}), "
+            "multiscale off (every step full resolution)")
+
+
+def run_reference_script(extra, timeout):
+    """baseline/run_reference.py in a child process (its own CUDA context / torch flags); returns its JSON line or an
+    {"unavailable": why} dict.  Never raises: a comparator that cannot run must not take the engine's line down."""
+    script = os.path.join(ROOT, "baseline", "run_reference.py")
+    try:
+        r = subprocess.run([sys.executable, script] + list(extra), capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"timed out after {timeout} s"}
+    for ln in reversed(r.stdout.splitlines()):
+        if ln.startswith("{"):
+            try:
+                return json.loads(ln)
+            except Exception:
+                break
+    return {"unavailable": ("rc %d: " % r.returncode) + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")}
 
 
 def load_peaks():
@@ -126,22 +156,33 @@ def cpu_oracle_step_time(lat: int, max_seconds: float, max_steps: int, warmup: i
 
 
 def run_reference_arm(args):
-    """CPU arm (see module docstring). Rank 0 only."""
+    """CPU arm (see module docstring). Rank 0 only; other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    lat = args.size // 8
-    n, dt, done_w, threads = cpu_oracle_step_time(lat, max_seconds=150.0, max_steps=max(1, args.steps), warmup=args.warmup)
-    v = n / dt
-    sample = (f"{n} timed + {done_w} warm-up full {args.size}x{args.size} CFG steps (2-row UNet fwd + CFG + dpmpp_2m update) "
-              f"of the oracle port (torch fp32 CPU), capped at 150 s wall")
+    K, W = max(1, args.steps), min(1, max(0, args.warmup))
+    ref = run_reference_script(["--device", "cpu", "--size", str(args.size), "--steps", str(K), "--warmup", str(W),
+                                "--bs", str(args.bs)], timeout=1500)
+    if "unavailable" not in ref:
+        v, n, dt, done_w, threads, kind = ref["it_per_s"], ref["steps"], ref["seconds"], ref["warmup"], ref["threads"], "reference"
+        sample = (f"{n} timed + {done_w} warm-up full {args.size}x{args.size} sampler steps of the UNMODIFIED reference "
+                  f"(baseline/_ref: sampling.ksampler('dpmpp_2m_cfgpp', enable_multiscale=False) + sampling.sample on the CPU, "
+                  f"weights {ref['unet_dtype']} cast per call to {ref['manual_cast']}, {ref['attention']}, torch {ref['torch']})")
+        dtype = "f32"
+    else:
+        lat = args.size // 8
+        n, dt, done_w, threads = cpu_oracle_step_time(lat, max_seconds=150.0, max_steps=K, warmup=W)
+        v, kind = n / dt, "port"
+        sample = (f"{n} timed + {done_w} warm-up full {args.size}x{args.size} CFG steps (2-row UNet fwd + CFG + dpmpp_2m update) "
+                  f"of the oracle port (torch fp32 CPU), capped at 150 s wall; reference snapshot unavailable: {ref['unavailable']}")
+        dtype = "f32"
     line = {
         "impl": "reference", "metric": "it/s (UNet sampler steps/sec)", "value": v, "unit": "it/s", "n_gpus": args.gpus,
         "steps": n, "warmup": done_w, "ms_per_step": 1000.0 * dt / n, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"SD1.5 txt2img {args.size}x{args.size} dpmpp_2m_cfgpp bs=1 (CFG pair, UNet batch 2), "
-                               "multiscale off", "sampler": "dpmpp_2m_cfgpp", "scheduler": "karras", "cfg": 7.0},
-        "cpu_baseline": {"value": v, "unit": "it/s", "cores": threads, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": workload_string(args.size, args.bs), "sampler": "dpmpp_2m_cfgpp", "scheduler": "karras",
+                   "cfg": 7.0, "images_per_gpu": args.bs},
+        "cpu_baseline": {"value": v, "unit": "it/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -159,6 +200,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the full-run / pipe() end-to-end secondary numbers")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="N = 1: skip the bs=32 / HiresFix batch configurations")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the unmodified reference on this GPU")
     ap.add_argument("--workload", default="sd15", choices=["sd15", "flux"],
                     help="sd15 = BASELINE config 2 (the contract line); flux = config 4, Flux.1-dev sized DiT steps (1 GPU)")
     args = ap.parse_args()
@@ -193,7 +236,7 @@ def main():
     # ---- weights: rank 0 generates the seeded synthetic state dict, NCCL-broadcasts it (north_star: weights broadcast once)
     from lightdiffusion_next_b200.synth import unet_shapes, synth_tensor
     shapes = unet_shapes()
-    eng = Engine(max_rows=2 * bs, max_h=lat, max_w=lat, max_ctx_tokens=77, use_graph=not args.no_graph, device=dev)
+    eng = Engine(max_rows=max(2 * bs, 8), max_h=lat, max_w=lat, max_ctx_tokens=77, use_graph=not args.no_graph, device=dev)
     names = sorted(shapes)
     sd = {}
     for nme in names:
@@ -317,19 +360,19 @@ def main():
         attn_flops = 4.0 * B2 * H * N * N * d
         achieved = attn_flops / (attn_ms / 1000.0) / 1e12
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")  # dram__bytes_read + write of one `ncu --set full` capture of this kernel, re-measured per round
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("attn_l0_dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        hbm_roof = hbm_roofline(eng, dev, bs, lat, peaks)
         step_tflop = (UNET_TFLOP_1024 if args.size == 1024 else UNET_TFLOP_512 if args.size == 512 else None)
         line = {
             "metric": "it/s (UNet sampler steps/sec)", "value": its, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"SD1.5 txt2img {args.size}x{args.size} dpmpp_2m_cfgpp bs={bs}/GPU (CFG pair, UNet batch {2*bs}), "
-                                   "multiscale off (every step full resolution)",
+            "config": {"workload": workload_string(args.size, bs),
                        "sampler": "dpmpp_2m_cfgpp", "scheduler": "karras", "cfg": cfg, "images_per_gpu": bs,
                        "weights": "seeded synthetic SD1.5 UNet (859.5M params, bf16 in HBM)",
                        "l2": "working set per step (1.72 GB weights + activations) exceeds the 126 MB L2; no flush needed",
@@ -348,17 +391,187 @@ def main():
             line["step_roofline"] = {"bound": "tensor", "achieved": whole, "peak": peaks["bf16_sus"], "unit": "TFLOP/s",
                                      "frac": whole / peaks["bf16_sus"], "tflop_per_step": step_tflop,
                                      "peak_source": peaks["source"] + " (sustained)"}
+        line["roofline_hbm"] = hbm_roof
+    # ---------------------------------------------------------------- sharded product path (every rank takes part)
+    sharded = None
+    if not args.no_secondary and (world > 1 or not args.no_config3):
+        sharded = sharded_metrics(eng, args.size, dev, world, rank)
+    if rank == 0:
+        if sharded is not None:
+            line["sharded" if world > 1 else "batch_configs"] = sharded
         if world == 1 and not args.no_secondary:
             line["secondary"] = secondary_metrics(eng, args.size, dev)
+            if not args.no_gpu_reference:
+                line["secondary"].update(gpu_reference_metrics(args.size, its))
         if world == 1 and not args.no_cpu_baseline:
-            n, dt, done_w, threads = cpu_oracle_step_time(lat, max_seconds=60.0, max_steps=1, warmup=0)
-            line["cpu_baseline"] = {"value": n / dt, "unit": "it/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n} full {args.size}x{args.size} CFG step(s) of the oracle port "
-                                              "(torch fp32 CPU, all host threads), no warm-up"}
+            line["cpu_baseline"] = cpu_baseline(args.size, lat)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cpu_baseline(size: int, lat: int) -> dict:
+    """Bounded CPU sample on the box's host cores: one full-size sampler step of the UNMODIFIED reference (baseline/_ref)
+    after its own one-step warm-up run; the oracle port if the snapshot is missing."""
+    ref = run_reference_script(["--device", "cpu", "--size", str(size), "--steps", "2", "--warmup", "1"], timeout=600)
+    if "unavailable" not in ref:
+        return {"value": ref["it_per_s"], "unit": "it/s", "cores": ref["threads"], "kind": "reference",
+                "sample": f"2 full {size}x{size} sampler steps (+1 warm-up) of the unmodified reference on the CPU "
+                          f"(sampling.ksampler + sampling.sample, multiscale off, {ref['unet_dtype']} weights cast per call to "
+                          f"{ref['manual_cast']}, torch {ref['torch']}, all host threads)"}
+    n, dt, done_w, threads = cpu_oracle_step_time(lat, max_seconds=60.0, max_steps=1, warmup=0)
+    return {"value": n / dt, "unit": "it/s", "cores": threads, "kind": "port",
+            "sample": f"{n} full {size}x{size} CFG step(s) of the oracle port (torch fp32 CPU, all host threads), no warm-up; "
+                      f"reference snapshot unavailable: {ref['unavailable']}"}
+
+
+def gpu_reference_metrics(size: int, engine_its: float) -> dict:
+    """north_star's comparator: the reference's own GPU path (fp16 UNet, torch SDPA) on THIS GPU through its stock sampling
+    stack, and the same reference loop with backend.install() (every UNet call answered by the engine through
+    model_function_wrapper).  Child processes; 30 steps after a 5-step warm-up run; whole-run wall clock."""
+    out = {}
+    ref = run_reference_script(["--device", "cuda", "--size", str(size), "--steps", "30", "--warmup", "5"], timeout=900)
+    out["gpu_reference"] = ref
+    seam = run_reference_script(["--device", "cuda", "--size", str(size), "--steps", "30", "--warmup", "5", "--seam"], timeout=900)
+    out["seam"] = seam
+    dflt = run_reference_script(["--device", "cuda", "--size", str(size), "--steps", "30", "--warmup", "5", "--default-schedule"],
+                                timeout=900)
+    out["gpu_reference_default_schedule"] = dflt
+    if "it_per_s" in ref:
+        out["vs_gpu_reference"] = {"engine_loop": engine_its / ref["it_per_s"],
+                                   "through_reference_seam": (seam["it_per_s"] / ref["it_per_s"]) if "it_per_s" in seam else None,
+                                   "what": "engine it/s (this line's `value`; and the reference's own loop over the engine seam) "
+                                           "/ the unmodified reference's it/s on the same GPU, same workload, multiscale off"}
+    return out
+
+
+def hbm_roofline(eng, dev, bs: int, lat: int, peaks: dict) -> dict:
+    """HBM-bound kernels of the step timed alone at their level-0 shape (UNet batch 2*bs, lat x lat, 320 channels):
+    achieved = ALGORITHMIC bytes (one read + one write of the tensor) / time, against the measured copy bandwidth."""
+    import torch
+    from lightdiffusion_next_b200 import _lib as L
+    lib = eng.lib
+    B2, HW, C = 2 * bs, lat * lat, 320
+    x = torch.randn(B2 * HW, C, device=dev).bfloat16()
+    y = torch.empty_like(x)
+    gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(reps):
+            fn()
+        a1.record(stream)
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps
+
+    gn_ms = timed(lambda: L.check(lib.ldn_groupnorm_bf16(x.data_ptr(), C, None, 0, B2, HW, 32, 1e-5, gam.data_ptr(), bet.data_ptr(),
+                                                         1, y.data_ptr(), L.cur_stream())))
+    ln_ms = timed(lambda: L.check(lib.ldn_layernorm_bf16(x.data_ptr(), B2 * HW, C, 1e-5, gam.data_ptr(), bet.data_ptr(), y.data_ptr(),
+                                                         L.cur_stream())))
+    nbytes = 2.0 * x.numel() * 2
+    gn, ln = nbytes / (gn_ms * 1e-3) / 1e9, nbytes / (ln_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "gn_stats + gn_apply (GroupNorm 32 + SiLU, [%d, %d] bf16)" % (B2 * HW, C), "achieved": gn,
+            "peak": peaks["hbm"], "unit": "GB/s", "frac": gn / peaks["hbm"], "ms_per_launch": gn_ms,
+            "algorithmic_bytes": nbytes, "note": "the tensor (%.0f MB) fits the 126 MB L2, back-to-back repeats may hit it" % (x.numel() * 2 / 1e6),
+            "layernorm": {"kernel": "layernorm_kernel", "achieved": ln, "frac": ln / peaks["hbm"], "ms_per_launch": ln_ms},
+            "peak_source": peaks["source"]}
+
+
+def sharded_metrics(eng, size: int, dev, world: int, rank: int) -> dict:
+    """BASELINE config 3 (bs = 32 in total, 32 / N images per GPU, UNet batch 8 per call) and config 5 (one HiresFix image per
+    GPU: 512 -> bislerp x4 latent -> 2048, 10 steps euler_ancestral_cfgpp / normal / denoise 0.45, VAE decode 2048^2) through
+    the product's sharded driver (distributed.sample_sharded: per-rank replay of the full-batch noise, no collective in the
+    loop, gather of the final latents on rank 0).  Wall clock bracketed by barrier + device synchronise on every rank, max
+    over ranks.  In-run check: rank 0 recomputes the LAST rank's last four images in its own process and compares them with the
+    rows it gathered (dpmpp_2m_cfgpp: bit-equal -- the engine is deterministic and batch rows are independent)."""
+    import torch
+    import torch.distributed as dist
+    from lightdiffusion_next_b200 import distributed as D
+    from lightdiffusion_next_b200 import sampling as S
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tmax(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    out = {}
+    lat = size // 8
+    g = torch.Generator().manual_seed(99)
+    pos, neg = torch.randn(1, 77, 768, generator=g), torch.randn(1, 77, 768, generator=g)
+    total, steps, per_call = 32, 30, 4
+    latent = {"samples": torch.zeros(total, 4, lat, lat)}
+    kw = dict(enable_multiscale=False, images_per_call=per_call)
+    # warm-up: builds + captures the UNet-batch-8 program (3 steps on the first `world * per_call` images)
+    D.sample_sharded(eng, 7, 3, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, {"samples": latent["samples"][:world * per_call]}, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    res = D.sample_sharded(eng, 42, steps, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, latent, **kw)[0]
+    barrier()
+    dt = tmax(time.perf_counter() - t0)
+    ok = None
+    if rank == 0:
+        full = res["samples"]
+        a, b = total - per_call, total  # the last call of the last rank
+        chk = S.sample(eng, 42, steps, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, {"samples": latent["samples"][a:b]},
+                       noise=S.prepare_noise(latent["samples"], 42)[a:b], enable_multiscale=False,
+                       batch_slice=(a, b, total))[0]["samples"]
+        ok = bool(torch.equal(chk, full[a:b])) and full.shape[0] == total and bool(torch.isfinite(full).all())
+    out["config3"] = {"what": f"SD1.5 {size}x{size} bs=32 sharded over {world} GPU(s) ({total // world} images/GPU, UNet batch {2 * per_call} per call), "
+                              f"{steps} steps dpmpp_2m_cfgpp multiscale off, latents gathered on rank 0",
+                      "image_it_per_s": total * steps / dt, "seconds": dt, "images": total,
+                      "gathered_equals_single_process": ok}
+    # ---- config 5: one image per GPU
+    if size == 1024:
+        n_img = world
+        lat5 = {"samples": torch.zeros(n_img, 4, 64, 64)}
+        from lightdiffusion_next_b200.latent import latent_upscale
+        from lightdiffusion_next_b200.synth import synth_state_dict, vae_decoder_shapes
+        eng.load_vae(synth_state_dict(vae_decoder_shapes(), seed=4321))
+
+        def hires_run(seed, steps1, steps2):
+            first = D.sample_sharded(eng, seed, steps1, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, lat5, images_per_call=1)[0]
+            # LatentUpscale runs on the host in the reference (bislerp, src/Utilities/upscale.py); rank 0 holds the batch
+            if world > 1:
+                up = [latent_upscale({"samples": first["samples"]}, 2048, 2048)["samples"]] if rank == 0 else [None]
+                dist.broadcast_object_list(up, 0)
+                up = up[0]
+            else:
+                up = latent_upscale({"samples": first["samples"]}, 2048, 2048)["samples"]
+            second = D.sample_sharded(eng, seed + 1, steps2, 8.0, "euler_ancestral_cfgpp", "normal", pos, neg, {"samples": up},
+                                      images_per_call=1, denoise=0.45)[0]
+            lo, hi = D.shard_range(n_img, rank, world)
+            mine = up[lo:hi] if second is None else second["samples"][lo:hi]
+            if world > 1:  # every rank decodes its own image: scatter the final latents back
+                mine = D.scatter_rows(second["samples"] if rank == 0 else None, (4, 256, 256), n_img, dev)
+            img = eng.vae_decode(mine.to(dev))
+            return D.gather_rows(img, n_img)
+
+        hires_run(1, 2, 2)  # warm-up (program build / graph capture at 64^2 and 256^2 latents, VAE 2048^2)
+        barrier()
+        t0 = time.perf_counter()
+        imgs = hires_run(5, 20, 10)
+        barrier()
+        dt5 = tmax(time.perf_counter() - t0)
+        out["config5"] = {"what": f"SD1.5 HiresFix 512 -> 2048 + VAE decode 2048^2, 1 image/GPU on {world} GPU(s): 20 steps dpmpp_2m_cfgpp @512 "
+                                  "(reference-default multiscale), bislerp x4 on the host, 10 steps euler_ancestral_cfgpp/normal/denoise 0.45 "
+                                  "@2048, decode, images gathered on rank 0",
+                          "seconds": dt5, "images_per_s": n_img / dt5,
+                          "finite": bool(torch.isfinite(imgs).all()) if rank == 0 else None,
+                          "shape": list(imgs.shape) if rank == 0 else None}
+    return out
 
 
 def run_flux(args):

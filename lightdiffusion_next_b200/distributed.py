@@ -88,12 +88,15 @@ def gather_rows(mine: torch.Tensor, batch: int, dst: int = 0) -> Optional[torch.
 
 
 def sample_sharded(engine, seed: int, steps: int, cfg: float, sampler_name: str, scheduler: str, positive: torch.Tensor,
-                   negative: torch.Tensor, latent_image: Dict[str, torch.Tensor], **kw):
+                   negative: torch.Tensor, latent_image: Dict[str, torch.Tensor], images_per_call: int = 0, **kw):
     """KSampler.sample for a batch sharded over the ranks.  positive/negative: [1 or B, T, 768] on every rank.
     Returns ({"samples": [B,4,h,w]},) on rank 0 and (None,) elsewhere.  Reproduces the single-process batch result for
     every sampler: the initial noise is each rank's slice of the same full-batch draw, and the per-step noise of the ancestral
     / SDE samplers is drawn on every rank for the WHOLE batch from identically seeded generators and sliced (`batch_slice`),
-    so image i gets the noise it would get as row i of the unsharded batch -- never the same noise as another image."""
+    so image i gets the noise it would get as row i of the unsharded batch -- never the same noise as another image.
+    images_per_call > 0 bounds the UNet batch: a rank's images are sampled in consecutive groups of that size (one launch
+    program, bounded activation memory); for the deterministic samplers the result is unchanged, for the ancestral / SDE
+    ones every group re-seeds the generators (each group consumes the whole-batch noise stream from its start)."""
     from . import sampling as S
 
     latent = latent_image["samples"]
@@ -109,11 +112,18 @@ def sample_sharded(engine, seed: int, steps: int, cfg: float, sampler_name: str,
     dev = engine.device
     out = None
     if hi > lo:
-        pos = positive if positive.shape[0] == 1 else positive[lo:hi]
-        neg = negative if negative.shape[0] == 1 else negative[lo:hi]
-        res = S.sample(engine, seed, steps, cfg, sampler_name, scheduler, pos, neg, {"samples": latent[lo:hi]},
-                       noise=noise, batch_slice=(lo, hi, B), **kw)
-        out = res[0]["samples"].to(dev)
+        step = images_per_call if images_per_call > 0 else hi - lo
+        parts = []
+        for a in range(lo, hi, step):
+            b = min(hi, a + step)
+            if a > lo:
+                S.prepare_noise(latent, seed)  # same generator state at the start of every group
+            pos = positive if positive.shape[0] == 1 else positive[a:b]
+            neg = negative if negative.shape[0] == 1 else negative[a:b]
+            res = S.sample(engine, seed, steps, cfg, sampler_name, scheduler, pos, neg, {"samples": latent[a:b]},
+                           noise=noise[a - lo:b - lo], batch_slice=(a, b, B), **kw)
+            parts.append(res[0]["samples"].to(dev))
+        out = torch.cat(parts) if len(parts) > 1 else parts[0]
     else:
         out = torch.empty((0,) + tuple(latent.shape[1:]), device=dev)
     full = gather_rows(out, B)
