@@ -40,9 +40,13 @@ class EngineWrapper:
         A UNet weight reload (Engine.weights_epoch) invalidates it, because the engine then drops its K/V buffers."""
         eng = self.engine
         epoch = eng.weights_epoch.get(0, 0)
-        ident = (id(ctx), ctx._version, ctx.data_ptr(), tuple(ctx.shape))
+        try:
+            version = ctx._version
+        except RuntimeError:   # inference tensors (the reference samples under torch.inference_mode) track no version:
+            version = None     # an in-place change would go unseen, so identity alone proves nothing -> compare content
+        ident = (id(ctx), version, ctx.data_ptr(), tuple(ctx.shape))
         if self._ctx_copy is not None and self._ctx_epoch == epoch:
-            if ident == self._ctx_ident[0] and self._ctx_ident[1] is ctx:
+            if version is not None and ident == self._ctx_ident[0] and self._ctx_ident[1] is ctx:
                 return
             c = ctx.to(eng.device, torch.float32)
             if c.shape == self._ctx_copy.shape and torch.equal(c, self._ctx_copy):

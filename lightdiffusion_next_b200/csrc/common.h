@@ -179,6 +179,8 @@ void finish_attn5_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn5(const AttnPlan& plan, cudaStream_t stream);
 void finish_attn6_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn6(const AttnPlan& plan, cudaStream_t stream);
+void finish_attn7_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
+void launch_attn7(const AttnPlan& plan, cudaStream_t stream);
 void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)

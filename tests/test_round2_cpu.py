@@ -132,6 +132,11 @@ def test_seam_context_cache_is_keyed_on_content(unet_sd):
     assert eng.context_uploads == 3
     call(torch.cat([b, b], 1), torch.cat([a, a], 1))   # another token count
     assert eng.context_uploads == 4
+    # the reference samples under torch.inference_mode (pipeline.py:281): inference tensors have no version counter
+    with torch.inference_mode():
+        for _ in range(3):
+            call(a, b)
+    assert eng.context_uploads == 5
 
 
 class RecordedTokenizer:
@@ -232,9 +237,10 @@ def forbidden(*a, **k):
 m = backend.install(mp, engine=eng)
 model.apply_model = forbidden
 assert m is not mp and "model_function_wrapper" not in mp.model_options
-res = sampling.KSampler().sample(model=m, seed=42, steps=6, cfg=7.0, sampler_name="dpmpp_2m_cfgpp", scheduler="karras",
-                                 denoise=1.0, positive=[[g["ctx_pos"], {}]], negative=[[g["ctx_neg"], {}]],
-                                 latent_image={"samples": torch.zeros(1, 4, 16, 16)}, pipeline=True)
+with torch.inference_mode():   # as the reference's pipeline() runs it (src/user/pipeline.py:281)
+    res = sampling.KSampler().sample(model=m, seed=42, steps=6, cfg=7.0, sampler_name="dpmpp_2m_cfgpp", scheduler="karras",
+                                     denoise=1.0, positive=[[g["ctx_pos"], {}]], negative=[[g["ctx_neg"], {}]],
+                                     latent_image={"samples": torch.zeros(1, 4, 16, 16)}, pipeline=True)
 out, ref = res[0]["samples"], g["dpmpp_2m_final"]
 err = float((out - ref).norm() / ref.norm())
 print("err", err, "uploads", eng.context_uploads, "denoise", eng.denoise_calls)
