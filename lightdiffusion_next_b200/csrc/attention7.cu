@@ -7,7 +7,7 @@
 // warps of the same TMEM lane quarter.  Generation 5 ran 2 softmax warps per scheduler, each holding 128 scores per
 // thread in registers; its profile (profiles/r1_attention_ncu_full.md) showed the schedulers issuing 55 % of the cycles
 // with the MUFU at 49 % and the tensor pipe at 29 % -- neither pipe saturated, the loop was bound by dependent-instruction
-// latency with too few warps to hide it.  Here 4 softmax warps per scheduler hold 64 scores each (<= 112 registers), so
+// latency with too few warps to hide it.  Here 4 softmax warps per scheduler hold 64 scores each (<= 104 registers), so
 // one warp's TMEM load / max reduction / barrier waits overlap the other warps' exponentials.  The two halves of a row
 // agree on the running maximum through a 4 KB shared-memory exchange and a 64-thread named barrier per key tile.
 #include "common.h"
@@ -86,7 +86,10 @@ __global__ void __launch_bounds__(kA7Threads, 1) attn7_tc_kernel(const __grid_co
   const int n_tiles = (p.Nk + kK3 - 1) / kK3;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    // Register budget: the CTA is launched with 96 registers x 640 threads = 61440; setmaxnreg can only hand out what other
+    // warps released (it never draws on unallocated file space), so 128 x 48 + 512 x 104 = 59392 must stay below that --
+    // asking for 112 here deadlocked the last softmax warps at their setmaxnreg.inc.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
       if (lane == 0) {
         mbar_arrive_expect_tx(q_full, 2 * atom_bytes);
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kA7Threads, 1) attn7_tc_kernel(const __grid_co
     }
   } else {
     // ---------------------------------------------------------------- softmax: 16 warps, two threads per score row
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int sw = warp - 4;
     const int t = sw >> 3;           // query tile
     const int hsel = (sw >> 2) & 1;  // which 64 keys of the 128-key tile this thread owns
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(kA7Threads, 1) attn7_tc_kernel(const __grid_co
     uint64_t* const my_p_full = &p_full[t];
     uint64_t* const my_pv_done = &pv_done[t];
     const int pair_bar = 1 + t * 4 + qd;  // named barrier shared by the two warps that split these 32 rows
+    const uint32_t hm_addr = smem_u32(half_max) + (uint32_t)t * 1024u + (uint32_t)r * 4u;
     float m_used = 0.f;  // exponent offset currently baked into O (scaled log2 units); identical in both halves of a row
 
     for (int j = 0; j < n_tiles; ++j) {
@@ -222,10 +226,13 @@ __global__ void __launch_bounds__(kA7Threads, 1) attn7_tc_kernel(const __grid_co
       }
       // the other half of the row: write mine, 64-thread barrier, read the partner's (buffers alternate with the tile
       // parity, so a write for tile j + 2 cannot overtake the partner's read for tile j: the barrier of tile j + 1 sits between)
-      float* hm = half_max + (((j & 1) * 2 + t) * 2) * 128;
-      hm[hsel * 128 + r] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const uint32_t hm = hm_addr + (uint32_t)(j & 1) * 2048u;  // shared-space address: [parity][tile][half][row]
+      const float mine = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(hm + (uint32_t)hsel * 512u), "f"(mine) : "memory");
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      const float mx = fmaxf(hm[r], hm[128 + r]) * sc;
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(hm + (uint32_t)(hsel ^ 1) * 512u) : "memory");
+      const float mx = fmaxf(mine, other) * sc;
       if (j == 0) {
         m_used = mx;
       } else {
