@@ -360,13 +360,7 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
     // 1.92 ms at N = 16384 -- and was dropped: the limiter was MMA issue, not softmax latency.)
     // generation 5 (P kept in tensor memory, TS-form P*V); generation 3 (P through shared memory) was retired once v5
     // had replaced it on every path
-    // generation 7: generation 5's data path with two softmax threads per score row (16 softmax warps): long key
-    // sequences only -- with a handful of key tiles (cross-attention) the extra warps buy nothing
-    static const int d40_gen = getenv("LDN_ATTN_D40") ? atoi(getenv("LDN_ATTN_D40")) : 5;
-    if (d40_gen == 7 && a.Nk >= 1024)
-      finish_attn7_plan(plan, a.Nq, a.Nk, a.heads, a.B);
-    else
-      finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+    finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   } else if (a.d == 80 && p.vt_head_stride == 96 && !a.causal) {
     finish_attn6_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // generation 6: ones-row V^T, P aliased over S in TMEM
   } else if (a.d == 128 && p.vt_head_stride == 128 && !a.causal && !force_v1) {
@@ -391,7 +385,6 @@ static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 
 void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
   if (plan.p.variant == 6) return launch_attn6(plan, stream);
-  if (plan.p.variant == 7) return launch_attn7(plan, stream);
   if (plan.p.variant == 5) return launch_attn5(plan, stream);
   if (plan.p.variant == 2) return launch_attn2(plan, stream);
   if (plan.p.bias) {

@@ -179,14 +179,12 @@ void finish_attn5_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn5(const AttnPlan& plan, cudaStream_t stream);
 void finish_attn6_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn6(const AttnPlan& plan, cudaStream_t stream);
-void finish_attn7_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
-void launch_attn7(const AttnPlan& plan, cudaStream_t stream);
 void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)
 // GroupNorm over NHWC bf16 input that may be a virtual concat of two tensors along C.
 // stats_ws: workspace of groupnorm_ws_bytes(B) bytes.
-inline size_t groupnorm_ws_bytes(int B) { return (size_t)B * 1024 * 32 * 16 + (size_t)B * 32 * 8 + (size_t)B * 8 + 256; }  // must be zero-initialised (arrival counters)
+inline size_t groupnorm_ws_bytes(int B) { return (size_t)B * 1024 * 32 * 16 + (size_t)B * 32 * 8 + (size_t)B * 4 + 256; }  // must be zero-initialised (arrival counters)
 void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
                       const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws,
                       cudaStream_t stream);

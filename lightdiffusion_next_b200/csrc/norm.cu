@@ -10,8 +10,6 @@
 #include "common.h"
 #include "ptx.cuh"
 
-#include <cstdlib>
-
 namespace ldn {
 
 // ------------------------------------------------------------------ GroupNorm statistics (deterministic: no atomics)
@@ -217,257 +215,6 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16*
   for (; pix < p_end; pix += R) apply(*reinterpret_cast<const uint4*>(src + (size_t)pix * ld), pix);
 }
 
-// ------------------------------------------------------------------ GroupNorm in ONE launch (statistics + apply)
-// Replaces the gn_stats / gn_apply pair wherever the whole grid can be resident at once (grid <= SM count, one CTA per SM).
-// Every CTA owns a slice of `rows_per_block` pixels of one batch row:
-//   phase 1  stream the slice from global memory ONCE, park it in shared memory (kResident) and accumulate the per-thread
-//            channel sums; reduce to one (sum, sumsq) double2 per group and CTA exactly as gn_stats_kernel does;
-//   barrier  arrival counter per batch row; the last CTA to arrive folds the partials of all CTAs in a fixed order (the result
-//            does not depend on which CTA is last: deterministic), publishes (mean, rstd) and bumps a sequence word that the
-//            other CTAs of the batch row poll with acquire loads (bounded: a protocol bug traps instead of hanging the GPU);
-//   phase 2  normalise (+SiLU) the slice out of shared memory and write it once.
-// Traffic: one read + one write of the tensor -- the algorithmic minimum -- instead of two reads + one write in two launches.
-// When the slice does not fit in shared memory (kResident = false: VAE-sized tensors, wide skip concats at level 0) phase 2
-// re-reads the slice from global memory (L2 for UNet-sized tensors); still one launch.
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-template <bool kResident>
-__global__ void __launch_bounds__(1024, 1)
-gn_fused_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW, int cpg, int rows_per_block,
-                int R, double2* __restrict__ partial, unsigned int* __restrict__ counters, unsigned int* __restrict__ seq,
-                float eps, float2* __restrict__ mean_rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                int silu, bf16* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t gn_smem[];
-  float(*s_part)[4] = reinterpret_cast<float(*)[4]>(gn_smem);             // [1024][4]
-  uint4* slice = reinterpret_cast<uint4*>(gn_smem + 1024 * 4 * sizeof(float));  // [rows_per_block][C / 8] (kResident)
-  const int C = C0 + C1;
-  const int nvec = C >> 3;
-  const bool active = (int)threadIdx.x < nvec * R;
-  const int cv = threadIdx.x % nvec;
-  const int prow = threadIdx.x / nvec;
-  const int b = blockIdx.y;
-  const int c = cv * 8;
-  const int p_begin = blockIdx.x * rows_per_block;
-  const int p_end = min(HW, p_begin + rows_per_block);
-  __shared__ unsigned int s_seq0;
-  if (threadIdx.x == 0) s_seq0 = ld_acquire_u32(&seq[b]);  // read BEFORE this CTA arrives: the bump needs every arrival
-  const bf16* src = nullptr;
-  int ld = 0;
-  if (active) {
-    if (c < C0) {
-      src = x0 + (size_t)b * HW * C0 + c;
-      ld = C0;
-    } else {
-      src = x1 + (size_t)b * HW * C1 + (c - C0);
-      ld = C1;
-    }
-    float s[8], q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-    auto acc = [&](const uint4& v) {
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = bf16_lo(w[i]), bb = bf16_hi(w[i]);
-        s[2 * i] += a;
-        q[2 * i] += a * a;
-        s[2 * i + 1] += bb;
-        q[2 * i + 1] += bb * bb;
-      }
-    };
-    int pix = p_begin + prow;
-    for (; pix + 3 * R < p_end; pix += 4 * R) {  // four independent 16-byte loads in flight per thread
-      uint4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(pix + u * R) * ld);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (kResident) slice[(size_t)(pix + u * R - p_begin) * nvec + cv] = v[u];
-        acc(v[u]);
-      }
-    }
-    for (; pix < p_end; pix += R) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)pix * ld);
-      if (kResident) slice[(size_t)(pix - p_begin) * nvec + cv] = v;
-      acc(v);
-    }
-    const int g_lo = c / cpg;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if ((c + i) / cpg == g_lo) {
-        a0 += s[i];
-        a1 += q[i];
-      } else {
-        a2 += s[i];
-        a3 += q[i];
-      }
-    }
-    s_part[threadIdx.x][0] = a0;
-    s_part[threadIdx.x][1] = a1;
-    s_part[threadIdx.x][2] = a2;
-    s_part[threadIdx.x][3] = a3;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int g = warp; g < 32; g += nwarps) {
-    const int first = (g * cpg) >> 3;
-    const int last = ((g + 1) * cpg - 1) >> 3;
-    const int ncv = last - first + 1;
-    double sum = 0.0, sq = 0.0;
-    for (int idx = lane; idx < ncv * R; idx += 32) {
-      const int v = first + idx % ncv;
-      const int pr = idx / ncv;
-      const int t = pr * nvec + v;
-      const int g_lo = (v * 8) / cpg;
-      if (g_lo == g) {
-        sum += (double)s_part[t][0];
-        sq += (double)s_part[t][1];
-      } else if (g_lo + 1 == g) {
-        sum += (double)s_part[t][2];
-        sq += (double)s_part[t][3];
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    }
-    if (lane == 0) partial[((size_t)b * gridDim.x + blockIdx.x) * 32 + g] = make_double2(sum, sq);
-  }
-  // ---- barrier over the CTAs of this batch row
-  __shared__ unsigned int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[b], 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    const int splits = gridDim.x;
-    const double n = (double)HW * cpg;
-    for (int g = warp; g < 32; g += nwarps) {
-      double sum = 0.0, sq = 0.0;
-      for (int sp = lane; sp < splits; sp += 32) {
-        const double2 v = __ldcg(&partial[((size_t)b * splits + sp) * 32 + g]);
-        sum += v.x;
-        sq += v.y;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      }
-      if (lane == 0) {
-        const double mean = sum / n;
-        double var = sq / n - mean * mean;
-        if (var < 0) var = 0;
-        mean_rstd[b * 32 + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-      }
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      counters[b] = 0;  // re-armed for the next launch (ordered before the release below)
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&seq[b]), "r"(s_seq0 + 1u) : "memory");
-    }
-  } else {
-    if (threadIdx.x == 0) {
-      unsigned int spins = 0;
-      while (ld_acquire_u32(&seq[b]) == s_seq0) {
-        __nanosleep(40);
-        if (++spins > (1u << 24)) {
-          printf("ldn: groupnorm grid barrier timeout block=(%d,%d)\n", blockIdx.x, blockIdx.y);
-          __trap();
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (!active) return;
-  // ---- phase 2: normalise (+SiLU)
-  float a[8], sh[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 mr = __ldcg(&mean_rstd[b * 32 + (c + i) / cpg]);
-    a[i] = mr.y * gamma[c + i];
-    sh[i] = beta[c + i] - mr.x * a[i];
-  }
-  bf16* dst = out + (size_t)b * HW * C + c;
-  auto apply = [&](const uint4& v, int pix) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float y0 = fmaf(bf16_lo(w[i]), a[2 * i], sh[2 * i]);
-      float y1 = fmaf(bf16_hi(w[i]), a[2 * i + 1], sh[2 * i + 1]);
-      if (silu) {
-        y0 = silu_f(y0);
-        y1 = silu_f(y1);
-      }
-      o[i] = pack_bf16x2(y0, y1);
-    }
-    *reinterpret_cast<uint4*>(dst + (size_t)pix * C) = make_uint4(o[0], o[1], o[2], o[3]);
-  };
-  if (kResident) {
-    for (int pix = p_begin + prow; pix < p_end; pix += R) apply(slice[(size_t)(pix - p_begin) * nvec + cv], pix);
-  } else {
-    int pix = p_begin + prow;
-    for (; pix + 3 * R < p_end; pix += 4 * R) {
-      uint4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(pix + u * R) * ld);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) apply(v[u], pix + u * R);
-    }
-    for (; pix < p_end; pix += R) apply(*reinterpret_cast<const uint4*>(src + (size_t)pix * ld), pix);
-  }
-}
-
-// Single-launch path: returns false when the grid could not be fully resident (the caller then uses the two-kernel path).
-static bool launch_groupnorm_fused(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int cpg, float eps,
-                                   const float* gamma, const float* beta, bool silu, bf16* out, double2* partial,
-                                   float2* mean_rstd, unsigned int* counters, unsigned int* seq, cudaStream_t stream) {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    LDN_CUDA(cudaGetDevice(&dev));
-    LDN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    LDN_CUDA(cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
-    LDN_CUDA(cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  }
-  if (B > num_sms) return false;
-  const int C = C0 + C1;
-  const int nvec = C / 8;
-  if (nvec > 1024) return false;
-  // one CTA per SM at most: every CTA of the grid must be resident for the in-kernel barrier
-  int splits = num_sms / B;
-  if (splits > LDN_GN_MAX_SPLITS) splits = LDN_GN_MAX_SPLITS;
-  int min_rows = 16;  // small tensors: fewer, fatter CTAs (fewer arrivals at the barrier)
-  if (splits > (HW + min_rows - 1) / min_rows) splits = (HW + min_rows - 1) / min_rows;
-  if (splits < 1) splits = 1;
-  const int rows_per_block = (HW + splits - 1) / splits;
-  splits = (HW + rows_per_block - 1) / rows_per_block;
-  int R = 1024 / nvec;
-  if (R > rows_per_block) R = rows_per_block;
-  if (R < 1) R = 1;
-  const int threads = (nvec * R + 31) / 32 * 32;
-  const size_t part_bytes = 1024 * 4 * sizeof(float);
-  const size_t slice_bytes = (size_t)rows_per_block * nvec * 16;
-  const bool resident = part_bytes + slice_bytes <= (size_t)(227 * 1024 - 64 - 1024);
-  if (resident)
-    gn_fused_kernel<true><<<dim3(splits, B), threads, part_bytes + slice_bytes, stream>>>(
-        x0, C0, x1, C1, HW, cpg, rows_per_block, R, partial, counters, seq, eps, mean_rstd, gamma, beta, silu ? 1 : 0, out);
-  else
-    gn_fused_kernel<false><<<dim3(splits, B), threads, part_bytes, stream>>>(
-        x0, C0, x1, C1, HW, cpg, rows_per_block, R, partial, counters, seq, eps, mean_rstd, gamma, beta, silu ? 1 : 0, out);
-  LDN_CUDA(cudaGetLastError());
-  return true;
-}
-
 void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
                       const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws,
                       cudaStream_t stream) {
@@ -480,11 +227,6 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   double2* partial = reinterpret_cast<double2*>(stats_ws);
   float2* mean_rstd = reinterpret_cast<float2*>(partial + (size_t)B * LDN_GN_MAX_SPLITS * 32);
   unsigned int* counters = reinterpret_cast<unsigned int*>(mean_rstd + (size_t)B * 32);  // zero-initialised workspace
-  unsigned int* seq = counters + B;  // barrier sequence words of the single-launch kernel
-  static const bool fused = !(getenv("LDN_GN_FUSED") && atoi(getenv("LDN_GN_FUSED")) == 0);
-  if (fused && launch_groupnorm_fused(x0, C0, x1, C1, B, HW, cpg, eps, gamma, beta, silu, out, partial, mean_rstd, counters,
-                                      seq, stream))
-    return;
   const int nvec = C / 8;
   // R pixel rows per block pass; every thread should see >= 4 pixels (>= 8 when the tensor is large) so that its
   // 16-byte loads overlap, and the grid should still cover the 148 SMs where the tensor is big enough for that.
