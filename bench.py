@@ -713,7 +713,75 @@ def run_flux(args):
                           "peak_source": peaks["source"] + " (sustained)"},
         "cpu_baseline": None,
     }
+    if not args.no_secondary:
+        line["secondary"] = {"flux_image_e2e": flux_image_e2e(eng, dev, args.size)}
     print(json.dumps(line), flush=True)
+
+
+def flux_image_e2e(eng, dev, size: int) -> dict:
+    """BASELINE config 4 end to end, the Flux branch of pipeline() (src/user/pipeline.py:218-275) on one engine:
+    CLIP-L pooled vector + T5-XXL states (CLIPTextEncodeFlux) -> 20 steps euler_cfgpp / beta, cfg 1, guidance 3
+    (two DiT forwards per step + the sampler's half-resolution calls at steps 2-3) -> 16-channel VAE decode -> image on
+    the host.  Seeded synthetic weights of the real sizes (T5-XXL encoder 4.76 G, Flux.1-dev 11.9 G, CLIP-L, VAE), generated
+    on the device; wall clock with a device synchronise on both sides, second run (the first builds / captures the programs)."""
+    import zlib
+
+    import torch
+
+    from lightdiffusion_next_b200 import t5 as T5H
+    from lightdiffusion_next_b200.pipeline import EMPTY_TOKENS, FluxPipeline
+    from lightdiffusion_next_b200.synth import clip_shapes, synth_state_dict, vae_decoder_shapes
+
+    t_load = time.perf_counter()
+    batch, nbytes = {}, 0
+    shapes = T5H.t5_shapes()
+    for k, shp in shapes.items():
+        g = torch.Generator(device=dev).manual_seed(zlib.crc32(k.encode()) & 0x7FFFFFFF)
+        if k == "shared.weight":
+            w = torch.randn(shp, generator=g, device=dev, dtype=torch.bfloat16)
+        elif k.endswith("relative_attention_bias.weight"):
+            w = torch.randn(shp, generator=g, device=dev)
+        elif len(shp) > 1:
+            w = torch.randn(shp, generator=g, device=dev, dtype=torch.bfloat16) * ((0.125 if ".q." in k else 0.5 if (".o." in k or ".wo." in k) else 1.0) / shp[1] ** 0.5)
+        else:
+            w = (1.0 + 0.1 * torch.randn(shp, generator=g, device=dev)).float()
+        batch[k] = w
+        nbytes += w.numel() * w.element_size()
+        if nbytes > 2 << 30:
+            eng.load_weights(5, batch)
+            batch, nbytes = {}, 0
+            torch.cuda.empty_cache()
+    if batch:
+        eng.load_weights(5, batch)
+    eng._t5_width = shapes["shared.weight"][1]
+    eng.load_clip(synth_state_dict(clip_shapes(), seed=777))
+    vsd = {k: v for k, v in synth_state_dict(vae_decoder_shapes(z=16), seed=9753).items() if not k.startswith("post_quant_conv")}
+    eng.load_vae(vsd)
+    torch.cuda.empty_cache()
+    t_load = time.perf_counter() - t_load
+    pipe = FluxPipeline(eng)
+    clip_tokens = [[(49406, 1.0)] + [(1000 + i, 1.0) for i in range(20)] + [(49407, 1.0)] * 56]
+    t5_tokens = [T5H.pad_tokens([100 + 7 * i for i in range(40)])]  # 40 ids + end token, padded to the reference's 256-token minimum
+    out = {}
+    for run in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cond = pipe.encode(clip_tokens, t5_tokens, guidance=3.0)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        lat = pipe.sample(cond, pipe.zero_out(cond), size, size, batch=1, seed=3, steps=20)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        img = pipe.decode(lat)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        out = {"seconds_per_image": t3 - t0, "images_per_s": 1.0 / (t3 - t0), "text_encode_s": t1 - t0, "sample_s": t2 - t1,
+               "sampler_it_per_s": 20 / (t2 - t1), "vae_decode_and_d2h_s": t3 - t2, "t5_tokens": len(t5_tokens[0]),
+               "shape": list(img.shape), "finite": bool(torch.isfinite(img).all().item())}
+    out["what"] = (f"Flux.1-dev {size}x{size} bs=1: CLIP-L + T5-XXL encode -> 20 steps euler_cfgpp / beta (2 DiT forwards per step + the "
+                   "half-resolution calls of steps 2-3) -> 16-channel VAE decode -> image to host; synthetic weights of the real sizes")
+    out["weight_setup_s"] = t_load
+    return out
 
 
 def secondary_metrics(eng, size: int, dev) -> dict:

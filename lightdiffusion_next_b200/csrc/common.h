@@ -61,7 +61,7 @@ struct GemmParams {
   const bf16* residual;
   long long ldr;
   int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
-  int epi_opt;       // bit 0: prefetching epilogue (persistent kernel), bit 1: packed-pair GEGLU arithmetic
+  int epi_opt;       // bit 0: 256-bit epilogue accesses, bit 1: packed-pair GEGLU arithmetic, bit 2: prefetching epilogue (persistent kernel)
   int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77),
             // 2 ReLU after the bias, 3 ReLU after the residual add (TAESD, src/AutoEncoders/taesd.py:39-63),
             // 4 GELU (tanh approximation) after the bias (Flux MLPs, src/BlackForest/Flux.py:283-294)
@@ -251,5 +251,7 @@ void launch_clip_embed(const long long* ids, const float* tok_emb, int vocab, co
                        const float* pos_emb, int rows, int T, int C, bf16* out, cudaStream_t stream);
 void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
                          cudaStream_t stream);
+void launch_softmax_rows_f32(const float* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
+                             cudaStream_t stream);
 
 }  // namespace ldn

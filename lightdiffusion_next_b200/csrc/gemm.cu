@@ -339,10 +339,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_persist_kernel(const 
         batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
       }
       const int acc = tl & 1;
-      mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
-      tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
+      if (p.epi == 0 && p.splits == 1 && (p.epi_opt & 5) == 5) {
+        gemm_epilogue_tile_prefetch(p, BN, n0, out_row, batch, t_lane, ehalf, &tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
+      } else {
+        mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
+        tc_fence_after();
+        gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -491,7 +495,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.head_dim = a.head_dim;
   p.head_slot = a.head_slot;
   p.act = a.act;
-  static const int epi_opt = getenv("LDN_GEMM_EPI_OPT") ? atoi(getenv("LDN_GEMM_EPI_OPT")) : 3;
+  static const int epi_opt = getenv("LDN_GEMM_EPI_OPT") ? atoi(getenv("LDN_GEMM_EPI_OPT")) : 7;
   p.epi_opt = epi_opt;
   {  // 256-bit epilogue accesses need 32-byte aligned rows
     const long long ldo_out = a.epi == 1 ? a.ldo : a.ldo;

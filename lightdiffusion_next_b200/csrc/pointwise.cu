@@ -648,11 +648,11 @@ __global__ void softmax_rows_kernel(const bf16* __restrict__ in, long long ld_in
 }
 // Register-resident variant: one block per row, the row is read once with 16-byte loads (MAXV per thread), reduced, and
 // written once -- 2 bytes read + 2 bytes written per element instead of three scalar passes.
-template <int MAXV>
-__global__ void __launch_bounds__(512) softmax_rows_vec_kernel(const bf16* __restrict__ in, long long ld_in,
+template <int MAXV, typename TIn>
+__global__ void __launch_bounds__(512) softmax_rows_vec_kernel(const TIn* __restrict__ in, long long ld_in,
                                                                bf16* __restrict__ out, long long ld_out, int cols,
                                                                float scale) {
-  const bf16* src = in + (size_t)blockIdx.x * ld_in;
+  const TIn* src = in + (size_t)blockIdx.x * ld_in;
   bf16* dst = out + (size_t)blockIdx.x * ld_out;
   __shared__ float red[32];
   const int nvec = cols >> 3;
@@ -663,14 +663,22 @@ __global__ void __launch_bounds__(512) softmax_rows_vec_kernel(const bf16* __res
   for (int k = 0; k < MAXV; ++k) {
     const int vi = threadIdx.x + k * 512;
     if (vi < nvec) {
-      const uint4 u = *reinterpret_cast<const uint4*>(src + (size_t)vi * 8);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      if constexpr (sizeof(TIn) == 4) {  // fp32 logits (VAE mid-block attention): two 16-byte loads
+        const float4 a = *reinterpret_cast<const float4*>(src + (size_t)vi * 8);
+        const float4 b = *reinterpret_cast<const float4*>(src + (size_t)vi * 8 + 4);
+        v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w;
+        v[k][4] = b.x; v[k][5] = b.y; v[k][6] = b.z; v[k][7] = b.w;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + (size_t)vi * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[k][2 * i] = bf16_lo(w[i]);
-        v[k][2 * i + 1] = bf16_hi(w[i]);
-        mx = fmaxf(mx, fmaxf(v[k][2 * i], v[k][2 * i + 1]));
+        for (int i = 0; i < 4; ++i) {
+          v[k][2 * i] = bf16_lo(w[i]);
+          v[k][2 * i + 1] = bf16_hi(w[i]);
+        }
       }
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) mx = fmaxf(mx, fmaxf(v[k][i], v[k][i + 1]));
     }
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -711,14 +719,50 @@ __global__ void __launch_bounds__(512) softmax_rows_vec_kernel(const bf16* __res
     }
   }
 }
+// Scalar fallback for fp32 logits (odd widths): three passes, one block per row.
+__global__ void softmax_rows_f32_kernel(const float* __restrict__ in, long long ld_in, bf16* __restrict__ out,
+                                        long long ld_out, int cols, float scale) {
+  const float* src = in + (size_t)blockIdx.x * ld_in;
+  bf16* dst = out + (size_t)blockIdx.x * ld_out;
+  __shared__ float red[32];
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, src[c]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += __expf((src[c] - mx) * scale);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) dst[c] = __float2bfloat16(__expf((src[c] - mx) * scale) * inv);
+}
+void launch_softmax_rows_f32(const float* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
+                             cudaStream_t stream) {
+  const bool vec_ok = cols % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec_ok && cols <= 512 * 8 * 4)
+    softmax_rows_vec_kernel<4, float><<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+  else if (vec_ok && cols <= 512 * 8 * 16)
+    softmax_rows_vec_kernel<16, float><<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+  else
+    softmax_rows_f32_kernel<<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+  LDN_CUDA(cudaGetLastError());
+}
 void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
                          cudaStream_t stream) {
   const bool vec_ok = cols % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (vec_ok && cols <= 512 * 8 * 4)
-    softmax_rows_vec_kernel<4><<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+    softmax_rows_vec_kernel<4, bf16><<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
   else if (vec_ok && cols <= 512 * 8 * 16)
-    softmax_rows_vec_kernel<16><<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
+    softmax_rows_vec_kernel<16, bf16><<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
   else
     softmax_rows_kernel<<<rows, 512, 0, stream>>>(in, ld_in, out, ld_out, cols, scale);
   LDN_CUDA(cudaGetLastError());

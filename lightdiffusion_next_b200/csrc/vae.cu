@@ -8,10 +8,11 @@
 //   Upsample (nearest 2x + conv3x3)                              VariationalAE.py:192-221
 //
 // Reuses the UNet's kernels: implicit-GEMM conv3x3 and GEMM on tcgen05, deterministic GroupNorm+SiLU. The mid-block
-// attention (N = h*w tokens, one head of 512) is done with two GEMMs around a row softmax on a materialised bf16 score
-// matrix per image (N x N: 512 MB at 1024^2, 8.6 GB at 2048^2 -- affordable with 180 GB of HBM and tensor-bound);
+// attention (N = h*w tokens, one head of 512) is done with two GEMMs around a row softmax on a materialised score
+// matrix per image, in query blocks of at most 1 GiB of fp32 logits (the whole N x N at 1024^2, 16 blocks at 2048^2);
 // V is produced transposed by swapping GEMM operands, and its bias is folded into proj_out's bias
 // (softmax rows sum to 1:  P (X Wv^T + 1 bv^T) Wp^T + bp = P X Wv^T Wp^T + (Wp bv + bp)).
+#include <algorithm>
 #include <cmath>
 #include <map>
 
@@ -130,7 +131,18 @@ struct VB {
     bf16* k = A.get<bf16>((size_t)B * Np * C, true);
     bf16* vt = A.get<bf16>((size_t)C * B * Np + 64, true);
     bf16* o = A.get<bf16>((size_t)T * C);
-    bf16* S = A.get<bf16>((size_t)Np * Np, true);
+    // The score matrix is materialised one QUERY BLOCK at a time, as FP32 LOGITS (QB x Np floats, capped at 1 GiB) plus the
+    // bf16 probabilities the softmax writes (QB x Np, 0.5 GiB): QB = N up to 16384 tokens = a 1024^2 image, 16 blocks of 4096
+    // queries at 2048^2 (where the whole N x N matrix would be 17 GB in fp32). Rows of a softmax are independent, so
+    // blocking changes nothing numerically; fp32 logits keep the exponent's argument exact where a bf16 logit of
+    // magnitude ~30 would carry an absolute error of ~0.06.
+    int QB = N;
+    {
+      const long long cap_rows = ((1LL << 28) / Np) / 128 * 128;  // 2^28 elements = 1 GiB of fp32
+      if (cap_rows >= 128 && cap_rows < N) QB = (int)cap_rows;
+    }
+    float* S = A.get<float>((size_t)QB * Np, true);
+    bf16* P = A.get<bf16>((size_t)QB * Np, true);  // pad columns N..Np-1 stay zero: the softmax writes the first N only
     bf16* out = A.get<bf16>((size_t)T * C);
     gn(p + ".norm", x, C, N, p + ".norm", false, sA);
     const float scale = 1.0f / sqrtf((float)C);
@@ -148,17 +160,21 @@ struct VB {
         a.out = vt + (size_t)b * Np; a.ldo = (long long)B * Np;
         gemm(p + ".vt", a);
       }
-      GemmArgs s;
-      s.A0 = q + (size_t)b * Np * C; s.lda0 = C; s.K0 = C; s.Wt = k + (size_t)b * Np * C; s.M = N; s.N = Np;
-      s.out = S; s.ldo = Np;
-      gemm(p + ".scores", s);
-      bf16* Sp = S;
-      add(p + ".softmax", [=](cudaStream_t st) { launch_softmax_rows(Sp, Np, Sp, Np, N, N, scale, st); });
-      GemmArgs pv;
-      pv.A0 = S; pv.lda0 = Np; pv.K0 = Np; pv.Wt = vt + (size_t)b * Np; pv.M = N; pv.N = C; pv.out = o + (size_t)b * N * C;
-      pv.ldo = C;
-      pv.wt_ld = (long long)B * Np;  // V^T rows are B*Np apart: describe the weight operand with its true leading dimension
-      gemm(p + ".pv", pv);
+      for (int q0 = 0; q0 < N; q0 += QB) {
+        const int rows = std::min(QB, N - q0);
+        GemmArgs s;
+        s.A0 = q + ((size_t)b * Np + q0) * C; s.lda0 = C; s.K0 = C; s.Wt = k + (size_t)b * Np * C; s.M = rows; s.N = Np;
+        s.out_f32 = S; s.ldo = Np;
+        gemm(p + ".scores", s);
+        float* Sp = S;
+        bf16* Pp = P;
+        add(p + ".softmax", [=](cudaStream_t st) { launch_softmax_rows_f32(Sp, Np, Pp, Np, rows, N, scale, st); });
+        GemmArgs pv;
+        pv.A0 = P; pv.lda0 = Np; pv.K0 = Np; pv.Wt = vt + (size_t)b * Np; pv.M = rows; pv.N = C;
+        pv.out = o + ((size_t)b * N + q0) * C; pv.ldo = C;
+        pv.wt_ld = (long long)B * Np;  // V^T rows are B*Np apart: describe the weight operand with its true leading dimension
+        gemm(p + ".pv", pv);
+      }
     }
     GemmArgs po;
     po.A0 = o; po.lda0 = C; po.K0 = C; po.Wt = e->W(1, p + ".proj_out.weight").b(); po.M = T; po.N = C;

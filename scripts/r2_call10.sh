@@ -1,0 +1,10 @@
+#!/bin/bash
+set -u
+O=gpurun_out/r2_call10; mkdir -p $O
+LDN_ATTN_D40=8 timeout -s KILL 200 python scripts/dev_attn40.py > $O/attn40_gen8.log 2>&1; echo "gen 8 rc=$?" | tee -a $O/summary.txt; cat $O/attn40_gen8.log | tail -12 | tee -a $O/summary.txt
+for poly in 0 8 4 2; do
+  LDN_ATTN_D40=8 LDN_ATTN_POLY=$poly timeout -s KILL 100 python scripts/dev_attn40.py --quick 2>&1 | tail -1 | tee -a $O/summary.txt
+done
+LDN_ATTN_D40=5 timeout -s KILL 100 python scripts/dev_attn40.py --quick 2>&1 | tail -1 | tee -a $O/summary.txt
+LDN_ATTN_D40=8 timeout -s KILL 300 python -m pytest tests/test_ops_gpu.py -q -k "attention" -p no:cacheprovider 2>&1 | tail -3 | tee -a $O/summary.txt
+LDN_ATTN_D40=8 timeout -s KILL 200 ncu --set full --clock-control none --import-source on -k regex:attn8 -s 2 -c 1 -o $O/attn8_full python scripts/dev_attn40.py --quick > $O/ncu_attn8.log 2>&1; echo "ncu rc=$?" | tee -a $O/summary.txt
