@@ -381,7 +381,7 @@ def main():
             "e2e": {"value": e2e_its, "unit": "it/s", "h2d_bytes_per_step": int(hx.numel() * 4),
                     "d2h_bytes_per_step": int(hout.numel() * 4), "ms_per_step": e2e_ms / K},
             "gpu_launches": int(K * (eng_launches(eng) + 1)),
-            "roofline": {"bound": "tensor", "kernel": "a5::attn5_tc_kernel (L0 self-attention, N=%d, d=40, B*H=%d)" % (N, B2 * H),
+            "roofline": {"bound": "tensor", "kernel": "a9::attn9_tc_kernel (L0 self-attention, N=%d, d=40, B*H=%d)" % (N, B2 * H),
                          "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                          "traffic": traffic, "peak_source": peaks["source"] + " (burst, kernel timed alone)",
                          "ms_per_launch": attn_ms, "launches_per_step": 5},

@@ -360,7 +360,13 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
     // 1.92 ms at N = 16384 -- and was dropped: the limiter was MMA issue, not softmax latency.)
     // generation 5 (P kept in tensor memory, TS-form P*V); generation 3 (P through shared memory) was retired once v5
     // had replaced it on every path
-    finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+    // generation 9 (attention9.cu: 64-key steps, two CTAs per SM) for long key sequences: 1.207 ms vs 1.319 ms at N = 16384,
+    // B*H = 16 (profiles/r2_attention9.md); generation 5 keeps the short ones (cross-attention, Nk = 77)
+    static const int d40_gen = getenv("LDN_ATTN_D40") ? atoi(getenv("LDN_ATTN_D40")) : 9;
+    if (d40_gen == 9 && a.Nk >= 512)
+      finish_attn9_plan(plan, a);
+    else
+      finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
   } else if (a.d == 80 && p.vt_head_stride == 96 && !a.causal) {
     finish_attn6_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // generation 6: ones-row V^T, P aliased over S in TMEM
   } else if (a.d == 128 && p.vt_head_stride == 128 && !a.causal && !force_v1) {
@@ -385,6 +391,7 @@ static void launch_attn_t(const AttnPlan& plan, cudaStream_t stream) {
 
 void launch_attn(const AttnPlan& plan, cudaStream_t stream) {
   if (plan.p.variant == 6) return launch_attn6(plan, stream);
+  if (plan.p.variant == 9) return launch_attn9(plan, stream);
   if (plan.p.variant == 5) return launch_attn5(plan, stream);
   if (plan.p.variant == 2) return launch_attn2(plan, stream);
   if (plan.p.bias) {

@@ -61,7 +61,8 @@ struct GemmParams {
   const bf16* residual;
   long long ldr;
   int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
-  int epi_opt;       // bit 0: 256-bit epilogue accesses, bit 1: packed-pair GEGLU arithmetic, bit 2: prefetching epilogue (persistent kernel)
+  int acc_stages;    // persistent kernel: accumulator stages in TMEM (2, or 1 when two CTAs share the SM and BN > 128)
+  int epi_opt;       // bit 0: 256-bit epilogue accesses, bit 1: packed-pair GEGLU arithmetic
   int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77),
             // 2 ReLU after the bias, 3 ReLU after the residual add (TAESD, src/AutoEncoders/taesd.py:39-63),
             // 4 GELU (tanh approximation) after the bias (Flux MLPs, src/BlackForest/Flux.py:283-294)
@@ -79,7 +80,8 @@ struct GemmPlan {
   dim3 grid;
   int smem_bytes;
   bool persistent = false;
-  int pgrid = 0;  // CTAs of the persistent kernel (<= SM count)
+  int pgrid = 0;  // CTAs of the persistent kernel (<= SM count x persist_occ)
+  int persist_occ = 1;  // persistent CTAs per SM (1 or 2)
   bool pair = false;  // CTA-pair kernel (gemm_pair.cu); pgrid is then an even CTA count
   int pair_smem_bytes = 0;
   bool pair_occ2 = false;  // one tile per CTA pair, two CTAs per SM (single accumulator stage)
@@ -179,6 +181,8 @@ void finish_attn5_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn5(const AttnPlan& plan, cudaStream_t stream);
 void finish_attn6_plan(AttnPlan& plan, int Nq, int Nk, int heads, int B);
 void launch_attn6(const AttnPlan& plan, cudaStream_t stream);
+void finish_attn9_plan(AttnPlan& plan, const AttnArgs& a);
+void launch_attn9(const AttnPlan& plan, cudaStream_t stream);
 void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)

@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
 // the epilogue warps drain the previous accumulator (two accumulator stages in TMEM: tmem_full / tmem_empty), and the
 // shared-memory ring is as deep as the whole SM allows. Short-K GEMMs (1x1 projections, K = 320) were dominated by the
 // per-CTA prologue + pipeline ramp of the one-tile-per-CTA kernel.
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_persist_kernel(const __grid_constant__ GemmParams p) {
+template <int kOcc>
+__global__ void __launch_bounds__(kGemmThreads, kOcc) gemm_tc_persist_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -196,7 +197,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_persist_kernel(const 
   uint64_t* tfull_bar = empty_bar + stages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained (8 arrivals: one per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const uint32_t acc_stride = (uint32_t)p.tmem_cols / 2;
+  // two accumulator stages (tile i + 1 accumulates while tile i drains), or one when two CTAs share the SM and a tile
+  // needs more than 128 of the CTA's 256 columns (the other CTA then fills the tensor pipe during the drain)
+  const bool two_acc = p.acc_stages == 2;
+  const uint32_t acc_stride = two_acc ? (uint32_t)p.tmem_cols / 2 : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA0);
@@ -281,8 +285,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_persist_kernel(const 
       const int z = w / mn_tiles;
       const int kc_begin = z * p.chunks_per_split;
       const int kc_end = min(p.num_k_chunks, kc_begin + p.chunks_per_split);
-      const int acc = tl & 1;
-      mbar_wait(&tempty_bar[acc], (((uint32_t)tl >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator stage
+      const int acc = two_acc ? (tl & 1) : 0;
+      mbar_wait(&tempty_bar[acc], ((two_acc ? ((uint32_t)tl >> 1) : (uint32_t)tl) & 1u) ^ 1u);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
@@ -338,15 +342,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_persist_kernel(const 
           out_row = (m / p.row_head_dim) * p.row_head_slot + (m % p.row_head_dim);
         batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
       }
-      const int acc = tl & 1;
+      const int acc = two_acc ? (tl & 1) : 0;
+      const uint32_t acc_parity = (two_acc ? ((uint32_t)tl >> 1) : (uint32_t)tl) & 1u;
       const uint32_t t_lane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      if (p.epi == 0 && p.splits == 1 && (p.epi_opt & 5) == 5) {
-        gemm_epilogue_tile_prefetch(p, BN, n0, out_row, batch, t_lane, ehalf, &tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
-      } else {
-        mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
-        tc_fence_after();
-        gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
-      }
+      mbar_wait(&tfull_bar[acc], acc_parity);
+      tc_fence_after();
+      gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -495,7 +496,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.head_dim = a.head_dim;
   p.head_slot = a.head_slot;
   p.act = a.act;
-  static const int epi_opt = getenv("LDN_GEMM_EPI_OPT") ? atoi(getenv("LDN_GEMM_EPI_OPT")) : 7;
+  static const int epi_opt = getenv("LDN_GEMM_EPI_OPT") ? atoi(getenv("LDN_GEMM_EPI_OPT")) : 3;
   p.epi_opt = epi_opt;
   {  // 256-bit epilogue accesses need 32-byte aligned rows
     const long long ldo_out = a.epi == 1 ? a.ldo : a.ldo;
@@ -551,18 +552,37 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   // long-K problems (3x3 convs) two independent CTAs per SM keep the tensor pipe busier (measured 1018 vs 796 TFLOP/s)
   static const int persist_max_chunks = getenv("LDN_GEMM_PERSIST_MAX") ? atoi(getenv("LDN_GEMM_PERSIST_MAX")) : 20;
   plan.persistent = !force_v1 && p.chunks_per_split <= persist_max_chunks;
+  // Two persistent CTAs per SM (LDN_GEMM_OCC2): sixteen epilogue warps per SM instead of eight.  The short-K GEMMs are bound
+  // by their epilogue (TMEM drain + residual fetch + stores, all latency), not by the tensor pipe.
+  // Measured (scripts/dev_gemm_graph.py, profiles/r2_gemm_occ2.md): 28.8 -> 24.9 us for the 320 x 320 projections with a residual
+  // (M = 32768), 18.8 -> 16.8 us at level 1; the GEGLU / QKV projections (no residual read, wide N) lose 5-15 %, so mode 2
+  // (default) applies it to residual GEMMs with K <= 640 only.  0: never, 1: every persistent GEMM.
+  static const int occ2_mode = getenv("LDN_GEMM_OCC2") ? atoi(getenv("LDN_GEMM_OCC2")) : 2;
+  const bool occ2 = occ2_mode == 1 || (occ2_mode == 2 && a.residual && a.epi == 0 && p.num_k_chunks <= 10 && m_rows >= 8192);
+  p.acc_stages = 2;
+  plan.persist_occ = 1;
   if (plan.persistent) {
     int acc_stride = 32;
     while (acc_stride < BN) acc_stride <<= 1;
-    p.tmem_cols = 2 * acc_stride;  // <= 512
-    int pst = (225 * 1024 - 2048) / stage_bytes;
-    if (pst > 8) pst = 8;
-    const int total_chunks = p.chunks_per_split;
-    (void)total_chunks;
-    p.stages = pst;
-    plan.smem_bytes = pst * stage_bytes + 1024 + 512;
     const int total = (int)(plan.grid.x * plan.grid.y * plan.grid.z);
-    plan.pgrid = total < 148 ? total : 148;
+    if (occ2 && total > 148) {
+      plan.persist_occ = 2;
+      p.acc_stages = 2 * acc_stride <= 256 ? 2 : 1;
+      p.tmem_cols = p.acc_stages * acc_stride;  // <= 256
+      int pst = (112 * 1024 - 2048) / stage_bytes;
+      if (pst > 8) pst = 8;
+      if (pst < 2) pst = 2;
+      p.stages = pst;
+      plan.smem_bytes = pst * stage_bytes + 1024 + 512;
+      plan.pgrid = total < 296 ? total : 296;
+    } else {
+      p.tmem_cols = 2 * acc_stride;  // <= 512
+      int pst = (225 * 1024 - 2048) / stage_bytes;
+      if (pst > 8) pst = 8;
+      p.stages = pst;
+      plan.smem_bytes = pst * stage_bytes + 1024 + 512;
+      plan.pgrid = total < 148 ? total : 148;
+    }
   }
   // CTA-pair variant (gemm_pair.cu): 256 x BN tiles, each CTA loads half of the B tile
   static const int pair_mode = getenv("LDN_GEMM_PAIR") ? atoi(getenv("LDN_GEMM_PAIR")) : 0;
@@ -608,10 +628,14 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   } else if (plan.persistent) {
     static bool attr2 = false;
     if (!attr2) {
-      LDN_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      LDN_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      LDN_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
       attr2 = true;
     }
-    gemm_tc_persist_kernel<<<plan.pgrid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    if (plan.persist_occ == 2)
+      gemm_tc_persist_kernel<2><<<plan.pgrid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    else
+      gemm_tc_persist_kernel<1><<<plan.pgrid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
   } else {
     gemm_tc_kernel<<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
   }

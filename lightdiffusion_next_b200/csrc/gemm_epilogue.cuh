@@ -53,120 +53,6 @@ __device__ __forceinline__ float2 geglu2(float2 a, float2 g) {
   return fmul2(a, fmul2(g, phi));
 }
 
-// Plain epilogue (epi == 0) of one 16-column chunk whose accumulator values are already in registers: bias, time-embedding
-// row bias, activation, column gate, residual (`w`: the 16 bf16 residual values of this chunk, fetched by the caller), store.
-__device__ __forceinline__ void epi0_finish_chunk(const GemmParams& p, const int n, const long long out_row, const int batch,
-                                                  const uint32_t* v, const uint32_t* w) {
-  float f[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-  if (p.bias) {
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-      f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-    }
-  }
-  if (p.rowbias) {
-    const float* rb = p.rowbias + (long long)batch * p.ld_rowbias + n;
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      const float4 bv = *reinterpret_cast<const float4*>(rb + i);
-      f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-    }
-  }
-  if (p.act == 1) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = f[i] / (1.0f + __expf(-1.702f * f[i]));
-  } else if (p.act == 2) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-  } else if (p.act == 4) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float x = f[i];
-      const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
-      f[i] = __fdividef(x, 1.0f + __expf(-2.0f * u));
-    }
-  }
-  if (p.colgate) {
-    const float* gp = p.colgate + (long long)batch * p.ld_colgate + n;
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      const float4 gv = *reinterpret_cast<const float4*>(gp + i);
-      f[i] *= gv.x; f[i + 1] *= gv.y; f[i + 2] *= gv.z; f[i + 3] *= gv.w;
-    }
-  }
-  if (p.residual) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      f[2 * i] += bf16_lo(w[i]);
-      f[2 * i + 1] += bf16_hi(w[i]);
-    }
-  }
-  if (p.act == 3) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-  }
-  if (p.out_f32) {
-    float4* op = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldo + n);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-  } else if (p.head_dim == 0) {
-    uint32_t o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-    st_global_256(p.out + out_row * p.ldo + n, o);
-  } else {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      int col = n + h * 8;
-      col = (col / p.head_dim) * p.head_slot + (col % p.head_dim);
-      uint4 ov;
-      ov.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
-      ov.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
-      ov.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
-      ov.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
-      *reinterpret_cast<uint4*>(p.out + out_row * p.ldo + col) = ov;
-    }
-  }
-}
-
-// Latency-hiding form of the plain epilogue for the persistent kernel (one CTA per SM: registers are plentiful).
-// The short-K GEMMs (K = 320: five chunks per tile) are bound by their epilogue, and the old loop exposed, per 16-column
-// chunk, one TMEM read and one global residual read (~1 us from L2) back to back.  Here every residual chunk of the tile
-// row (<= 8 x 32 bytes per thread) is requested BEFORE the accumulator barrier is waited for -- the addresses do not depend
-// on the accumulator -- and the TMEM read of chunk k+1 is in flight while chunk k is finished and stored.
-// Requires the 256-bit access path (32-byte aligned rows); returns after the last TMEM read has completed.
-__device__ __forceinline__ void gemm_epilogue_tile_prefetch(const GemmParams& p, const int BN, const int n0,
-                                                            const long long out_row, const int batch, const uint32_t t_lane,
-                                                            const int ehalf, uint64_t* acc_bar, const uint32_t acc_parity) {
-  const int c_first = ehalf * 16;
-  uint32_t wres[8][8];
-  if (p.residual) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c_first + k * 32;
-      if (c < BN && out_row >= 0 && n0 + c < p.N) ld_global_256(p.residual + out_row * p.ldr + n0 + c, wres[k]);
-    }
-  }
-  mbar_wait(acc_bar, acc_parity);
-  tc_fence_after();
-  uint32_t v[2][16];
-  if (c_first < BN) tmem_ld16(t_lane + (uint32_t)c_first, v[0]);
-  tmem_ld_wait();
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = c_first + k * 32;
-    if (c < BN) {
-      if (c + 32 < BN) tmem_ld16(t_lane + (uint32_t)(c + 32), v[(k + 1) & 1]);
-      if (out_row >= 0 && n0 + c < p.N) epi0_finish_chunk(p, n0 + c, out_row, batch, v[k & 1], wres[k]);
-      __syncwarp();
-      tmem_ld_wait();
-    }
-  }
-}
-
 // Drains one 128 x BN fp32 accumulator tile from TMEM (columns starting at t_lane) through the fused epilogue.
 // Executed by the 8 epilogue warps; `ehalf` selects which alternate 16-column chunks this warp handles.
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const int BN, const int n0, const long long out_row,
