@@ -338,14 +338,14 @@ def unet_forward(sd: Dict[str, Tensor], x: Tensor, t: Tensor, context: Tensor, c
     return _conv(sd, "out.2", F.silu(_gn(sd, "out.0", h, 1e-5)))
 
 
-def apply_model(sd, x: Tensor, sigma: Tensor, context: Tensor, tables=None) -> Tensor:
+def apply_model(sd, x: Tensor, sigma: Tensor, context: Tensor, tables=None, cfg=SD15) -> Tensor:
     """BaseModel.apply_model, src/Model/ModelBase.py:72-133 with EPS scaling (sampling.py:26-56):
     denoised = x - unet(x / sqrt(sigma^2+1), timestep(sigma), ctx) * sigma."""
     _, log_sigmas = tables or make_sigma_tables()
     s = sigma.view(-1, 1, 1, 1)
     xc = x / (s ** 2 + 1.0) ** 0.5
     t = timestep_index(sigma, log_sigmas).float()
-    eps = unet_forward(sd, xc, t, context)
+    eps = unet_forward(sd, xc, t, context, cfg)
     return x - eps * s
 
 

@@ -8,8 +8,9 @@ from oracle import sd15_oracle as O
 
 
 class FakeEngine:
-    def __init__(self, sd, vae_sd=None, clip_sd=None):
+    def __init__(self, sd, vae_sd=None, clip_sd=None, unet_cfg=None):
         self.sd = sd
+        self.unet_cfg = unet_cfg or O.SD15  # host-logic tests that pin nothing to a golden use a narrow UNet (conftest.TINY_UNET)
         self.vae_sd = vae_sd
         self.clip_sd = clip_sd
         self.device = torch.device("cpu")
@@ -26,7 +27,7 @@ class FakeEngine:
         self.context_uploads += 1
 
     def denoise(self, x, sigma, out=None):
-        r = O.apply_model(self.sd, x, sigma, self.ctx, self.tables)
+        r = O.apply_model(self.sd, x, sigma, self.ctx, self.tables, self.unet_cfg)
         self.denoise_calls += 1
         if out is not None:
             out.copy_(r)

@@ -104,15 +104,17 @@ sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests")
 from lightdiffusion_next_b200 import distributed as D, sampling as S
 from lightdiffusion_next_b200.synth import unet_shapes, synth_tensor
 from fake_engine import FakeEngine
+from conftest import TINY_UNET
+from oracle import sd15_oracle as O
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 torch.set_num_threads(4)
-shapes = {{k: v for k, v in unet_shapes().items()}}
+shapes = O.unet_param_shapes(TINY_UNET)  # narrow UNet of the SD1.5 topology: this test pins host logic, not numerics
 sd = D.broadcast_state_dict(shapes, synth_tensor, "cpu")
 # rank 1 received exactly what rank 0 generated
 chk = synth_tensor("out.2.weight", shapes["out.2.weight"])
 assert torch.equal(sd["out.2.weight"], chk)
-eng = FakeEngine(sd)
+eng = FakeEngine(sd, unet_cfg=TINY_UNET)
 g = torch.Generator().manual_seed(1234)
 pos = torch.randn(1, 77, 768, generator=g); neg = torch.randn(1, 77, 768, generator=g)
 B = 3  # ragged over 2 ranks
@@ -125,11 +127,15 @@ dist.barrier(); dist.destroy_process_group()
 """
 
 
-def test_two_rank_gloo_sharded_sampling_equals_single_process(tmp_path, unet_sd):
+def test_two_rank_gloo_sharded_sampling_equals_single_process(tmp_path):
     """world_size=2 over gloo on CPU: weights broadcast, noise scattered, latents gathered; the sharded batch equals
     the single-process batch bit-for-bit in structure (same noise rows) and numerically in value."""
     from lightdiffusion_next_b200 import sampling as S
+    from lightdiffusion_next_b200.synth import synth_tensor
     from fake_engine import FakeEngine
+    from conftest import TINY_UNET
+    from oracle import sd15_oracle as O
+    tiny_sd = {k: synth_tensor(k, shp) for k, shp in O.unet_param_shapes(TINY_UNET).items()}
     out = str(tmp_path / "sharded.pt")
     script = tmp_path / "worker.py"
     script.write_text(_WORKER.format(root=ROOT, out=out))
@@ -142,11 +148,11 @@ def test_two_rank_gloo_sharded_sampling_equals_single_process(tmp_path, unet_sd)
     g = torch.Generator().manual_seed(1234)
     pos = torch.randn(1, 77, 768, generator=g)
     neg = torch.randn(1, 77, 768, generator=g)
-    single = S.sample(FakeEngine(unet_sd), 42, 2, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg,
+    single = S.sample(FakeEngine(tiny_sd, unet_cfg=TINY_UNET), 42, 2, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg,
                       {"samples": torch.zeros(3, 4, 16, 16)})[0]["samples"]
     assert sharded["dpmpp_2m"].shape == single.shape
     assert rel(sharded["dpmpp_2m"], single) < 1e-5
-    single_a = S.sample(FakeEngine(unet_sd), 42, 2, 7.0, "euler_ancestral_cfgpp", "karras", pos, neg,
+    single_a = S.sample(FakeEngine(tiny_sd, unet_cfg=TINY_UNET), 42, 2, 7.0, "euler_ancestral_cfgpp", "karras", pos, neg,
                         {"samples": torch.zeros(3, 4, 8, 8)})[0]["samples"]
     assert rel(sharded["euler_a"], single_a) < 1e-5   # exact noise rows: shard-invariant per-step draws
     assert rel(single_a[0], single_a[1]) > 0.5        # ... and different images get different noise

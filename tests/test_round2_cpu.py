@@ -152,7 +152,7 @@ class RecordedTokenizer:
         return {"l": [list(zip(r.tolist(), w.tolist())) for r, w in zip(self.g[f"{n}_ids"], self.g[f"{n}_weights"])]}
 
 
-def test_pipeline_prompt_str_surface(unet_sd):
+def test_pipeline_prompt_str_surface(tiny_unet_sd):
     """pipeline(engine, prompt: str, w, h, ...) == tokenizer -> CLIPTextEncode x2 -> KSampler -> VAEDecode composed by hand
     (src/user/pipeline.py:31-55, 278-372), with the reference's argument names; out-of-scope flags raise."""
     from fake_engine import FakeEngine
@@ -161,7 +161,8 @@ def test_pipeline_prompt_str_surface(unet_sd):
     from oracle import sd15_oracle as O
     vsd = O.synth_state_dict(O.vae_decoder_param_shapes(), seed=4321)
     csd = O.synth_state_dict(O.clip_param_shapes(), seed=777)
-    eng = FakeEngine(unet_sd, vsd, csd)
+    from conftest import TINY_UNET
+    eng = FakeEngine(tiny_unet_sd, vsd, csd, unet_cfg=TINY_UNET)  # composition test: a narrow UNet stands in for the denoiser
     g = torch.load(os.path.join(GOLDEN, "clip_small.pt"))
     tok = RecordedTokenizer(g)
     prompt, negative = "a (red:1.3) cube on a (blue:0.7) sphere", "a photograph of an astronaut riding a horse"
