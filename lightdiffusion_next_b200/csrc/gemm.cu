@@ -541,6 +541,14 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
       if (p.conv) p.rows_per_batch = a.H * a.W;
     }
   }
+  // Experiment (off): a grid of at most one CTA per SM can never have two CTAs resident, so it could take the whole SM's
+  // shared memory for a deeper ring.  The level-2 convs (128 tiles) did not get faster: their ~935 clk per 36 KB chunk is
+  // the SM's L2 -> shared-memory ingest rate, not the TMA round trip.
+  static const int deep_single = getenv("LDN_GEMM_DEEP_SINGLE") ? atoi(getenv("LDN_GEMM_DEEP_SINGLE")) : 0;  // measured: no gain (L2 convs 85.7 -> 96.1 us, profiles/r2_experiments.md section 11)
+  if (deep_single && (long long)plan.grid.x * plan.grid.y * plan.grid.z <= 148) {
+    stages = (225 * 1024 - 1024 - 256) / stage_bytes;
+    if (stages > 8) stages = 8;
+  }
   if (stages > p.chunks_per_split) stages = p.chunks_per_split;
   p.stages = stages;
   plan.smem_bytes = stages * stage_bytes + 1024 + 256;
