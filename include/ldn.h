@@ -131,7 +131,11 @@ int ldn_conv3x3_bf16(const void* x, const void* Wt, int B, int H, int W, int Cin
 /* Q: [B*Nq, heads*slot], K: [B*nk_pad, heads*slot], Vt: [vt_rows, B*nk_pad] (all bf16); out: [B*Nq, heads*d].
  * vt_head_stride: rows per head in Vt; 0 or d = plain V^T. For d = 40 (stride 48) and d = 80 (stride 96) the padded
  * layout selects the fastest kernels and requires row d of every head to be all ones (remaining pad rows zero): the
- * softmax row sum is then computed by the tensor core. */
+ * softmax row sum is then computed by the tensor core.
+ * causal: bit 0 = causal mask; bit 1 (d = 40 with the padded layout only) = FOLDED operands: Q already carries
+ * scale * log2(e) and column 40 of every K head slot holds 1.0 -- the long-sequence kernel then keeps the running offset
+ * -m in column 40 of its Q tile, so the tensor core delivers scaled, offset scores and the softmax needs no scale-subtract
+ * (`scale` is ignored; this is how the UNet program calls its level-0 self-attention). */
 int ldn_attention_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* Vt, int64_t ldvt,
                        int64_t vt_rows, int vt_head_stride, int B, int heads, int Nq, int Nk, int nk_pad, int d,
                        int slot, int causal, float scale, void* out, int64_t ldo, void* stream);

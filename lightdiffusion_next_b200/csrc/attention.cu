@@ -318,7 +318,7 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
   p.dv = dp;
   p.slot = a.slot;
   p.causal = a.causal;
-  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.scale_log2 = a.fold ? 1.0f : a.scale * 1.4426950408889634f;  // folded operands: Q already carries scale * log2(e)
   p.out = a.out;
   p.ldo = a.ldo;
   p.bias = a.bias;
@@ -363,10 +363,13 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
     // generation 9 (attention9.cu: 64-key steps, two CTAs per SM) for long key sequences: 1.207 ms vs 1.319 ms at N = 16384,
     // B*H = 16 (profiles/r2_attention9.md); generation 5 keeps the short ones (cross-attention, Nk = 77)
     static const int d40_gen = getenv("LDN_ATTN_D40") ? atoi(getenv("LDN_ATTN_D40")) : 9;
-    if (d40_gen == 9 && a.Nk >= 512)
+    static const int fold_on = getenv("LDN_ATTN_FOLD") ? atoi(getenv("LDN_ATTN_FOLD")) : 1;
+    if (d40_gen == 9 && a.Nk >= 512) {
       finish_attn9_plan(plan, a);
-    else
+      p.fold = (a.fold && fold_on) ? 1 : 0;  // (other kernels ignore the ones column: column 40 of Q is zero in global memory)
+    } else {
       finish_attn5_plan(plan, a.Nq, a.Nk, a.heads, a.B);
+    }
   } else if (a.d == 80 && p.vt_head_stride == 96 && !a.causal) {
     finish_attn6_plan(plan, a.Nq, a.Nk, a.heads, a.B);  // generation 6: ones-row V^T, P aliased over S in TMEM
   } else if (a.d == 128 && p.vt_head_stride == 128 && !a.causal && !force_v1) {

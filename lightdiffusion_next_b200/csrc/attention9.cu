@@ -38,7 +38,7 @@ static constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 using namespace asm_sm;
 
-template <uint32_t kPolyMask>
+template <uint32_t kPolyMask, bool kFold>
 __global__ void __launch_bounds__(kThreads, 2) attn9_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -205,36 +205,82 @@ __global__ void __launch_bounds__(kThreads, 2) attn9_tc_kernel(const __grid_cons
         mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])));
         mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        // lazy rescale: only when this row's max outgrew the offset baked into O by more than 2^8.  S(j) was committed
-        // behind P*V(j - 1), so every earlier P*V has landed and none is in flight until this thread arrives on p_full.
-        const bool need = mx > m_used + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = need ? mx : m_used;
-          const float f = ex2m(m_used - m_new);  // 1 for rows that do not need it
+      if constexpr (kFold) {
+        // Folded variant: the MMA already delivered s' = s * scale * log2(e) - m_used (Q is pre-scaled; column 40 of the Q
+        // tile holds -m_used of the row and column 40 of K holds ones), so the common path has no scale-subtract at all.
+        // When the row maximum outgrows the offset (always at step 0, where m_used = 0), the offset is moved: subtract the
+        // (bf16-exact) increment from the scores in registers, rescale O, and publish the new -m to the Q tile in shared
+        // memory for the S MMAs to come (none is in flight: S(j + 1) is issued behind this thread's arrival on p_full).
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        const bool upd = (j == 0) || (mx > kRescaleThreshold);
+        if (__any_sync(0xffffffffu, upd)) {
+          const float m_new = upd ? __bfloat162float(__float2bfloat16_rn(m_used + mx)) : m_used;
+          const float delta = m_new - m_used;  // exact: both are bf16 values of similar magnitude
           m_used = m_new;
+          if (j > 0) {
+            const float f = ex2m(-delta);  // 1 for rows that do not move
 #pragma unroll
-          for (int c = 0; c < kDV; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_o + (uint32_t)c, v);
-            tmem_ld_wait();
+            for (int c = 0; c < kDV; c += 16) {
+              uint32_t v[16];
+              tmem_ld16(tmem_o + (uint32_t)c, v);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            tmem_st16(tmem_o + (uint32_t)c, v);
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st16(tmem_o + (uint32_t)c, v);
+            }
+          }
+          const float2 nd = make_float2(-delta, -delta);
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const float2 e = fadd2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), nd);
+            sv[i] = __float_as_uint(e.x);
+            sv[i + 1] = __float_as_uint(e.y);
+          }
+          // row r of the 128B-swizzled tile: 16-byte chunk 5 (columns 40..47) lands at chunk 5 ^ (r % 8)
+          const __nv_bfloat16 nm = __float2bfloat16_rn(-m_new);
+          *reinterpret_cast<__nv_bfloat16*>(q_smem + (size_t)t * q_bytes + (size_t)r * 128 + (size_t)((5 ^ (r & 7)) << 4)) = nm;
+          fence_proxy_async_smem();
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w[4];
+          exp8_pack_raw(sv + c * 8, kPolyMask == 0x10000u ? 2 : (int)((mask8 >> c) & 1u), w);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tmem_s + (uint32_t)(c * 4)), "r"(w[0]),
+                       "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
+        }
+      } else {
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          // lazy rescale: only when this row's max outgrew the offset baked into O by more than 2^8.  S(j) was committed
+          // behind P*V(j - 1), so every earlier P*V has landed and none is in flight until this thread arrives on p_full.
+          const bool need = mx > m_used + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? mx : m_used;
+            const float f = ex2m(m_used - m_new);  // 1 for rows that do not need it
+            m_used = m_new;
+#pragma unroll
+            for (int c = 0; c < kDV; c += 16) {
+              uint32_t v[16];
+              tmem_ld16(tmem_o + (uint32_t)c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st16(tmem_o + (uint32_t)c, v);
+            }
           }
         }
-      }
-      const float m_off = m_used;
+        const float m_off = m_used;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t w[4];
-        exp8_pack(sv + c * 8, sc, -m_off, kPolyMask == 0x10000u ? 2 : (int)((mask8 >> c) & 1u), w);
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tmem_s + (uint32_t)(c * 4)), "r"(w[0]),
-                     "r"(w[1]), "r"(w[2]), "r"(w[3])
-                     : "memory");
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w[4];
+          exp8_pack(sv + c * 8, sc, -m_off, kPolyMask == 0x10000u ? 2 : (int)((mask8 >> c) & 1u), w);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tmem_s + (uint32_t)(c * 4)), "r"(w[0]),
+                       "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -281,15 +327,22 @@ __global__ void __launch_bounds__(kThreads, 2) attn9_tc_kernel(const __grid_cons
 }  // namespace a9
 using namespace a9;
 
-template <uint32_t kPolyMask>
-static void launch_attn9_t(const AttnPlan& plan, cudaStream_t stream) {
+template <uint32_t kPolyMask, bool kFold>
+static void launch_attn9_t2(const AttnPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDN_CUDA(cudaFuncSetAttribute(attn9_tc_kernel<kPolyMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(attn9_tc_kernel<kPolyMask, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr_set = true;
   }
-  attn9_tc_kernel<kPolyMask><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
+  attn9_tc_kernel<kPolyMask, kFold><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.p);
   LDN_CUDA(cudaGetLastError());
+}
+template <uint32_t kPolyMask>
+static void launch_attn9_t(const AttnPlan& plan, cudaStream_t stream) {
+  if (plan.p.fold)
+    launch_attn9_t2<kPolyMask, true>(plan, stream);
+  else
+    launch_attn9_t2<kPolyMask, false>(plan, stream);
 }
 
 // kPolyMask: bit c (even steps) / bit 8 + c (odd steps) set = chunk c of a step's 64 scores takes the polynomial ex2

@@ -50,6 +50,34 @@ __device__ __forceinline__ void exp8_pack(const uint32_t* s, float sc, float neg
     w[k] = pack_bf16x2(e.x, e.y);
   }
 }
+
+// exp2 of eight scores that already carry scale and offset (attention9.cu, folded variant: the tensor core produced
+// s * scale * log2(e) - m through an extra operand column), packed to 4 bf16x2 words.  Same modes as exp8_pack.
+__device__ __forceinline__ void exp8_pack_raw(const uint32_t* s, int mode, uint32_t* w) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 e = make_float2(__uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1]));
+    if (mode == 1) {
+      e.x = fmaxf(e.x, -125.0f);
+      e.y = fmaxf(e.y, -125.0f);
+      const float2 t = fadd2(e, make_float2(12582912.0f, 12582912.0f));
+      const float2 n = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
+      const float2 f = ffma2(n, make_float2(-1.0f, -1.0f), e);
+      float2 q = ffma2(f, make_float2(0.0555041086f, 0.0555041086f), make_float2(0.2402265070f, 0.2402265070f));
+      q = ffma2(q, f, make_float2(0.6931471806f, 0.6931471806f));
+      q = ffma2(q, f, make_float2(1.0f, 1.0f));
+      e.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+      e.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+    } else if (mode == 0) {
+      e.x = ex2m(e.x);
+      e.y = ex2m(e.y);
+    } else {
+      e.x *= 0.001f;
+      e.y *= 0.001f;
+    }
+    w[k] = pack_bf16x2(e.x, e.y);
+  }
+}
 __device__ __forceinline__ uint32_t pin3(uint32_t v) {
   asm volatile("mov.u32 %0, %0;" : "+r"(v));
   return v;

@@ -80,7 +80,7 @@ extern "C" int ldn_attention_bf16(const void* Q, int64_t ldq, const void* K, int
   AttnArgs a;
   a.Q = (const bf16*)Q; a.ldq = ldq; a.K = (const bf16*)K; a.ldk = ldk; a.Vt = (const bf16*)Vt; a.ldvt = ldvt;
   a.vt_rows = vt_rows; a.vt_head_stride = vt_head_stride; a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.nk_pad = nk_pad; a.d = d; a.slot = slot;
-  a.causal = causal; a.scale = scale; a.out = (bf16*)out; a.ldo = ldo;
+  a.causal = causal & 1; a.fold = (causal & 2) ? 1 : 0; a.scale = scale; a.out = (bf16*)out; a.ldo = ldo;
   AttnPlan plan = make_attn_plan(a);
   launch_attn(plan, (cudaStream_t)stream);
   LDN_API_END

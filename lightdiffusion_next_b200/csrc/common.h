@@ -145,6 +145,7 @@ struct AttnParams {
   int variant;       // 1: attention.cu (one query tile per CTA); 2: attention2.cu (two query tiles, d <= 64); 5: attention5.cu (d = 40, S / O / P in TMEM); 6: attention6.cu (d = 80)
   int pingpong;      // variant 3: softmax warpgroups alternate on the MUFU
   int p_bufs;        // variant 3: P buffers per query tile in shared memory (1 or 2)
+  int fold;          // variant 9: Q arrives pre-scaled by scale * log2(e) and column d of every K row holds 1.0: the kernel keeps -m in column d of its Q tile
   int poly_mod;      // variant 2: every poly_mod-th group of 8 exponentials runs on the FMA pipes (0 = all MUFU)
   bf16* out;         // [B*Nq, heads*d]
   long long ldo;
@@ -168,6 +169,7 @@ struct AttnArgs {
   int kv_batch_stride = 0;  // K rows per batch (0 = nk_pad)
   int vt_head_stride = 0;   // rows per head in Vt (0 = d). d = 40 with stride 48 / d = 80 with stride 96: row d of every head must be all ones
   int causal = 0;
+  int fold = 0;             // d = 40 only: Q is pre-scaled by scale * log2(e) and column 40 of every K slot holds 1.0 (see attention9.cu)
   float scale;
   bf16* out;
   long long ldo;

@@ -74,6 +74,17 @@ __global__ void fill_ones_rows_kernel(bf16* __restrict__ vt, int heads, long lon
   }
 }
 
+// Folded attention operands (attention9.cu): column d of every head slot in the K half of a [Q | K] buffer holds 1.0, so that
+// column d of the kernel's Q tile (where it keeps -m of the row) is added to every score by the tensor core.
+__global__ void fill_k_ones_kernel(bf16* __restrict__ qk, long long rows, long long ld, int heads, int slot, int k_off, int col) {
+  const long long total = rows * heads;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / heads;
+    const int h = (int)(i % heads);
+    qk[row * ld + k_off + h * slot + col] = __float2bfloat16(1.0f);
+  }
+}
+
 }  // namespace ldn
 
 using namespace ldn;
@@ -90,6 +101,7 @@ struct STW {
   std::string prefix;
   int C, d, slot;
   bf16* Wqk = nullptr;    // [2C, C]
+  float* qk_gate = nullptr;  // d = 40: per-column multiplier of the [Q | K] projection, scale * log2(e) on the Q half (attention9.cu, folded operands)
   bf16* Wff1 = nullptr;   // interleaved [8C, C]
   float* bff1 = nullptr;  // interleaved [8C]
   int ff_bn = 256;
@@ -270,6 +282,14 @@ void unet_finalize(ldn_engine* e, cudaStream_t stream) {
     LDN_CUDA(cudaMemcpyAsync(s.Wqk, wq.p, (size_t)C * C * sizeof(bf16), cudaMemcpyDeviceToDevice, stream));
     LDN_CUDA(cudaMemcpyAsync(s.Wqk + (size_t)C * C, wk.p, (size_t)C * C * sizeof(bf16), cudaMemcpyDeviceToDevice,
                              stream));
+    if (s.d == 40) {
+      std::vector<float> gate((size_t)2 * C, 1.0f);
+      const float qs = (1.0f / sqrtf((float)s.d)) * 1.4426950408889634f;
+      for (int i = 0; i < C; ++i) gate[i] = qs;
+      s.qk_gate = U.arena.get<float>((size_t)2 * C);
+      LDN_CUDA(cudaMemcpyAsync(s.qk_gate, gate.data(), gate.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+      LDN_CUDA(cudaStreamSynchronize(stream));  // `gate` is a pageable temporary
+    }
     const DevTensor& wf = e->W(0, tb + ".ff.net.0.proj.weight");
     const DevTensor& bf = e->W(0, tb + ".ff.net.0.proj.bias");
     LDN_CHECK(wf.shape[0] == 8 * C && wf.shape[1] == C, "GEGLU proj shape mismatch at " + s.prefix);
@@ -455,6 +475,7 @@ struct Builder {
       GemmArgs a;
       a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = s.Wqk; a.M = T; a.N = 2 * C;
       a.out = QK; a.ldo = ldqk; a.head_dim = s.d; a.head_slot = s.slot;
+      a.colgate = s.qk_gate; a.ld_colgate = 0;  // d = 40: Q leaves the projection already scaled by scale * log2(e)
       gemm(tb + ".attn1.qk", a);
       const bool ones = sVt40[level] != nullptr;  // V^T with a ones row per head: 48 (d = 40) / 96 (d = 80) rows
       const int hs = s.d == 40 ? 48 : 96;
@@ -469,6 +490,7 @@ struct Builder {
       at.Vt = Vt; at.ldvt = Tld; at.vt_rows = ones ? U.heads * hs : C;
       at.vt_head_stride = ones ? hs : 0;
       at.B = B; at.heads = U.heads; at.Nq = N; at.Nk = N; at.nk_pad = N; at.d = s.d; at.slot = s.slot;
+      at.fold = s.qk_gate ? 1 : 0;
       if (N % 8 != 0) {
         LDN_CHECK(!ones, "head-dim-40 level with a token count that is not a multiple of 8");
         // per-batch key offsets b*N would start TMA boxes at non-16B-aligned addresses: re-lay V^T with padded batches
@@ -586,6 +608,12 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
       bd.sQK.push_back(U.attn_level[level] ? A.get<bf16>((size_t)B * h * w * 2 * U.heads * slot, true) : nullptr);
       bf16* vt40 = nullptr;
       const int dh = c / U.heads;
+      if (U.attn_level[level] && dh == 40) {
+        // the K half's pad column 40 is never written by the projections (they scatter columns 0..39 of every head slot)
+        fill_k_ones_kernel<<<64, 256>>>(bd.sQK.back(), (long long)B * h * w, 2LL * U.heads * slot, U.heads, slot, U.heads * slot, dh);
+        LDN_CUDA(cudaGetLastError());
+        LDN_CUDA(cudaDeviceSynchronize());
+      }
       if (U.attn_level[level] && (dh == 40 || dh == 80) && (h * w) % 8 == 0) {
         const int hs = dh == 40 ? 48 : 96;
         const long long tld = ((long long)B * h * w + 15) / 16 * 16;

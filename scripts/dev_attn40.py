@@ -4,18 +4,21 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lightdiffusion_next_b200 import _lib as L
 lib = L.load(); torch.manual_seed(0); dev = "cuda"
-tag = f"gen={os.environ.get('LDN_ATTN_D40', '5')} poly={os.environ.get('LDN_ATTN_POLY', '3')}"
+FOLD = int(os.environ.get("FOLD", "0"))  # 1: folded operands (Q pre-scaled, ones column in K; `causal` bit 1 of the C entry)
+tag = f"gen={os.environ.get('LDN_ATTN_D40', '9')} poly={os.environ.get('LDN_ATTN_POLY', '3')} fold={FOLD}"
 def attn(B, H, Nq, Nk, d=40, reps=10, spread=1.0):
     hs, slot = 48, 64
     nk_pad = (Nk + 127) // 128 * 128 if Nk % 8 else Nk
     q = (torch.randn(B, H, Nq, d, device=dev) * spread).bfloat16(); k = torch.randn(B, H, Nk, d, device=dev).bfloat16(); v = torch.randn(B, H, Nk, d, device=dev).bfloat16()
     Qb = torch.zeros(B * Nq, H * slot, device=dev, dtype=torch.bfloat16); Kb = torch.zeros(B * nk_pad, H * slot, device=dev, dtype=torch.bfloat16)
-    Qb.view(B, Nq, H, slot)[..., :d] = q.permute(0, 2, 1, 3); Kb.view(B, nk_pad, H, slot)[:, :Nk, :, :d] = k.permute(0, 2, 1, 3)
+    qs = (q.float() * (d ** -0.5 * 1.4426950408889634)).bfloat16() if FOLD else q
+    Qb.view(B, Nq, H, slot)[..., :d] = qs.permute(0, 2, 1, 3); Kb.view(B, nk_pad, H, slot)[:, :Nk, :, :d] = k.permute(0, 2, 1, 3)
+    if FOLD: Kb.view(B, nk_pad, H, slot)[:, :Nk, :, d] = 1.0
     Vt = torch.zeros(H * hs, B * nk_pad, device=dev, dtype=torch.bfloat16); Vt.view(H, hs, B, nk_pad)[:, :d, :, :Nk] = v.permute(1, 3, 0, 2)
     Vt.view(H, hs, B, nk_pad)[:, d] = 1.0
     out = torch.zeros(B * Nq, H * d, device=dev, dtype=torch.bfloat16)
     def run():
-        L.check(lib.ldn_attention_bf16(Qb.data_ptr(), H * slot, Kb.data_ptr(), H * slot, Vt.data_ptr(), B * nk_pad, H * hs, hs, B, H, Nq, Nk, nk_pad, d, slot, 0, d ** -0.5, out.data_ptr(), H * d, L.cur_stream()))
+        L.check(lib.ldn_attention_bf16(Qb.data_ptr(), H * slot, Kb.data_ptr(), H * slot, Vt.data_ptr(), B * nk_pad, H * hs, hs, B, H, Nq, Nk, nk_pad, d, slot, 2 if FOLD else 0, d ** -0.5, out.data_ptr(), H * d, L.cur_stream()))
     run(); torch.cuda.synchronize()
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).permute(0, 2, 1, 3).reshape(B * Nq, H * d)
     rel = ((out.float() - ref).norm() / ref.norm()).item()

@@ -145,6 +145,46 @@ def test_attention(lib, B, H, Nq, Nk, d, causal, ones):
     ref = ref.permute(0, 2, 1, 3).reshape(B * Nq, H * d)
     assert rel(out, ref) < TOL
 
+@pytest.mark.parametrize("B,H,Nq,Nk,grow", [(2, 8, 1024, 1024, True), (1, 8, 4096, 4096, False), (1, 2, 200, 1090, True),
+                                            (1, 2, 300, 520, True), (2, 8, 1024, 77, False)])
+def test_attention_folded_operands(lib, B, H, Nq, Nk, grow):
+    """`causal` bit 1 of ldn_attention_bf16 (d = 40, ones-row V^T): Q arrives pre-scaled by scale * log2(e) and column 40 of
+    every K head slot holds 1.0; the long-sequence kernel (attention9.cu, folded variant) keeps -m in column 40 of its Q
+    tile so that the tensor core delivers offset scores.  This is how the UNet program calls its level-0 self-attention.
+    The fp32 reference is built from the SAME rounded, pre-scaled Q (the UNet rounds once, after the scale).  Nk = 77 takes
+    the short-sequence kernel, which must ignore the ones column (column 40 of Q is zero in global memory)."""
+    L, l = lib
+    torch.manual_seed(Nq + Nk)
+    d, slot, hs = 40, 64, 48
+    qs_scale = d ** -0.5 * 1.4426950408889634
+    nk_pad = (Nk + 127) // 128 * 128 if Nk % 8 else Nk
+    qs = (torch.randn(B, H, Nq, d, device="cuda") * qs_scale).bfloat16()  # what the projection epilogue would store
+    k = torch.randn(B, H, Nk, d, device="cuda").bfloat16()
+    v = torch.randn(B, H, Nk, d, device="cuda").bfloat16()
+    if grow:  # the running offset has to move several times along the keys
+        k = (k.float() * torch.linspace(0.2, 3.0, Nk, device="cuda")[None, None, :, None]).bfloat16()
+    Qb = torch.zeros(B * Nq, H * slot, device="cuda", dtype=torch.bfloat16)
+    Kb = torch.zeros(B * nk_pad, H * slot, device="cuda", dtype=torch.bfloat16)
+    Qb.view(B, Nq, H, slot)[..., :d] = qs.permute(0, 2, 1, 3)
+    Kb.view(B, nk_pad, H, slot)[:, :Nk, :, :d] = k.permute(0, 2, 1, 3)
+    Kb.view(B, nk_pad, H, slot)[:, :, :, d] = 1.0
+    Vt = torch.zeros(H * hs, B * nk_pad, device="cuda", dtype=torch.bfloat16)
+    Vt.view(H, hs, B, nk_pad)[:, :d, :, :Nk] = v.permute(1, 3, 0, 2)
+    Vt.view(H, hs, B, nk_pad)[:, d] = 1.0
+    out = torch.zeros(B * Nq, H * d, device="cuda", dtype=torch.bfloat16)
+
+    def run():
+        L.check(l.ldn_attention_bf16(Qb.data_ptr(), H * slot, Kb.data_ptr(), H * slot, Vt.data_ptr(), B * nk_pad, H * hs, hs,
+                                     B, H, Nq, Nk, nk_pad, d, slot, 2, 0.0, out.data_ptr(), H * d, L.cur_stream()))
+    run()
+    ref = F.scaled_dot_product_attention(qs.float() / 1.4426950408889634, k.float(), v.float(), scale=1.0)
+    ref = ref.permute(0, 2, 1, 3).reshape(B * Nq, H * d)
+    assert rel(out, ref) < TOL
+    first = out.clone()
+    run()
+    torch.cuda.synchronize()
+    assert torch.equal(first, out)  # bit-deterministic
+
 
 @pytest.mark.parametrize("B,HW,C0,C1,silu,eps", [(2, 256, 320, 0, True, 1e-5), (2, 1024, 640, 320, True, 1e-5),
                                                  (2, 64, 1280, 640, True, 1e-5), (1, 4096, 320, 0, False, 1e-6),
