@@ -361,10 +361,11 @@ AttnPlan make_attn_plan(const AttnArgs& a) {
     // generation 5 (P kept in tensor memory, TS-form P*V); generation 3 (P through shared memory) was retired once v5
     // had replaced it on every path
     // generation 9 (attention9.cu: 64-key steps, two CTAs per SM) for long key sequences: 1.207 ms vs 1.319 ms at N = 16384,
-    // B*H = 16 (profiles/r2_attention9.md); generation 5 keeps the short ones (cross-attention, Nk = 77)
+    // B*H = 16 (profiles/r2_attention9.md); generation 5 keeps only key sequences shorter than one 64-key step
     static const int d40_gen = getenv("LDN_ATTN_D40") ? atoi(getenv("LDN_ATTN_D40")) : 9;
     static const int fold_on = getenv("LDN_ATTN_FOLD") ? atoi(getenv("LDN_ATTN_FOLD")) : 1;
-    if (d40_gen == 9 && a.Nk >= 512) {
+    static const int gen9_min_nk = getenv("LDN_ATTN9_MIN_NK") ? atoi(getenv("LDN_ATTN9_MIN_NK")) : 64;  // cross-attention (Nk = 77) included: step 15.86 -> 15.79 ms
+    if (d40_gen == 9 && a.Nk >= gen9_min_nk) {
       finish_attn9_plan(plan, a);
       p.fold = (a.fold && fold_on) ? 1 : 0;  // (other kernels ignore the ones column: column 40 of Q is zero in global memory)
     } else {
