@@ -61,6 +61,18 @@ struct GemmParams {
   const bf16* residual;
   long long ldr;
   int head_dim, head_slot;  // head_dim > 0: col n -> (n / head_dim) * head_slot + n % head_dim
+  // LayerNorm folded into the GEMM that consumes it (transformer.py:154-157 norm1/2/3 -> q/k/v, q, GEGLU projections):
+  //   LN(x) W^T = rstd * (x W'^T - mean * c) + d   with W' = W * gamma (bf16), c[n] = sum_k W'[n,k], d[n] = sum_k W[n,k] beta[k] (+ bias)
+  // The PRODUCER of x (proj_in / attention out-projections) leaves per-row partial sums, the consumer finishes them.
+  float2* rowstat_out;        // producer: [M, rowstat_parts] (sum, sum of squares) over the columns this (n-tile, epilogue half) stored
+  int rowstat_parts;          // = 2 * n-tiles of the producer
+  const float2* ln_parts;     // consumer, row mode: the producer's partials for the rows of A
+  int ln_nparts;
+  float ln_inv_k, ln_eps;     // 1 / normalised width, epsilon
+  const float* ln_c;          // row mode: [N]; column mode: [M]
+  const float* ln_d;
+  float2* ln_final_out;       // row mode, optional: n-tile 0 / half 0 stores (rstd, -rstd * mean) per row for a later column-mode GEMM
+  const float2* ln_final_in;  // column mode (operand-swapped V^T GEMM: output COLUMNS are tokens): per column (rstd, -rstd * mean)
   int acc_stages;    // persistent kernel: accumulator stages in TMEM (2, or 1 when two CTAs share the SM and BN > 128)
   int epi_opt;       // bit 0: 256-bit epilogue accesses, bit 1: packed-pair GEGLU arithmetic
   int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77),
@@ -116,6 +128,16 @@ struct GemmArgs {
   int head_dim = 0, head_slot = 0;
   int row_head_dim = 0, row_head_slot = 0;
   int act = 0;
+  // folded LayerNorm (see GemmParams)
+  float2* rowstat_out = nullptr;
+  const float2* ln_parts = nullptr;
+  int ln_nparts = 0;
+  int ln_width = 0;
+  float ln_eps = 1e-5f;
+  const float* ln_c = nullptr;
+  const float* ln_d = nullptr;
+  float2* ln_final_out = nullptr;
+  const float2* ln_final_in = nullptr;
   int BN = 0;  // 0 = choose
   long long wt_ld = 0;  // leading dimension of Wt in elements (0 = K)
   int wt_rows = 0;  // valid rows of Wt if fewer than N (the rest are zero-filled by TMA)

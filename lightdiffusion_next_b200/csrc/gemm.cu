@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
 
     long long out_row;  // output row index (pixel / token), -1 if masked
     int batch;
+    int m_row = -1;
     if (p.conv) {
       const int bx = r % p.BW;
       const int by = (r / p.BW) % p.BH;
@@ -159,12 +160,13 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       batch = b;
     } else {
       const int m = m0 + r;
+      m_row = m;
       out_row = (m < p.M) ? m : -1;
       if (p.row_head_dim > 0 && out_row >= 0) out_row = (m / p.row_head_dim) * p.row_head_slot + (m % p.row_head_dim);
       batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
     }
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, (int)blockIdx.z);
+    gemm_epilogue_tile<0>(p, BN, n0, out_row, batch, t_lane, ehalf, (int)blockIdx.z, m_row);
   }
 
   tc_fence_before();
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
 // the epilogue warps drain the previous accumulator (two accumulator stages in TMEM: tmem_full / tmem_empty), and the
 // shared-memory ring is as deep as the whole SM allows. Short-K GEMMs (1x1 projections, K = 320) were dominated by the
 // per-CTA prologue + pipeline ramp of the one-tile-per-CTA kernel.
-template <int kOcc>
+template <int kOcc, int kLn>
 __global__ void __launch_bounds__(kGemmThreads, kOcc) gemm_tc_persist_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(kGemmThreads, kOcc) gemm_tc_persist_kernel(con
       const int n0 = nt * BN;
       long long out_row;
       int batch;
+      int m_row = -1;
       if (p.conv) {
         int t = mt;
         const int tx = t % p.tiles_x;
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(kGemmThreads, kOcc) gemm_tc_persist_kernel(con
         batch = b;
       } else {
         const int m = mt * kBM + r;
+        m_row = m;
         out_row = (m < p.M) ? m : -1;
         if (p.row_head_dim > 0 && out_row >= 0)
           out_row = (m / p.row_head_dim) * p.row_head_slot + (m % p.row_head_dim);
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(kGemmThreads, kOcc) gemm_tc_persist_kernel(con
       const uint32_t t_lane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
       mbar_wait(&tfull_bar[acc], acc_parity);
       tc_fence_after();
-      gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
+      gemm_epilogue_tile<kLn>(p, BN, n0, out_row, batch, t_lane, ehalf, z, m_row);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -496,6 +500,18 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.head_dim = a.head_dim;
   p.head_slot = a.head_slot;
   p.act = a.act;
+  p.rowstat_out = a.rowstat_out;
+  p.rowstat_parts = 2 * (int)plan.grid.x;
+  p.ln_parts = a.ln_parts;
+  p.ln_nparts = a.ln_nparts;
+  p.ln_inv_k = a.ln_width > 0 ? 1.0f / (float)a.ln_width : 0.f;
+  p.ln_eps = a.ln_eps;
+  p.ln_c = a.ln_c;
+  p.ln_d = a.ln_d;
+  p.ln_final_out = a.ln_final_out;
+  p.ln_final_in = a.ln_final_in;
+  if (a.ln_parts || a.ln_final_in) LDN_CHECK(a.ln_c && a.ln_d && !a.bias && !a.conv, "gemm: folded LayerNorm needs ln_c / ln_d and carries the bias in ln_d");
+  if (a.rowstat_out) LDN_CHECK(!a.conv && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && !a.out_f32, "gemm: row statistics are produced by plain epilogues only");
   static const int epi_opt = getenv("LDN_GEMM_EPI_OPT") ? atoi(getenv("LDN_GEMM_EPI_OPT")) : 3;
   p.epi_opt = epi_opt;
   {  // 256-bit epilogue accesses need 32-byte aligned rows
@@ -526,7 +542,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   const int tiles = plan.grid.x * plan.grid.y;
   static const bool no_split = getenv("LDN_GEMM_NOSPLIT") != nullptr;  // experiments only
   static const int split_max_tiles = getenv("LDN_GEMM_SPLIT_MAX_TILES") ? atoi(getenv("LDN_GEMM_SPLIT_MAX_TILES")) : 74;
-  if (!no_split && a.splitk_ws && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && a.act == 0 && !a.colgate && !a.out_f32 && tiles <= split_max_tiles && p.num_k_chunks >= 40) {
+  if (!no_split && a.splitk_ws && !a.rowstat_out && !a.ln_parts && !a.ln_final_in && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && a.act == 0 && !a.colgate && !a.out_f32 && tiles <= split_max_tiles && p.num_k_chunks >= 40) {
     int splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > p.num_k_chunks / 8) splits = p.num_k_chunks / 8;
     if (splits > 16) splits = 16;
@@ -634,17 +650,35 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.pair) {
     launch_gemm_pair(plan, stream);
   } else if (plan.persistent) {
+    // folded-LayerNorm role of this GEMM (compile-time variants of the epilogue): 1 row consumer, 2 column consumer, 3 producer
+    const int ln = plan.p.ln_parts ? 1 : plan.p.ln_final_in ? 2 : plan.p.rowstat_out ? 3 : 0;
     static bool attr2 = false;
     if (!attr2) {
-      LDN_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      LDN_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+      auto prime = [](auto kern, int smem_max) { LDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); };
+      prime(gemm_tc_persist_kernel<1, 0>, 227 * 1024); prime(gemm_tc_persist_kernel<1, 1>, 227 * 1024);
+      prime(gemm_tc_persist_kernel<1, 2>, 227 * 1024); prime(gemm_tc_persist_kernel<1, 3>, 227 * 1024);
+      prime(gemm_tc_persist_kernel<2, 0>, 113 * 1024); prime(gemm_tc_persist_kernel<2, 1>, 113 * 1024);
+      prime(gemm_tc_persist_kernel<2, 2>, 113 * 1024); prime(gemm_tc_persist_kernel<2, 3>, 113 * 1024);
       attr2 = true;
     }
-    if (plan.persist_occ == 2)
-      gemm_tc_persist_kernel<2><<<plan.pgrid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
-    else
-      gemm_tc_persist_kernel<1><<<plan.pgrid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    auto go = [&](auto kern, int) { kern<<<plan.pgrid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p); };
+    if (plan.persist_occ == 2) {
+      switch (ln) {
+        case 1: go(gemm_tc_persist_kernel<2, 1>, 113 * 1024); break;
+        case 2: go(gemm_tc_persist_kernel<2, 2>, 113 * 1024); break;
+        case 3: go(gemm_tc_persist_kernel<2, 3>, 113 * 1024); break;
+        default: go(gemm_tc_persist_kernel<2, 0>, 113 * 1024); break;
+      }
+    } else {
+      switch (ln) {
+        case 1: go(gemm_tc_persist_kernel<1, 1>, 227 * 1024); break;
+        case 2: go(gemm_tc_persist_kernel<1, 2>, 227 * 1024); break;
+        case 3: go(gemm_tc_persist_kernel<1, 3>, 227 * 1024); break;
+        default: go(gemm_tc_persist_kernel<1, 0>, 227 * 1024); break;
+      }
+    }
   } else {
+    LDN_CHECK(!plan.p.ln_parts && !plan.p.ln_final_in && !plan.p.rowstat_out, "gemm: folded LayerNorm runs on the persistent kernel only (K <= 1280)");
     gemm_tc_kernel<<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
   }
   LDN_CUDA(cudaGetLastError());

@@ -55,9 +55,35 @@ __device__ __forceinline__ float2 geglu2(float2 a, float2 g) {
 
 // Drains one 128 x BN fp32 accumulator tile from TMEM (columns starting at t_lane) through the fused epilogue.
 // Executed by the 8 epilogue warps; `ehalf` selects which alternate 16-column chunks this warp handles.
+// `m_row`: the GEMM row index of this thread (token / channel) before any head-slot remapping, or -1 (conv).
+// kLn (compile time, so that the plain epilogue carries none of it -- these epilogues are sensitive to every register and
+// instruction): 0 no folded LayerNorm; 1 consumer, row mode; 2 consumer, column mode; 3 producer of row statistics.
+template <int kLn = 0>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const int BN, const int n0, const long long out_row,
                                                    const int batch, const uint32_t t_lane, const int ehalf,
-                                                   const int split_z) {
+                                                   const int split_z, const int m_row = -1) {
+    // ---- folded LayerNorm, consumer side: per-row (rstd, -rstd * mean) from the producer's partial sums (fixed order)
+    float ln_a = 1.f, ln_b = 0.f;
+    if (kLn == 1 && m_row >= 0 && m_row < p.M) {
+      float sum = 0.f, sq = 0.f;
+      const float2* pp = p.ln_parts + (long long)m_row * p.ln_nparts;
+      for (int i = 0; i < p.ln_nparts; ++i) {
+        const float2 v = pp[i];
+        sum += v.x;
+        sq += v.y;
+      }
+      const float mean = sum * p.ln_inv_k;
+      const float var = fmaxf(sq * p.ln_inv_k - mean * mean, 0.f);
+      ln_a = rsqrtf(var + p.ln_eps);
+      ln_b = -ln_a * mean;
+      if (p.ln_final_out != nullptr && n0 == 0 && ehalf == 0) p.ln_final_out[m_row] = make_float2(ln_a, ln_b);
+    }
+    float ln_cv = 0.f, ln_dv = 0.f;  // column mode: this output row's c / d
+    if (kLn == 2 && m_row >= 0 && m_row < p.M) {
+      ln_cv = p.ln_c[m_row];
+      ln_dv = p.ln_d[m_row];
+    }
+    float st_sum = 0.f, st_sq = 0.f;  // producer side: statistics of the values this thread stores
 
     if (p.splits > 1) {
       // split-K: raw fp32 partial tile; bias / residual are applied by splitk_reduce_kernel
@@ -86,6 +112,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (kLn == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_c + n + i));
+            const float4 dv = __ldg(reinterpret_cast<const float4*>(p.ln_d + n + i));
+            f[i] = fmaf(ln_a, f[i], fmaf(ln_b, cv.x, dv.x));
+            f[i + 1] = fmaf(ln_a, f[i + 1], fmaf(ln_b, cv.y, dv.y));
+            f[i + 2] = fmaf(ln_a, f[i + 2], fmaf(ln_b, cv.z, dv.z));
+            f[i + 3] = fmaf(ln_a, f[i + 3], fmaf(ln_b, cv.w, dv.w));
+          }
+        } else if (kLn == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {  // (rstd, -rstd * mean) of two tokens per 16-byte load
+            const float4 ab = __ldg(reinterpret_cast<const float4*>(p.ln_final_in + n + i));
+            f[i] = fmaf(ab.x, f[i], fmaf(ab.y, ln_cv, ln_dv));
+            f[i + 1] = fmaf(ab.z, f[i + 1], fmaf(ab.w, ln_cv, ln_dv));
+          }
+        }
         if (p.bias) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -143,6 +187,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
         }
+        if (kLn == 3) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            st_sum += f[i];
+            st_sq = fmaf(f[i], f[i], st_sq);
+          }
+        }
         if (p.out_f32) {
           float4* op = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldo + n);
 #pragma unroll
@@ -168,6 +219,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
         }
         __syncwarp();
       }
+      if (kLn == 3 && m_row >= 0 && m_row < p.M)
+        p.rowstat_out[(long long)m_row * p.rowstat_parts + (n0 / BN) * 2 + ehalf] = make_float2(st_sum, st_sq);
     } else {
       // GEGLU: weight rows were interleaved at load time so that this tile holds BN/2 value columns followed
       // by the BN/2 matching gate columns (Activation.py:30-31: x, gate = proj(x).chunk(2); x * gelu(gate)).
@@ -178,7 +231,18 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
         tmem_ld16(t_lane + (uint32_t)c, va);
         tmem_ld16(t_lane + (uint32_t)(half + c), vg);
         float ba[16], bg[16];  // bias vectors fetched while the TMEM loads are in flight
-        if (p.bias && (n0 + c) < p.N) {
+        if (kLn == 1 && (n0 + c) < p.N) {
+          // folded LayerNorm: value / gate = ln_a * acc + (ln_b * c[n] + d[n]); the bias travels inside d
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 ca = __ldg(reinterpret_cast<const float4*>(p.ln_c + n0 + c + i));
+            const float4 da = __ldg(reinterpret_cast<const float4*>(p.ln_d + n0 + c + i));
+            const float4 cg = __ldg(reinterpret_cast<const float4*>(p.ln_c + n0 + half + c + i));
+            const float4 dg = __ldg(reinterpret_cast<const float4*>(p.ln_d + n0 + half + c + i));
+            ba[i] = fmaf(ln_b, ca.x, da.x); ba[i + 1] = fmaf(ln_b, ca.y, da.y); ba[i + 2] = fmaf(ln_b, ca.z, da.z); ba[i + 3] = fmaf(ln_b, ca.w, da.w);
+            bg[i] = fmaf(ln_b, cg.x, dg.x); bg[i + 1] = fmaf(ln_b, cg.y, dg.y); bg[i + 2] = fmaf(ln_b, cg.z, dg.z); bg[i + 3] = fmaf(ln_b, cg.w, dg.w);
+          }
+        } else if (p.bias && (n0 + c) < p.N) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 x4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + i));
@@ -196,7 +260,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
           for (int i = 0; i < 16; ++i) {
             float a = __uint_as_float(va[i]);
             float g = __uint_as_float(vg[i]);
-            if (p.bias) {
+            if (kLn == 1) {
+              a = fmaf(ln_a, a, ba[i]);
+              g = fmaf(ln_a, g, bg[i]);
+            } else if (p.bias) {
               a += ba[i];
               g += bg[i];
             }
@@ -207,7 +274,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
         for (int i = 0; i < 16; i += 2) {
           float2 a = make_float2(__uint_as_float(va[i]), __uint_as_float(va[i + 1]));
           float2 g = make_float2(__uint_as_float(vg[i]), __uint_as_float(vg[i + 1]));
-          if (p.bias) {
+          if (kLn == 1) {
+            a = ffma2(a, make_float2(ln_a, ln_a), make_float2(ba[i], ba[i + 1]));
+            g = ffma2(g, make_float2(ln_a, ln_a), make_float2(bg[i], bg[i + 1]));
+          } else if (p.bias) {
             a = fadd2(a, make_float2(ba[i], ba[i + 1]));
             g = fadd2(g, make_float2(bg[i], bg[i + 1]));
           }

@@ -85,6 +85,34 @@ __global__ void fill_k_ones_kernel(bf16* __restrict__ qk, long long rows, long l
   }
 }
 
+// Folded LayerNorm (gemm_epilogue.cuh): LN(x) W^T = rstd * (x W'^T - mean * c) + d.  One warp per weight row, in place:
+//   d[n] = sum_k W[n,k] beta[k] (+ bias[n]);  W'[n,k] = bf16(W[n,k] * gamma[k]);  c[n] = sum_k W'[n,k] (the ROUNDED values the MMA will see).
+__global__ void ln_fold_prepare_kernel(bf16* __restrict__ W, int rows, int K, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ bias,
+                                       float* __restrict__ c, float* __restrict__ d) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  bf16* w = W + (size_t)row * K;
+  float cs = 0.f, ds = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float x = __bfloat162float(w[k]);
+    ds = fmaf(x, beta[k], ds);
+    const bf16 y = __float2bfloat16(x * gamma[k]);
+    w[k] = y;
+    cs += __bfloat162float(y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+  }
+  if (lane == 0) {
+    c[row] = cs;
+    d[row] = ds + (bias ? bias[row] : 0.f);
+  }
+}
+
 }  // namespace ldn
 
 using namespace ldn;
@@ -104,6 +132,10 @@ struct STW {
   float* qk_gate = nullptr;  // d = 40: per-column multiplier of the [Q | K] projection, scale * log2(e) on the Q half (attention9.cu, folded operands)
   bf16* Wff1 = nullptr;   // interleaved [8C, C]
   float* bff1 = nullptr;  // interleaved [8C]
+  // folded LayerNorms (norm1 -> [q|k] and v^T, norm2 -> cross-attention q, norm3 -> GEGLU): gamma-scaled weight copies + c / d vectors
+  bool ln_fold = false;
+  bf16 *Wqk_f = nullptr, *Wv_f = nullptr, *Wq2_f = nullptr, *Wff1_f = nullptr;
+  float *cqk = nullptr, *dqk = nullptr, *cv = nullptr, *dv = nullptr, *cq2 = nullptr, *dq2 = nullptr, *cff = nullptr, *dff = nullptr;
   int ff_bn = 256;
   int index;  // 0..15, order of execution
 };
@@ -299,6 +331,26 @@ void unet_finalize(ldn_engine* e, cudaStream_t stream) {
     s.bff1 = U.arena.get<float>((size_t)8 * C);
     geglu_interleave_kernel<<<8 * C, 128, 0, stream>>>(wf.b(), bf.f(), 4 * C, C, s.ff_bn / 2, s.Wff1, s.bff1);
     LDN_CUDA(cudaGetLastError());
+    // SURVEY K5, built and measured (profiles/r2_experiments.md section 16): 48 launches fewer, same accuracy, but the K = C projections
+    // are bound by their epilogues and the extra ~50 instructions per 16-column chunk cost more than the LayerNorm kernels did
+    // (15.87 vs 15.81 ms per step).  Opt-in.
+    static const int ln_fold_on = getenv("LDN_LN_FOLD") ? atoi(getenv("LDN_LN_FOLD")) : 0;
+    if (ln_fold_on) {
+      s.ln_fold = true;
+      auto fold = [&](const bf16* src, int rows, const std::string& norm, const float* bias, bf16*& Wf, float*& cvec, float*& dvec) {
+        Wf = U.arena.get<bf16>((size_t)rows * C);
+        cvec = U.arena.get<float>((size_t)rows);
+        dvec = U.arena.get<float>((size_t)rows);
+        LDN_CUDA(cudaMemcpyAsync(Wf, src, (size_t)rows * C * sizeof(bf16), cudaMemcpyDeviceToDevice, stream));
+        ln_fold_prepare_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(Wf, rows, C, e->W(0, tb + norm + ".weight").f(),
+                                                                           e->W(0, tb + norm + ".bias").f(), bias, cvec, dvec);
+        LDN_CUDA(cudaGetLastError());
+      };
+      fold(s.Wqk, 2 * C, ".norm1", nullptr, s.Wqk_f, s.cqk, s.dqk);
+      fold(e->W(0, tb + ".attn1.to_v.weight").b(), C, ".norm1", nullptr, s.Wv_f, s.cv, s.dv);
+      fold(e->W(0, tb + ".attn2.to_q.weight").b(), C, ".norm2", nullptr, s.Wq2_f, s.cq2, s.dq2);
+      fold(s.Wff1, 8 * C, ".norm3", s.bff1, s.Wff1_f, s.cff, s.dff);
+    }
   }
   // context buffers (capacity from the config)
   const int cap_rows = e->cfg.max_rows > 0 ? e->cfg.max_rows : 2;
@@ -379,6 +431,8 @@ struct Builder {
   float* splitk_ws = nullptr;
   size_t splitk_ws_bytes = 0;
   float* gn_ws = nullptr;
+  float2* ln_parts = nullptr;  // [tokens, 16] row-statistics partials of the token stream (folded LayerNorm)
+  float2* ln_final = nullptr;  // [tokens] (rstd, -rstd * mean) of norm1, for the operand-swapped V^T GEMM
   float *temb = nullptr, *emb1 = nullptr, *emb = nullptr, *emb_all = nullptr;
 
   void add(const std::string& name, Step s, int launches = 1) {
@@ -386,7 +440,8 @@ struct Builder {
     P.names.push_back(name);
     P.launches += launches;
   }
-  void gemm(const std::string& name, const GemmArgs& a0) {
+  // returns the number of row-statistics partials per row the plan writes (meaningful when a0.rowstat_out is set)
+  int gemm(const std::string& name, const GemmArgs& a0) {
     GemmArgs a = a0;
     a.splitk_ws = splitk_ws;
     a.splitk_ws_bytes = splitk_ws_bytes;
@@ -395,6 +450,8 @@ struct Builder {
     const long long Kk = a.conv ? 9LL * a.Cin : (long long)a.K0 + a.K1;
     add(name + " [M=" + std::to_string(Mm) + " N=" + std::to_string(a.N) + " K=" + std::to_string(Kk) + "]",
         [plan](cudaStream_t st) { launch_gemm(plan, st); }, plan.p.splits > 1 ? 2 : 1);  // split-K adds its reduce kernel
+    if (a.rowstat_out) LDN_CHECK(plan.p.rowstat_parts <= 16, "row-statistics buffer holds 16 partials per row");
+    return plan.p.rowstat_parts;
   }
   void groupnorm(const std::string& name, const bf16* x0, int C0, const bf16* x1, int C1, int HW, float eps,
                  const std::string& wprefix, bool silu, bf16* out) {
@@ -462,18 +519,27 @@ struct Builder {
     bf16* QK = sQK[level];
     const long long ldqk = 2LL * U.heads * s.slot;
     const float scale = 1.0f / sqrtf((float)s.d);
+    // LayerNorm folded into the consuming projections (norm1 / norm2 / norm3 have no kernel of their own): the producers of
+    // the token stream X leave per-row partial sums in `ln_parts`, the consumers read the raw X.  Needs 16-token-aligned rows.
+    const bool fold = s.ln_fold && (T % 16 == 0);
+    int nparts = 0;
     groupnorm(s.prefix + ".norm", x, C, nullptr, 0, N, 1e-6f, s.prefix + ".norm", false, sA);
     {
       GemmArgs a;
       a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = e->W(0, s.prefix + ".proj_in.weight").b(); a.M = T; a.N = C;
       a.bias = e->W(0, s.prefix + ".proj_in.bias").f(); a.out = X; a.ldo = C;
-      gemm(s.prefix + ".proj_in", a);
+      if (fold) a.rowstat_out = ln_parts;  // statistics of X for norm1
+      nparts = gemm(s.prefix + ".proj_in", a);
     }
     // ---- self-attention
-    layernorm(tb + ".norm1", X, T, C, tb + ".norm1", sA);
+    if (!fold) layernorm(tb + ".norm1", X, T, C, tb + ".norm1", sA);
     {
       GemmArgs a;
-      a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = s.Wqk; a.M = T; a.N = 2 * C;
+      a.A0 = fold ? X : sA; a.lda0 = C; a.K0 = C; a.Wt = fold ? s.Wqk_f : s.Wqk; a.M = T; a.N = 2 * C;
+      if (fold) {
+        a.ln_parts = ln_parts; a.ln_nparts = nparts; a.ln_width = C; a.ln_c = s.cqk; a.ln_d = s.dqk;
+        a.ln_final_out = ln_final;  // (rstd, -rstd * mean) per token for the V^T GEMM below
+      }
       a.out = QK; a.ldo = ldqk; a.head_dim = s.d; a.head_slot = s.slot;
       a.colgate = s.qk_gate; a.ld_colgate = 0;  // d = 40: Q leaves the projection already scaled by scale * log2(e)
       gemm(tb + ".attn1.qk", a);
@@ -481,7 +547,9 @@ struct Builder {
       const int hs = s.d == 40 ? 48 : 96;
       bf16* Vt = ones ? sVt40[level] : sVt;
       GemmArgs v;
-      v.A0 = e->W(0, tb + ".attn1.to_v.weight").b(); v.lda0 = C; v.K0 = C; v.Wt = sA; v.M = C; v.N = Tld; v.wt_rows = T;
+      v.A0 = fold ? s.Wv_f : e->W(0, tb + ".attn1.to_v.weight").b(); v.lda0 = C; v.K0 = C; v.Wt = fold ? X : sA; v.M = C; v.N = Tld;
+      v.wt_rows = T;
+      if (fold) { v.ln_final_in = ln_final; v.ln_c = s.cv; v.ln_d = s.dv; }  // output columns are tokens here
       v.out = Vt; v.ldo = Tld;
       if (ones) { v.row_head_dim = s.d; v.row_head_slot = hs; }
       gemm(tb + ".attn1.vt", v);
@@ -513,13 +581,15 @@ struct Builder {
       GemmArgs o;
       o.A0 = sO; o.lda0 = C; o.K0 = C; o.Wt = e->W(0, tb + ".attn1.to_out.0.weight").b(); o.M = T; o.N = C;
       o.bias = e->W(0, tb + ".attn1.to_out.0.bias").f(); o.residual = X; o.ldr = C; o.out = X; o.ldo = C;
-      gemm(tb + ".attn1.out", o);
+      if (fold) o.rowstat_out = ln_parts;  // statistics of the updated X for norm2
+      nparts = gemm(tb + ".attn1.out", o);
     }
     // ---- cross-attention (K/V precomputed by ldn_set_context)
-    layernorm(tb + ".norm2", X, T, C, tb + ".norm2", sA);
+    if (!fold) layernorm(tb + ".norm2", X, T, C, tb + ".norm2", sA);
     {
       GemmArgs a;
-      a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = e->W(0, tb + ".attn2.to_q.weight").b(); a.M = T; a.N = C;
+      a.A0 = fold ? X : sA; a.lda0 = C; a.K0 = C; a.Wt = fold ? s.Wq2_f : e->W(0, tb + ".attn2.to_q.weight").b(); a.M = T; a.N = C;
+      if (fold) { a.ln_parts = ln_parts; a.ln_nparts = nparts; a.ln_width = C; a.ln_c = s.cq2; a.ln_d = s.dq2; }
       a.out = QK; a.ldo = ldqk; a.head_dim = s.d; a.head_slot = s.slot;
       gemm(tb + ".attn2.q", a);
       AttnArgs at;
@@ -533,13 +603,16 @@ struct Builder {
       GemmArgs o;
       o.A0 = sO; o.lda0 = C; o.K0 = C; o.Wt = e->W(0, tb + ".attn2.to_out.0.weight").b(); o.M = T; o.N = C;
       o.bias = e->W(0, tb + ".attn2.to_out.0.bias").f(); o.residual = X; o.ldr = C; o.out = X; o.ldo = C;
-      gemm(tb + ".attn2.out", o);
+      if (fold) o.rowstat_out = ln_parts;  // statistics of the updated X for norm3
+      nparts = gemm(tb + ".attn2.out", o);
     }
     // ---- GEGLU feed-forward
-    layernorm(tb + ".norm3", X, T, C, tb + ".norm3", sA);
+    if (!fold) layernorm(tb + ".norm3", X, T, C, tb + ".norm3", sA);
     {
       GemmArgs a;
-      a.A0 = sA; a.lda0 = C; a.K0 = C; a.Wt = s.Wff1; a.M = T; a.N = 8 * C; a.bias = s.bff1; a.epi = 1;
+      a.A0 = fold ? X : sA; a.lda0 = C; a.K0 = C; a.Wt = fold ? s.Wff1_f : s.Wff1; a.M = T; a.N = 8 * C; a.epi = 1;
+      if (fold) { a.ln_parts = ln_parts; a.ln_nparts = nparts; a.ln_width = C; a.ln_c = s.cff; a.ln_d = s.dff; }
+      else a.bias = s.bff1;
       a.BN = s.ff_bn; a.out = sG; a.ldo = 4 * C;
       gemm(tb + ".ff.geglu", a);
       GemmArgs o;
@@ -635,6 +708,8 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
     }
   }
   bd.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B), true));
+  bd.ln_parts = A.get<float2>((size_t)B * H * W * 16, true);
+  bd.ln_final = A.get<float2>((size_t)B * H * W + 16, true);
   bd.temb = A.get<float>((size_t)B * U.model_ch);
   bd.emb1 = A.get<float>((size_t)B * U.temb_dim);
   bd.emb = A.get<float>((size_t)B * U.temb_dim);
