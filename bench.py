@@ -331,11 +331,16 @@ def main():
 
     if rank == 0:
         # ------------------------------------------------------------ roofline of the dominant kernel
-        # L0 self-attention (attn_tc_kernel<48>: N=16384 tokens, 8 heads, d=40, UNet batch 2): 42 % of step FLOPs.
+        # L0 self-attention (a9::attn9_tc_kernel: N=16384 tokens, 8 heads, d=40, UNet batch 2): 42 % of step FLOPs.  Called exactly
+        # as the UNet program calls it: the [Q | K] buffer with Q pre-scaled by scale * log2(e) and a ones column in every K head
+        # slot (folded operands, `causal` bit 1 of the C entry -- include/ldn.h).
         lib = eng.lib
         B2, H, N, d, slot = 2 * bs, 8, lat * lat, 40, 64
-        Qb = torch.randn(B2 * N, 2 * H * slot, device=dev).bfloat16()
+        Qb = torch.randn(B2 * N, 2 * H * slot, device=dev)
+        Qb.view(B2 * N, 2 * H, slot)[:, :H] *= d ** -0.5 * 1.4426950408889634
+        Qb = Qb.bfloat16()
         Qb.view(B2 * N, 2 * H, slot)[:, :, d:] = 0
+        Qb.view(B2 * N, 2 * H, slot)[:, H:, d] = 1.0
         Vt = torch.zeros(H * 48, B2 * N, device=dev, dtype=torch.bfloat16)   # 48 rows per head: 40 values, ones row, 7 zero rows
         Vt.view(H, 48, B2 * N)[:, :d] = torch.randn(H, d, B2 * N, device=dev).bfloat16()
         Vt.view(H, 48, B2 * N)[:, d] = 1.0
@@ -343,7 +348,7 @@ def main():
 
         def attn():
             L.check(lib.ldn_attention_bf16(Qb.data_ptr(), 2 * H * slot, Qb.data_ptr() + 2 * H * slot, 2 * H * slot,
-                                           Vt.data_ptr(), B2 * N, H * 48, 48, B2, H, N, N, N, d, slot, 0, d ** -0.5,
+                                           Vt.data_ptr(), B2 * N, H * 48, 48, B2, H, N, N, N, d, slot, 2, d ** -0.5,
                                            Ob.data_ptr(), H * d, L.cur_stream()))
         for _ in range(3):
             attn()
