@@ -92,6 +92,7 @@ struct GemmPlan {
   dim3 grid;
   int smem_bytes;
   bool persistent = false;
+  bool lean = false;  // plain bf16 epilogue (bias / rowbias / residual only): compile-time lean variant of the kernels
   int pgrid = 0;  // CTAs of the persistent kernel (<= SM count x persist_occ)
   int persist_occ = 1;  // persistent CTAs per SM (1 or 2)
   bool pair = false;  // CTA-pair kernel (gemm_pair.cu); pgrid is then an even CTA count

@@ -27,6 +27,7 @@
 
 namespace ldn {
 
+template <bool kLean>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -144,8 +145,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int ehalf = (warp - 2) >> 2;  // the two warps of a quarter take alternate 16-column chunks
     const int r = q * 32 + lane;
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
+    if constexpr (!kLean) {
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+    }
 
     long long out_row;  // output row index (pixel / token), -1 if masked
     int batch;
@@ -166,7 +169,17 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
     }
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    gemm_epilogue_tile<0>(p, BN, n0, out_row, batch, t_lane, ehalf, (int)blockIdx.z, m_row);
+    if constexpr (kLean) {
+      // lean epilogue: the residual of the first chunks is requested before the accumulator wait (the whole main loop)
+      constexpr int kPf = 3;
+      uint32_t wres[kPf][8];
+      lean_prefetch_residual<kPf>(p, BN, n0, out_row, ehalf, wres);
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+      gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
+    } else {
+      gemm_epilogue_tile<0>(p, BN, n0, out_row, batch, t_lane, ehalf, (int)blockIdx.z, m_row);
+    }
   }
 
   tc_fence_before();
@@ -349,6 +362,19 @@ __global__ void __launch_bounds__(kGemmThreads, kOcc) gemm_tc_persist_kernel(con
       const int acc = two_acc ? (tl & 1) : 0;
       const uint32_t acc_parity = (two_acc ? ((uint32_t)tl >> 1) : (uint32_t)tl) & 1u;
       const uint32_t t_lane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      if constexpr (kLn == 5) {
+        // lean epilogue with residual prefetch: the reads of this tile's residual are in flight while its main loop runs
+        constexpr int kPf = kOcc == 1 ? 5 : 3;
+        uint32_t wres[kPf][8];
+        lean_prefetch_residual<kPf>(p, BN, n0, out_row, ehalf, wres);
+        mbar_wait(&tfull_bar[acc], acc_parity);
+        tc_fence_after();
+        gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        continue;
+      }
       mbar_wait(&tfull_bar[acc], acc_parity);
       tc_fence_after();
       gemm_epilogue_tile<kLn>(p, BN, n0, out_row, batch, t_lane, ehalf, z, m_row);
@@ -523,6 +549,9 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   }
   p.row_head_dim = a.row_head_dim;
   p.row_head_slot = a.row_head_slot;
+  static const int lean_on = getenv("LDN_GEMM_LEAN") ? atoi(getenv("LDN_GEMM_LEAN")) : 1;
+  plan.lean = lean_on && a.epi == 0 && a.act == 0 && !a.colgate && !a.out_f32 && a.head_dim == 0 && (p.epi_opt & 1) &&
+              !a.rowstat_out && !a.ln_parts && !a.ln_final_in;  // (split-K is decided below and clears it)
   if (a.head_dim > 0) LDN_CHECK(a.head_dim % 8 == 0, "gemm: head_dim must be a multiple of 8");
 
   int cols = 32;
@@ -548,6 +577,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
     if (splits > 16) splits = 16;
     while (splits > 1 && (size_t)splits * p.M * a.N * sizeof(float) > a.splitk_ws_bytes) --splits;
     if (splits > 1) {
+      plan.lean = false;
       p.chunks_per_split = (p.num_k_chunks + splits - 1) / splits;
       splits = (p.num_k_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
       p.splits = splits;
@@ -578,10 +608,11 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   plan.persistent = !force_v1 && p.chunks_per_split <= persist_max_chunks;
   // Two persistent CTAs per SM (LDN_GEMM_OCC2): sixteen epilogue warps per SM instead of eight.  The short-K GEMMs are bound
   // by their epilogue (TMEM drain + residual fetch + stores, all latency), not by the tensor pipe.
-  // Measured (scripts/dev_gemm_graph.py, profiles/r2_gemm_occ2.md): 28.8 -> 24.9 us for the 320 x 320 projections with a residual
-  // (M = 32768), 18.8 -> 16.8 us at level 1; the GEGLU / QKV projections (no residual read, wide N) lose 5-15 %, so mode 2
-  // (default) applies it to residual GEMMs with K <= 640 only.  0: never, 1: every persistent GEMM.
-  static const int occ2_mode = getenv("LDN_GEMM_OCC2") ? atoi(getenv("LDN_GEMM_OCC2")) : 2;
+  // Measured (scripts/dev_gemm_graph.py, profiles/r2_experiments.md sections 9 and 17): 28.8 -> 24.9 us for the 320 x 320 projections
+  // with a residual (M = 32768) -- more epilogue warps = more residual reads in flight.  The residual-prefetching lean epilogue
+  // gets the same parallelism from one CTA per SM (23.3 us) without the single-accumulator penalty, so the mode is off by
+  // default since.  0: never, 1: every persistent GEMM, 2: residual GEMMs with K <= 640 only.
+  static const int occ2_mode = getenv("LDN_GEMM_OCC2") ? atoi(getenv("LDN_GEMM_OCC2")) : 0;
   const bool occ2 = occ2_mode == 1 || (occ2_mode == 2 && a.residual && a.epi == 0 && p.num_k_chunks <= 10 && m_rows >= 8192);
   p.acc_stages = 2;
   plan.persist_occ = 1;
@@ -644,14 +675,16 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
 void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   if (plan.pair) {
     launch_gemm_pair(plan, stream);
   } else if (plan.persistent) {
     // folded-LayerNorm role of this GEMM (compile-time variants of the epilogue): 1 row consumer, 2 column consumer, 3 producer
-    const int ln = plan.p.ln_parts ? 1 : plan.p.ln_final_in ? 2 : plan.p.rowstat_out ? 3 : 0;
+    static const int lean_pf = getenv("LDN_GEMM_LEAN_PF") ? atoi(getenv("LDN_GEMM_LEAN_PF")) : 1;
+    const int ln = plan.p.ln_parts ? 1 : plan.p.ln_final_in ? 2 : plan.p.rowstat_out ? 3 : plan.lean ? ((lean_pf && plan.p.residual) ? 5 : 4) : 0;
     static bool attr2 = false;
     if (!attr2) {
       auto prime = [](auto kern, int smem_max) { LDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); };
@@ -659,6 +692,8 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
       prime(gemm_tc_persist_kernel<1, 2>, 227 * 1024); prime(gemm_tc_persist_kernel<1, 3>, 227 * 1024);
       prime(gemm_tc_persist_kernel<2, 0>, 113 * 1024); prime(gemm_tc_persist_kernel<2, 1>, 113 * 1024);
       prime(gemm_tc_persist_kernel<2, 2>, 113 * 1024); prime(gemm_tc_persist_kernel<2, 3>, 113 * 1024);
+      prime(gemm_tc_persist_kernel<1, 4>, 227 * 1024); prime(gemm_tc_persist_kernel<2, 4>, 113 * 1024);
+      prime(gemm_tc_persist_kernel<1, 5>, 227 * 1024); prime(gemm_tc_persist_kernel<2, 5>, 113 * 1024);
       attr2 = true;
     }
     auto go = [&](auto kern, int) { kern<<<plan.pgrid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p); };
@@ -667,6 +702,8 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
         case 1: go(gemm_tc_persist_kernel<2, 1>, 113 * 1024); break;
         case 2: go(gemm_tc_persist_kernel<2, 2>, 113 * 1024); break;
         case 3: go(gemm_tc_persist_kernel<2, 3>, 113 * 1024); break;
+        case 4: go(gemm_tc_persist_kernel<2, 4>, 113 * 1024); break;
+        case 5: go(gemm_tc_persist_kernel<2, 5>, 113 * 1024); break;
         default: go(gemm_tc_persist_kernel<2, 0>, 113 * 1024); break;
       }
     } else {
@@ -674,12 +711,17 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
         case 1: go(gemm_tc_persist_kernel<1, 1>, 227 * 1024); break;
         case 2: go(gemm_tc_persist_kernel<1, 2>, 227 * 1024); break;
         case 3: go(gemm_tc_persist_kernel<1, 3>, 227 * 1024); break;
+        case 4: go(gemm_tc_persist_kernel<1, 4>, 227 * 1024); break;
+        case 5: go(gemm_tc_persist_kernel<1, 5>, 227 * 1024); break;
         default: go(gemm_tc_persist_kernel<1, 0>, 227 * 1024); break;
       }
     }
   } else {
     LDN_CHECK(!plan.p.ln_parts && !plan.p.ln_final_in && !plan.p.rowstat_out, "gemm: folded LayerNorm runs on the persistent kernel only (K <= 1280)");
-    gemm_tc_kernel<<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    if (plan.lean)
+      gemm_tc_kernel<true><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    else
+      gemm_tc_kernel<false><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
   }
   LDN_CUDA(cudaGetLastError());
   if (plan.p.splits > 1) {

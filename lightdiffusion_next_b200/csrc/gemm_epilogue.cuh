@@ -53,6 +53,140 @@ __device__ __forceinline__ float2 geglu2(float2 a, float2 g) {
   return fmul2(a, fmul2(g, phi));
 }
 
+// Lean epilogue: out = acc (+ bias) (+ rowbias) (+ residual) as bf16 with 256-bit accesses -- the residual projections,
+// proj_in and the ResBlock convs.  The general epilogue below carries activations, column gates, head-slot scatter, fp32
+// output, GEGLU and split-K as run-time branches; these kernels are bound by their epilogue's instruction stream
+// (profiles/r2_experiments.md section 16: six more live registers and a few dead branches cost 0.38 ms per step), so the
+// common case gets its own compile-time variant.  The residual and bias loads are issued before the TMEM wait.
+__device__ __forceinline__ void gemm_epilogue_tile_lean(const GemmParams& p, const int BN, const int n0, const long long out_row,
+                                                        const int batch, const uint32_t t_lane, const int ehalf) {
+  const float* rb = p.rowbias ? p.rowbias + (long long)batch * p.ld_rowbias : nullptr;
+  for (int c = ehalf * 16; c < BN; c += 32) {
+    uint32_t v[16];
+    tmem_ld16(t_lane + (uint32_t)c, v);
+    const int n = n0 + c;
+    const bool ok = out_row >= 0 && n < p.N;
+    uint32_t w[8];
+    float4 b4[4];
+    if (ok) {
+      if (p.residual) ld_global_256(p.residual + out_row * p.ldr + n, w);
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (rb) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + n) + i);
+          b4[i].x += r4.x; b4[i].y += r4.y; b4[i].z += r4.z; b4[i].w += r4.w;
+        }
+      }
+    }
+    tmem_ld_wait();
+    if (ok) {
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[4 * i] = __uint_as_float(v[4 * i]) + b4[i].x;
+        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4[i].y;
+        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4[i].z;
+        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4[i].w;
+      }
+      if (p.residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[2 * i] += bf16_lo(w[i]);
+          f[2 * i + 1] += bf16_hi(w[i]);
+        }
+      }
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      st_global_256(p.out + out_row * p.ldo + n, o);
+    }
+    __syncwarp();
+  }
+}
+
+// Lean epilogue with the residual PREFETCHED: these GEMMs are bound by the memory-level parallelism of their epilogue --
+// every warp had one 32-byte-per-lane residual read in flight at a time (16 KB per SM against ~1 us of latency = the
+// 2.5 TB/s the K = 320 projections reach).  The persistent kernel's epilogue warps request the residual of the first kPf
+// chunks of their NEXT tile before they wait for its accumulator, so the reads overlap that tile's main loop.
+template <int kPf>
+__device__ __forceinline__ void lean_prefetch_residual(const GemmParams& p, const int BN, const int n0, const long long out_row,
+                                                       const int ehalf, uint32_t (&wres)[kPf][8]) {
+  if (p.residual == nullptr || out_row < 0) return;
+#pragma unroll
+  for (int k = 0; k < kPf; ++k) {
+    const int c = ehalf * 16 + k * 32;
+    if (c < BN && n0 + c < p.N) ld_global_256(p.residual + out_row * p.ldr + n0 + c, wres[k]);
+  }
+}
+template <int kPf>
+__device__ __forceinline__ void gemm_epilogue_tile_lean_pf(const GemmParams& p, const int BN, const int n0, const long long out_row,
+                                                           const int batch, const uint32_t t_lane, const int ehalf,
+                                                           uint32_t (&wres)[kPf][8]) {
+  const float* rb = p.rowbias ? p.rowbias + (long long)batch * p.ld_rowbias : nullptr;
+  auto chunk = [&](const int c, uint32_t* wpre) {
+    uint32_t v[16];
+    tmem_ld16(t_lane + (uint32_t)c, v);
+    const int n = n0 + c;
+    const bool ok = out_row >= 0 && n < p.N;
+    uint32_t wl[8];
+    float4 b4[4];
+    if (ok) {
+      if (p.residual && wpre == nullptr) ld_global_256(p.residual + out_row * p.ldr + n, wl);
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (rb) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + n) + i);
+          b4[i].x += r4.x; b4[i].y += r4.y; b4[i].z += r4.z; b4[i].w += r4.w;
+        }
+      }
+    }
+    tmem_ld_wait();
+    if (ok) {
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[4 * i] = __uint_as_float(v[4 * i]) + b4[i].x;
+        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4[i].y;
+        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4[i].z;
+        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4[i].w;
+      }
+      if (p.residual) {
+        const uint32_t* w = wpre ? wpre : wl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[2 * i] += bf16_lo(w[i]);
+          f[2 * i + 1] += bf16_hi(w[i]);
+        }
+      }
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      st_global_256(p.out + out_row * p.ldo + n, o);
+    }
+    __syncwarp();
+  };
+#pragma unroll
+  for (int k = 0; k < kPf; ++k) {
+    const int c = ehalf * 16 + k * 32;
+    if (c < BN) chunk(c, wres[k]);
+  }
+  for (int c = ehalf * 16 + kPf * 32; c < BN; c += 32) chunk(c, nullptr);
+}
+
 // Drains one 128 x BN fp32 accumulator tile from TMEM (columns starting at t_lane) through the fused epilogue.
 // Executed by the 8 epilogue warps; `ehalf` selects which alternate 16-column chunks this warp handles.
 // `m_row`: the GEMM row index of this thread (token / channel) before any head-slot remapping, or -1 (conv).
