@@ -19,7 +19,7 @@ namespace ldn {
 // The last block to arrive for a batch row (arrival counter) sums the split partials in a fixed order -> (mean, rstd).
 #define LDN_GN_MAX_SPLITS 1024
 
-__global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
+__global__ void __launch_bounds__(640, 2) gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
                                 int cpg, int rows_per_block, int R, double2* __restrict__ partial, unsigned int* __restrict__ counters,
                                 float eps, float2* __restrict__ mean_rstd) {
   const int C = C0 + C1;
@@ -28,7 +28,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16*
   const int cv = threadIdx.x % nvec;
   const int prow = threadIdx.x / nvec;
   const int b = blockIdx.y;
-  __shared__ float s_part[1024][4];  // per thread: {sum_lo, sq_lo, sum_hi, sq_hi} for groups g_lo = c/cpg and g_lo+1
+  __shared__ float s_part[640][4];  // per thread: {sum_lo, sq_lo, sum_hi, sq_hi} for groups g_lo = c/cpg and g_lo+1
   const int c = cv * 8;
   if (active) {
     const bf16* src;
@@ -159,7 +159,8 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU)
 // Same thread layout as the statistics kernel: grid (splits, B), block (C/8)*R threads; a thread owns 8 consecutive
 // channels (scale / shift held in registers) and walks a strided set of pixels with four 16-byte loads in flight.
-__global__ void gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
+// (two blocks of <= 640 threads per SM: at 54 registers the kernel fitted once and a 256-block grid needed two waves)
+__global__ void __launch_bounds__(640, 2) gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
                                 int cpg, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 const float2* __restrict__ mean_rstd, bf16* __restrict__ out, int rows_per_block,
                                 int R) {
@@ -221,7 +222,7 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   const int C = C0 + C1;
   LDN_CHECK(groups == 32, "groupnorm: only 32 groups supported");
   LDN_CHECK(C % 32 == 0 && C % 8 == 0 && C0 % 8 == 0, "groupnorm: channel counts must be multiples of 8/32");
-  LDN_CHECK(C / 8 <= 1024, "groupnorm: too many channels");
+  LDN_CHECK(C / 8 <= 640, "groupnorm: too many channels");
   const int cpg = C / groups;
   // workspace: [B][splits][32] double2 partials, then [B][32] float2 (mean, rstd)
   double2* partial = reinterpret_cast<double2*>(stats_ws);
@@ -230,7 +231,8 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   const int nvec = C / 8;
   // R pixel rows per block pass; every thread should see >= 4 pixels (>= 8 when the tensor is large) so that its
   // 16-byte loads overlap, and the grid should still cover the 148 SMs where the tensor is big enough for that.
-  int R = 1024 / nvec;
+  int R = 640 / nvec;  // blocks of at most 640 threads (the kernels' launch bounds)
+  if (R < 1) R = 1;
   if (R > 16) R = 16;
   while (R > 1 && (HW / (R * 4)) * B < 148) R >>= 1;
   const int threads = (nvec * R + 31) / 32 * 32;
