@@ -74,7 +74,7 @@ struct GemmParams {
   float2* ln_final_out;       // row mode, optional: n-tile 0 / half 0 stores (rstd, -rstd * mean) per row for a later column-mode GEMM
   const float2* ln_final_in;  // column mode (operand-swapped V^T GEMM: output COLUMNS are tokens): per column (rstd, -rstd * mean)
   int acc_stages;    // persistent kernel: accumulator stages in TMEM (2, or 1 when two CTAs share the SM and BN > 128)
-  int epi_opt;       // bit 0: 256-bit epilogue accesses, bit 1: packed-pair GEGLU arithmetic
+  int epi_opt;       // bit 0: 256-bit epilogue accesses, bit 1: packed-pair GEGLU arithmetic, bit 2: MUFU-free polynomial Phi in the packed GEGLU
   int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77),
             // 2 ReLU after the bias, 3 ReLU after the residual add (TAESD, src/AutoEncoders/taesd.py:39-63),
             // 4 GELU (tanh approximation) after the bias (Flux MLPs, src/BlackForest/Flux.py:283-294)

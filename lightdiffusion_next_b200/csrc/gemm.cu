@@ -538,7 +538,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   p.ln_final_in = a.ln_final_in;
   if (a.ln_parts || a.ln_final_in) LDN_CHECK(a.ln_c && a.ln_d && !a.bias && !a.conv, "gemm: folded LayerNorm needs ln_c / ln_d and carries the bias in ln_d");
   if (a.rowstat_out) LDN_CHECK(!a.conv && a.epi == 0 && a.head_dim == 0 && a.row_head_dim == 0 && !a.out_f32, "gemm: row statistics are produced by plain epilogues only");
-  static const int epi_opt = getenv("LDN_GEMM_EPI_OPT") ? atoi(getenv("LDN_GEMM_EPI_OPT")) : 3;
+  static const int epi_opt = getenv("LDN_GEMM_EPI_OPT") ? atoi(getenv("LDN_GEMM_EPI_OPT")) : 7;
   p.epi_opt = epi_opt;
   {  // 256-bit epilogue accesses need 32-byte aligned rows
     const long long ldo_out = a.epi == 1 ? a.ldo : a.ldo;
