@@ -6,6 +6,12 @@
 
 namespace ldn {
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+
 static constexpr int kBM = 128;
 static constexpr int kBK = 64;
 static constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
@@ -302,8 +308,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
           }
         }
         if (p.act == 1) {
+          // x * sigmoid(1.702 x) = x * (0.5 + 0.5 tanh(0.851 x)): one MUFU (tanh.approx, rel. error 2^-11) instead of ex2 + rcp
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = f[i] / (1.0f + __expf(-1.702f * f[i]));
+          for (int i = 0; i < 16; ++i) {
+            const float hx = 0.5f * f[i];
+            f[i] = fmaf(hx, tanh_approx(0.851f * f[i]), hx);
+          }
         } else if (p.act == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -313,7 +323,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const in
           for (int i = 0; i < 16; ++i) {
             const float x = f[i];
             const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
-            f[i] = __fdividef(x, 1.0f + __expf(-2.0f * u));
+            const float hx = 0.5f * x;
+            f[i] = fmaf(hx, tanh_approx(u), hx);  // one MUFU instead of ex2 + rcp
           }
         }
         if (p.colgate) {
