@@ -490,7 +490,7 @@ def hbm_roofline(eng, dev, bs: int, lat: int, peaks: dict) -> dict:
 
 def sharded_metrics(eng, size: int, dev, world: int, rank: int) -> dict:
     """BASELINE config 3 (bs = 32 in total, 32 / N images per GPU, UNet batch 8 per call) and config 5 (one HiresFix image per
-    GPU: 512 -> bislerp x4 latent -> 2048, 10 steps euler_ancestral_cfgpp / normal / denoise 0.45, VAE decode 2048^2) through
+    GPU: 512 -> bislerp x4 latent (ldn_bislerp) -> 2048, 10 steps euler_ancestral_cfgpp / normal / denoise 0.45, VAE decode 2048^2) through
     the product's sharded driver (distributed.sample_sharded: per-rank replay of the full-batch noise, no collective in the
     loop, gather of the final latents on rank 0).  Wall clock bracketed by barrier + device synchronise on every rank, max
     over ranks.  In-run check: rank 0 recomputes the LAST rank's last four images in its own process and compares them with the
@@ -548,13 +548,15 @@ def sharded_metrics(eng, size: int, dev, world: int, rank: int) -> dict:
 
         def hires_run(seed, steps1, steps2):
             first = D.sample_sharded(eng, seed, steps1, 7.0, "dpmpp_2m_cfgpp", "karras", pos, neg, lat5, images_per_call=1)[0]
-            # LatentUpscale runs on the host in the reference (bislerp, src/Utilities/upscale.py); rank 0 holds the batch
+            # LatentUpscale (bislerp, src/Utilities/upscale.py) on the engine's kernel; rank 0 holds the gathered batch
+            def upscale(lat):
+                return latent_upscale({"samples": lat["samples"].to(dev)}, 2048, 2048, engine=eng)["samples"].cpu()
             if world > 1:
-                up = [latent_upscale({"samples": first["samples"]}, 2048, 2048)["samples"]] if rank == 0 else [None]
+                up = [upscale(first)] if rank == 0 else [None]
                 dist.broadcast_object_list(up, 0)
                 up = up[0]
             else:
-                up = latent_upscale({"samples": first["samples"]}, 2048, 2048)["samples"]
+                up = upscale(first)
             second = D.sample_sharded(eng, seed + 1, steps2, 8.0, "euler_ancestral_cfgpp", "normal", pos, neg, {"samples": up},
                                       images_per_call=1, denoise=0.45)[0]
             lo, hi = D.shard_range(n_img, rank, world)
@@ -571,7 +573,7 @@ def sharded_metrics(eng, size: int, dev, world: int, rank: int) -> dict:
         barrier()
         dt5 = tmax(time.perf_counter() - t0)
         out["config5"] = {"what": f"SD1.5 HiresFix 512 -> 2048 + VAE decode 2048^2, 1 image/GPU on {world} GPU(s): 20 steps dpmpp_2m_cfgpp @512 "
-                                  "(reference-default multiscale), bislerp x4 on the host, 10 steps euler_ancestral_cfgpp/normal/denoise 0.45 "
+                                  "(reference-default multiscale), bislerp x4 on the device (ldn_bislerp), 10 steps euler_ancestral_cfgpp/normal/denoise 0.45 "
                                   "@2048, decode, images gathered on rank 0",
                           "seconds": dt5, "images_per_s": n_img / dt5,
                           "finite": bool(torch.isfinite(imgs).all()) if rank == 0 else None,

@@ -82,6 +82,11 @@ int ldn_cfg_step(const float* x, const float* den_uncond, const float* den_cond,
  * F.interpolate(mode="bilinear", align_corners=False): the down / up-scaling around the reference's half-resolution
  * (multiscale) sampler steps, src/sample/samplers.py:821-835 (dpmpp_2m_cfgpp), :1035-1051 (dpmpp_sde_cfgpp). */
 int ldn_resample_bilinear(const float* src, float* dst, int planes, int h, int w, int oh, int ow, void* stream);
+/* `bislerp` of the reference's LatentUpscale (src/Utilities/upscale.py:5-128, 144-166: the HiresFix branch of pipeline()):
+ * src [n, c, h, w] fp32 -> dst [n, c, oh, ow] fp32, a separable resize (width first) whose two-tap blend is a spherical
+ * interpolation of the c-vectors with the tap positions / ratios of bilinear resampling.  tmp: n * c * h * ow floats of
+ * scratch.  All pointers are device pointers. */
+int ldn_bislerp(const float* src, float* tmp, float* dst, int n, int c, int h, int w, int oh, int ow, void* stream);
 
 /* ---- VAE decode / CLIP encode */
 /* z: [B,zc,h,w] fp32, already un-scaled by the latent format (SD1.x: zc = 4, z / 0.18215; Flux VAE: zc = 16, no

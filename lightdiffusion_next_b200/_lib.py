@@ -47,6 +47,7 @@ SIGNATURES = {
     "ldn_unet_last_launches": [_p],
     "ldn_cfg_step": [_p, _p, _p, _f, _i, _f, _f, _f, _p, _p, _p, _l, _p],
     "ldn_resample_bilinear": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "ldn_bislerp": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "ldn_vae_decode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_vae_encode": [_p, _p, _p, _i, _i, _i, _p],
     "ldn_taesd_decode": [_p, _p, _p, _i, _i, _i, _p],

@@ -278,6 +278,7 @@ void launch_conv1x1_f32(const float* x, const float* W, const float* bias, int B
 // out[r, :] = (ids[r] < vocab ? tok_emb[ids[r], :] : extra[ids[r] - vocab, :]) + pos_emb[r % T, :]  -> bf16
 void launch_clip_embed(const long long* ids, const float* tok_emb, int vocab, const float* extra, const int* extra_n,
                        const float* pos_emb, int rows, int T, int C, bf16* out, cudaStream_t stream);
+void launch_bislerp(const float* src, float* tmp, float* dst, int n, int c, int h, int w, int H, int W, cudaStream_t stream);
 void launch_softmax_rows(const bf16* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,
                          cudaStream_t stream);
 void launch_softmax_rows_f32(const float* in, long long ld_in, bf16* out, long long ld_out, int rows, int cols, float scale,

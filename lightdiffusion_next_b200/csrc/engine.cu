@@ -268,6 +268,13 @@ int ldn_resample_bilinear(const float* src, float* dst, int planes, int h, int w
   LDN_API_END
 }
 
+int ldn_bislerp(const float* src, float* tmp, float* dst, int n, int c, int h, int w, int oh, int ow, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(src && tmp && dst && n >= 0 && c > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "ldn_bislerp: bad argument");
+  if (n > 0) launch_bislerp(src, tmp, dst, n, c, h, w, oh, ow, (cudaStream_t)stream);
+  LDN_API_END
+}
+
 int ldn_vae_decode(ldn_handle h, const float* z, float* rgb, int B, int lat_h, int lat_w, void* stream) {
   LDN_API_BEGIN
   LDN_CHECK(h && z && rgb, "ldn_vae_decode: bad argument");

@@ -620,6 +620,84 @@ void launch_resample_bilinear(const float* src, float* dst, int planes, int h, i
   LDN_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------ bislerp (LatentUpscale of the HiresFix branch)
+// One separable pass of the reference's `bislerp` (src/Utilities/upscale.py:5-128): along one axis the two taps of bilinear
+// resampling (positions and ratio derived exactly as the reference derives them: bilinear interpolation of the index
+// ramps, floor / truncation) are blended SPHERICALLY as C-vectors -- directions slerped, norms blended linearly; nearly
+// parallel vectors take the first tap, nearly opposite ones a linear blend.  One thread per output position of a line.
+// Strides in elements: element (line, c, i) lives at base(line) + c * stride_c + i * stride_i.
+__global__ void bislerp_pass_kernel(const float* __restrict__ src, float* __restrict__ dst, int lines, int inner, int C,
+                                    int L_in, int L_out, long long in_outer, long long in_inner, long long in_c, long long in_i,
+                                    long long out_outer, long long out_inner, long long out_c, long long out_i) {
+  const long long total = (long long)lines * L_out;
+  const float scale = (float)L_in / (float)L_out;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(idx % L_out);
+    const int line = (int)(idx / L_out);
+    const int lo_ = line % inner, ou_ = line / inner;
+    // taps: F.interpolate(arange(L_in), size=L_out, mode="bilinear") and the same for the ramp shifted by one (last entry clamped)
+    float sp = scale * ((float)X + 0.5f) - 0.5f;
+    sp = sp < 0.f ? 0.f : sp;
+    const int i0 = (int)sp;
+    const int ip = i0 < L_in - 1 ? 1 : 0;
+    const float l1 = sp - (float)i0, l0 = 1.f - l1;
+    const float v1 = __fadd_rn(__fmul_rn(l0, (float)i0), __fmul_rn(l1, (float)(i0 + ip)));
+    const float r = v1 - floorf(v1);
+    const int c1 = (int)v1;
+    const float h0 = (float)min(i0 + 1, L_in - 1), h1 = (float)min(i0 + ip + 1, L_in - 1);
+    const int c2 = (int)__fadd_rn(__fmul_rn(l0, h0), __fmul_rn(l1, h1));
+    const float* a = src + ou_ * in_outer + lo_ * in_inner + (long long)c1 * in_i;
+    const float* b = src + ou_ * in_outer + lo_ * in_inner + (long long)c2 * in_i;
+    float na = 0.f, nb = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float x = a[c * in_c], y = b[c * in_c];
+      na = fmaf(x, x, na);
+      nb = fmaf(y, y, nb);
+    }
+    na = sqrtf(na);
+    nb = sqrtf(nb);
+    float dot = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float ua = na == 0.f ? 0.f : a[c * in_c] / na;
+      const float ub = nb == 0.f ? 0.f : b[c * in_c] / nb;
+      dot = fmaf(ua, ub, dot);
+    }
+    const float omega = acosf(dot);
+    const float so = sinf(omega);
+    const float wa = sinf((1.f - r) * omega) / so, wb = sinf(r * omega) / so;
+    const float nrm = na * (1.f - r) + nb * r;
+    float* o = dst + ou_ * out_outer + lo_ * out_inner + (long long)X * out_i;
+    for (int c = 0; c < C; ++c) {
+      const float x = a[c * in_c], y = b[c * in_c];
+      const float ua = na == 0.f ? 0.f : x / na;
+      const float ub = nb == 0.f ? 0.f : y / nb;
+      float res = (wa * ua + wb * ub) * nrm;
+      if (dot > 1.f - 1e-5f) res = x;
+      if (dot < 1e-5f - 1.f) res = x * (1.f - r) + y * r;
+      o[c * out_c] = res;
+    }
+  }
+}
+// src [n, c, h, w] fp32 -> dst [n, c, H, W] fp32; tmp holds n * c * h * W floats (width pass first, as the reference).
+void launch_bislerp(const float* src, float* tmp, float* dst, int n, int c, int h, int w, int H, int W, cudaStream_t stream) {
+  {
+    const long long total = (long long)n * h * W;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bislerp_pass_kernel<<<blocks, 256, 0, stream>>>(src, tmp, n * h, h, c, w, W, (long long)c * h * w, w, (long long)h * w, 1,
+                                                    (long long)c * h * W, W, (long long)h * W, 1);
+    LDN_CUDA(cudaGetLastError());
+  }
+  {
+    const long long total = (long long)n * W * H;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bislerp_pass_kernel<<<blocks, 256, 0, stream>>>(tmp, dst, n * W, W, c, h, H, (long long)c * h * W, 1, (long long)h * W, W,
+                                                    (long long)c * H * W, 1, (long long)H * W, W);
+    LDN_CUDA(cudaGetLastError());
+  }
+}
+
 // ------------------------------------------------------------------ row softmax (VAE mid attention, materialised scores)
 // out[r, :] = softmax(in[r, :] * scale); one block per row.
 __global__ void softmax_rows_kernel(const bf16* __restrict__ in, long long ld_in, bf16* __restrict__ out,

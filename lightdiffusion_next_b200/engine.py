@@ -184,6 +184,19 @@ class Engine:
             L.check(self.lib.ldn_resample_bilinear(x.data_ptr(), out.data_ptr(), B * Cc, h, w, oh, ow, L.cur_stream()))
         return out
 
+    def bislerp(self, x: torch.Tensor, width: int, height: int) -> torch.Tensor:
+        """`bislerp(samples, width, height)` of the reference (src/Utilities/upscale.py:5-128) on the device: [n,c,h,w] fp32 ->
+        [n,c,height,width] fp32, two launches of the engine's separable slerp kernel (width first, as the reference)."""
+        assert x.is_cuda
+        xf = x.to(torch.float32).contiguous()
+        n, c, h, w = xf.shape
+        tmp = torch.empty(n, c, h, int(width), device=xf.device, dtype=torch.float32)
+        out = torch.empty(n, c, int(height), int(width), device=xf.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ldn_bislerp(xf.data_ptr(), tmp.data_ptr(), out.data_ptr(), n, c, h, w, int(height), int(width),
+                                         L.cur_stream()))
+        return out.to(x.dtype)
+
     # ------------------------------------------------------------------ VAE / CLIP
     def vae_decode(self, z: torch.Tensor) -> torch.Tensor:
         """z [B,4,h,w] fp32 (already / 0.18215) -> [B,8h,8w,3] fp32 in [0,1] (VAE.decode semantics)."""

@@ -44,10 +44,16 @@ def bislerp(samples: torch.Tensor, width: int, height: int) -> torch.Tensor:
     return x.permute(0, 2, 3, 1).contiguous().to(samples.dtype)      # [n, c, H, W]
 
 
-def latent_upscale(latent: dict, width: int, height: int) -> dict:
-    """LatentUpscale node: pixel sizes in, latent dict out (sizes clamped to >= 64 px like the reference)."""
+def latent_upscale(latent: dict, width: int, height: int, engine=None) -> dict:
+    """LatentUpscale node: pixel sizes in, latent dict out (sizes clamped to >= 64 px like the reference).  With an engine
+    and device-resident samples the resize runs on the engine's bislerp kernel (`ldn_bislerp`), otherwise on the host
+    restatement above (which is what the reference itself does with its CPU-resident latents)."""
     if width == 0 and height == 0:
         return latent
     out = dict(latent)
-    out["samples"] = bislerp(latent["samples"], max(64, width) // 8, max(64, height) // 8)
+    s = latent["samples"]
+    if engine is not None and s.is_cuda:
+        out["samples"] = engine.bislerp(s, max(64, width) // 8, max(64, height) // 8)
+    else:
+        out["samples"] = bislerp(s, max(64, width) // 8, max(64, height) // 8)
     return out

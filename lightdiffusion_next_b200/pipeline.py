@@ -131,7 +131,7 @@ def hires_fix(pipe: "Pipeline", samples: torch.Tensor, positive: torch.Tensor, n
     then a second KSampler pass with partial denoise.  `samples`: latents as returned by Pipeline.sample."""
     from .latent import latent_upscale
 
-    up = latent_upscale({"samples": samples}, width * 2, height * 2)
+    up = latent_upscale({"samples": samples}, width * 2, height * 2, engine=pipe.e if hasattr(pipe.e, "bislerp") else None)
     return S.sample(pipe.e, seed, steps, cfg, sampler_name, scheduler, positive, negative, up, denoise=denoise)[0]["samples"]
 
 

@@ -167,6 +167,27 @@ def test_hires_partial_denoise_vs_oracle(engine, unet_sd):
                    denoise=0.6)[0]["samples"]
     assert rel(out, ref) < TRAJ_TOL, rel(out, ref)
 
+def test_bislerp_on_the_device(engine):
+    """`ldn_bislerp` (the HiresFix LatentUpscale on the device) against the host restatement, which is bit-identical to the
+    reference's `bislerp` (tests/golden/hires_small.pt): the golden upscale itself, integer and fractional ratios, a
+    downscale, and a latent with a zero vector / parallel / opposite neighbours (the slerp's special cases)."""
+    from lightdiffusion_next_b200.latent import bislerp
+    g = torch.load(os.path.join(GOLDEN, "hires_small.pt"))
+    up = engine.bislerp(g["lat"].cuda(), 16, 16).cpu()
+    assert rel(up, g["up"]) < 1e-5 and float((up - g["up"]).abs().max()) < 1e-4
+    gen = torch.Generator().manual_seed(7)
+    for (n, c, h, w, H, W) in [(1, 4, 64, 64, 256, 256), (2, 4, 24, 40, 61, 77), (1, 16, 32, 32, 48, 80), (1, 4, 40, 24, 16, 16)]:
+        x = torch.randn(n, c, h, w, generator=gen)
+        if (n, c, h, w) == (2, 4, 24, 40):
+            x[0, :, 3, 5] = 0.0                     # zero vector
+            x[0, :, 7, 9] = 2.5 * x[0, :, 7, 8]     # parallel neighbours (first tap wins)
+            x[1, :, 11, 4] = -0.5 * x[1, :, 11, 3]  # opposite neighbours (linear blend)
+        ref = bislerp(x, W, H)
+        out = engine.bislerp(x.cuda(), W, H).cpu()
+        assert out.shape == ref.shape
+        assert rel(out, ref) < 1e-5, (n, c, h, w, H, W, rel(out, ref))
+        assert float((out - ref).abs().max()) < 1e-3
+
 
 def test_resample_bilinear_matches_aten(engine):
     import torch.nn.functional as F
