@@ -210,6 +210,8 @@ def test_entry_points_reject_null_arguments_with_an_error_code():
         "ldn_flux_forward": (None, None, None, None, None, None, None, None, 1, 16, 16, None),
         "ldn_clip_encode": (None, None, 1, None, None, None),
         "ldn_t5_encode": (None, None, None, 1, 16, None, None),
+        "ldn_resample_bilinear": (None, None, 1, 8, 8, 4, 4, None),
+        "ldn_bislerp": (None, None, None, 1, 4, 8, 8, 16, 16, None),
     }
     for name, args in calls.items():
         rc = getattr(lib, name)(*args)
