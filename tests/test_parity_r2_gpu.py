@@ -167,6 +167,7 @@ def test_hires_partial_denoise_vs_oracle(engine, unet_sd):
                    denoise=0.6)[0]["samples"]
     assert rel(out, ref) < TRAJ_TOL, rel(out, ref)
 
+
 def test_bislerp_on_the_device(engine):
     """`ldn_bislerp` (the HiresFix LatentUpscale on the device) against the host restatement, which is bit-identical to the
     reference's `bislerp` (tests/golden/hires_small.pt): the golden upscale itself, integer and fractional ratios, a
@@ -187,6 +188,35 @@ def test_bislerp_on_the_device(engine):
         assert out.shape == ref.shape
         assert rel(out, ref) < 1e-5, (n, c, h, w, H, W, rel(out, ref))
         assert float((out - ref).abs().max()) < 1e-3
+
+def test_pipeline_img2img_vs_oracle(engine, unet_sd):
+    """`Pipeline.img2img` (VAEEncode -> KSampler with denoise < 1, the img2img branch of the reference's pipeline,
+    src/user/pipeline.py:120-216 / VariationalAE.py:787-801) on the GPU: the encoded posterior sample against the oracle's
+    encoder with the same noise, and the partial-denoise pass from that latent against the fp32 oracle sampler."""
+    from lightdiffusion_next_b200.pipeline import Pipeline
+    from oracle import hires_oracle as H
+    from oracle import sd15_oracle as O
+    g = torch.load(os.path.join(GOLDEN, "hires_small.pt"))
+    vsd = dict(O.synth_state_dict(O.vae_decoder_param_shapes(), seed=4321))
+    vsd.update(O.synth_state_dict(O.vae_encoder_param_shapes(), seed=2468))
+    engine.load_vae(vsd)
+    pipe = Pipeline(engine)
+    pixels = torch.rand(1, 128, 128, 3, generator=torch.Generator().manual_seed(3))
+    noise = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(4))
+    mean, logvar = O.vae_encode_moments(vsd, pixels).chunk(2, dim=1)
+    enc_ref = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+    enc = engine.vae_encode(pixels, noise=noise)
+    assert rel(enc, enc_ref) < 2e-2, rel(enc, enc_ref)
+    # the pipeline call draws the posterior noise from the global CPU generator, like the reference
+    torch.manual_seed(11)
+    expect_noise = torch.randn(1, 4, 16, 16)
+    torch.manual_seed(11)
+    out = pipe.img2img(pixels, g["ctx_pos"], g["ctx_neg"], seed=21, steps=5, cfg=8.0, denoise=0.6, sampler_name="dpmpp_2m_cfgpp",
+                       scheduler="normal")  # (reference-default multiscale schedule, as the oracle's sampler runs it)
+    lat0 = engine.vae_encode(pixels, noise=expect_noise)
+    ref = H.ksample(unet_sd, 21, 5, 8.0, "dpmpp_2m_cfgpp", "normal", g["ctx_pos"], g["ctx_neg"], lat0, denoise=0.6)
+    assert out.shape == (1, 4, 16, 16) and torch.isfinite(out).all()
+    assert rel(out, ref) < TRAJ_TOL, rel(out, ref)
 
 
 def test_resample_bilinear_matches_aten(engine):
