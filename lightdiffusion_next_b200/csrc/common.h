@@ -212,10 +212,12 @@ void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / pointwise kernels (norm.cu, pointwise.cu)
 // GroupNorm over NHWC bf16 input that may be a virtual concat of two tensors along C.
-// stats_ws: workspace of groupnorm_ws_bytes(B) bytes.
-inline size_t groupnorm_ws_bytes(int B) { return (size_t)B * 1024 * 32 * 16 + (size_t)B * 32 * 8 + (size_t)B * 4 + 256; }  // must be zero-initialised (arrival counters)
+// stats_ws: workspace of groupnorm_ws_bytes(B) bytes: LDN_GN_SLOTS statistics slots ([B][32] x two 64-bit fixed-point totals).
+// Every GroupNorm instance of a program uses its own slot; the whole workspace is zeroed once per program execution.
+#define LDN_GN_SLOTS 160
+inline size_t groupnorm_ws_bytes(int B) { return (size_t)LDN_GN_SLOTS * B * 64 * sizeof(unsigned long long); }
 void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
-                      const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws,
+                      const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws, int slot,
                       cudaStream_t stream);
 void launch_layernorm(const bf16* x, int rows, int C, float eps, const float* gamma, const float* beta, bf16* out,
                       cudaStream_t stream, float* out_f32 = nullptr);

@@ -348,7 +348,8 @@ int ldn_groupnorm_bf16(const void* x0, int C0, const void* x1, int C1, int B, in
     LDN_CUDA(cudaMemset(ws, 0, groupnorm_ws_bytes(B)));
     ws_b = B;
   }
-  launch_groupnorm((const bf16*)x0, C0, (const bf16*)x1, C1, B, HW, groups, eps, gamma, beta, silu != 0, (bf16*)out, ws,
+  LDN_CUDA(cudaMemsetAsync(ws, 0, (size_t)B * 64 * sizeof(unsigned long long), (cudaStream_t)stream));  // statistics slot 0
+  launch_groupnorm((const bf16*)x0, C0, (const bf16*)x1, C1, B, HW, groups, eps, gamma, beta, silu != 0, (bf16*)out, ws, 0,
                    (cudaStream_t)stream);
   LDN_API_END
 }

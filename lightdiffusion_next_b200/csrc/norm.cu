@@ -12,16 +12,20 @@
 
 namespace ldn {
 
-// ------------------------------------------------------------------ GroupNorm statistics (deterministic: no atomics)
+// ------------------------------------------------------------------ GroupNorm statistics (deterministic)
 // Kernel 1, grid (splits, B), block (C/8)*R threads: every thread owns 8 consecutive channels for a strided set of
 // pixels, folds them into at most two (group, sum, sumsq) partials in shared memory, then warp g reduces the partials of
-// group g in a fixed order and writes one double2 per (batch, split, group).
-// The last block to arrive for a batch row (arrival counter) sums the split partials in a fixed order -> (mean, rstd).
-#define LDN_GN_MAX_SPLITS 1024
+// group g in a fixed order and ADDS them to the (batch, group) accumulator of this GroupNorm instance as 64-bit FIXED-POINT
+// integers (sum * 2^16, sum of squares * 2^12): integer addition is associative, so the totals do not depend on the order
+// in which the blocks arrive -- bit-deterministic without the arrival counter + memory fence + serial last-block fold the
+// first version ended with (a ~3 us tail on a ~6 us kernel).  The apply kernel converts the totals itself.  Accumulators
+// live in per-instance slots of the workspace, zeroed once per program execution (one memset node at its start).
+// Range: |sum| < 1.4e14, sum of squares < 2.2e15 per (batch, group) -- an RMS of ~67 000 over a 491 520-element group.
+#define LDN_GN_SUM_SCALE 65536.0
+#define LDN_GN_SQ_SCALE 4096.0
 
 __global__ void __launch_bounds__(640, 2) gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
-                                int cpg, int rows_per_block, int R, double2* __restrict__ partial, unsigned int* __restrict__ counters,
-                                float eps, float2* __restrict__ mean_rstd) {
+                                int cpg, int rows_per_block, int R, unsigned long long* __restrict__ acc) {
   const int C = C0 + C1;
   const int nvec = C >> 3;
   const bool active = (int)threadIdx.x < nvec * R;  // the block is padded to whole warps
@@ -118,39 +122,10 @@ __global__ void __launch_bounds__(640, 2) gn_stats_kernel(const bf16* __restrict
       sum += __shfl_xor_sync(0xffffffffu, sum, o);
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
-    if (lane == 0) partial[((size_t)b * gridDim.x + blockIdx.x) * 32 + g] = make_double2(sum, sq);
-  }
-  // The last block to finish for this batch row folds the split partials into (mean, rstd) -- in a fixed order, so the
-  // result does not depend on which block happens to be last (deterministic) -- and re-arms the counter.
-  __shared__ unsigned int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[b], 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    const int splits = gridDim.x;
-    const double n = (double)HW * cpg;
-    for (int g = warp; g < 32; g += nwarps) {
-      double sum = 0.0, sq = 0.0;
-      for (int sp = lane; sp < splits; sp += 32) {
-        const double2 v = __ldcg(&partial[((size_t)b * splits + sp) * 32 + g]);
-        sum += v.x;
-        sq += v.y;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      }
-      if (lane == 0) {
-        const double mean = sum / n;
-        double var = sq / n - mean * mean;
-        if (var < 0) var = 0;
-        mean_rstd[b * 32 + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
-      }
+    if (lane == 0) {
+      atomicAdd(&acc[(b * 32 + g) * 2], (unsigned long long)__double2ll_rn(sum * LDN_GN_SUM_SCALE));
+      atomicAdd(&acc[(b * 32 + g) * 2 + 1], (unsigned long long)__double2ll_rn(sq * LDN_GN_SQ_SCALE));
     }
-    if (threadIdx.x == 0) counters[b] = 0;
   }
 }
 
@@ -170,8 +145,8 @@ __device__ __forceinline__ float silu_f(float x) {
 // (two blocks of <= 640 threads per SM: at 54 registers the kernel fitted once and a 256-block grid needed two waves)
 __global__ void __launch_bounds__(640, 2) gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
                                 int cpg, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                const float2* __restrict__ mean_rstd, bf16* __restrict__ out, int rows_per_block,
-                                int R) {
+                                const unsigned long long* __restrict__ acc, float eps, bf16* __restrict__ out,
+                                int rows_per_block, int R) {
   const int C = C0 + C1;
   const int nvec = C >> 3;
   if ((int)threadIdx.x >= nvec * R) return;  // the block is padded to whole warps
@@ -179,12 +154,29 @@ __global__ void __launch_bounds__(640, 2) gn_apply_kernel(const bf16* __restrict
   const int prow = threadIdx.x / nvec;
   const int b = blockIdx.y;
   const int c = cv * 8;
+  // (mean, rstd) of the (at most two) groups this thread's 8 channels touch, from the fixed-point totals
+  const int g_lo = c / cpg;
+  float mean2[2], rstd2[2];
+  {
+    const double n = (double)HW * cpg;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int g = min(g_lo + k, 31);
+      const double sum = (double)(long long)acc[(b * 32 + g) * 2] * (1.0 / LDN_GN_SUM_SCALE);
+      const double sq = (double)(long long)acc[(b * 32 + g) * 2 + 1] * (1.0 / LDN_GN_SQ_SCALE);
+      const double mean = sum / n;
+      double var = sq / n - mean * mean;
+      if (var < 0) var = 0;
+      mean2[k] = (float)mean;
+      rstd2[k] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
   float a[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float2 mr = mean_rstd[b * 32 + (c + i) / cpg];
-    a[i] = mr.y * gamma[c + i];
-    sh[i] = beta[c + i] - mr.x * a[i];
+    const int k = ((c + i) / cpg == g_lo) ? 0 : 1;
+    a[i] = rstd2[k] * gamma[c + i];
+    sh[i] = beta[c + i] - mean2[k] * a[i];
   }
   const bf16* src;
   int ld;
@@ -225,17 +217,16 @@ __global__ void __launch_bounds__(640, 2) gn_apply_kernel(const bf16* __restrict
 }
 
 void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
-                      const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws,
+                      const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws, int slot,
                       cudaStream_t stream) {
   const int C = C0 + C1;
   LDN_CHECK(groups == 32, "groupnorm: only 32 groups supported");
   LDN_CHECK(C % 32 == 0 && C % 8 == 0 && C0 % 8 == 0, "groupnorm: channel counts must be multiples of 8/32");
   LDN_CHECK(C / 8 <= 640, "groupnorm: too many channels");
+  LDN_CHECK(slot >= 0 && slot < LDN_GN_SLOTS, "groupnorm: statistics slot out of range");
   const int cpg = C / groups;
-  // workspace: [B][splits][32] double2 partials, then [B][32] float2 (mean, rstd)
-  double2* partial = reinterpret_cast<double2*>(stats_ws);
-  float2* mean_rstd = reinterpret_cast<float2*>(partial + (size_t)B * LDN_GN_MAX_SPLITS * 32);
-  unsigned int* counters = reinterpret_cast<unsigned int*>(mean_rstd + (size_t)B * 32);  // zero-initialised workspace
+  // workspace: [slot][B][32] x (sum, sum of squares) as 64-bit fixed point; the slot must be zero when the statistics run
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(stats_ws) + (size_t)slot * B * 64;
   const int nvec = C / 8;
   // R pixel rows per block pass; every thread should see >= 4 pixels (>= 8 when the tensor is large) so that its
   // 16-byte loads overlap, and the grid should still cover the 148 SMs where the tensor is big enough for that.
@@ -248,15 +239,14 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   int rows_per_block = (HW + want_blocks - 1) / want_blocks;
   if (rows_per_block < 8 * R) rows_per_block = (HW >= 8 * R * want_blocks / 2) ? 8 * R : 4 * R;
   int splits = (HW + rows_per_block - 1) / rows_per_block;
-  if (splits > LDN_GN_MAX_SPLITS) {
-    rows_per_block = (HW + LDN_GN_MAX_SPLITS - 1) / LDN_GN_MAX_SPLITS;
+  if (splits > 1024) {
+    rows_per_block = (HW + 1023) / 1024;
     splits = (HW + rows_per_block - 1) / rows_per_block;
   }
-  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, R, partial, counters,
-                                                           eps, mean_rstd);
+  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, R, acc);
   LDN_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, gamma, beta, silu ? 1 : 0,
-                                                           mean_rstd, out, rows_per_block, R);
+  gn_apply_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, gamma, beta, silu ? 1 : 0, acc, eps, out,
+                                                           rows_per_block, R);
   LDN_CUDA(cudaGetLastError());
 }
 

@@ -431,6 +431,7 @@ struct Builder {
   float* splitk_ws = nullptr;
   size_t splitk_ws_bytes = 0;
   float* gn_ws = nullptr;
+  int gn_slots = 0;
   float2* ln_parts = nullptr;  // [tokens, 16] row-statistics partials of the token stream (folded LayerNorm)
   float2* ln_final = nullptr;  // [tokens] (rstd, -rstd * mean) of norm1, for the operand-swapped V^T GEMM
   float *temb = nullptr, *emb1 = nullptr, *emb = nullptr, *emb_all = nullptr;
@@ -459,7 +460,9 @@ struct Builder {
     const float* b = e->W(0, wprefix + ".bias").f();
     float* ws = gn_ws;
     int Bn = B;
-    add(name, [=](cudaStream_t st) { launch_groupnorm(x0, C0, x1, C1, Bn, HW, 32, eps, g, b, silu, out, ws, st); }, 2);  // stats + apply
+    const int slot = gn_slots++;  // every GroupNorm instance accumulates its statistics in its own (pre-zeroed) slot
+    LDN_CHECK(slot < LDN_GN_SLOTS, "too many GroupNorm instances for the statistics workspace");
+    add(name, [=](cudaStream_t st) { launch_groupnorm(x0, C0, x1, C1, Bn, HW, 32, eps, g, b, silu, out, ws, slot, st); }, 2);  // stats + apply
   }
   void layernorm(const std::string& name, const bf16* x, int rows, int C, const std::string& wprefix, bf16* out) {
     const float* g = e->W(0, wprefix + ".weight").f();
@@ -708,6 +711,11 @@ static Program* build_unet_program(ldn_engine* e, int B, int H, int W) {
     }
   }
   bd.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B), true));
+  {  // first node of the program: zero the GroupNorm statistics slots (fixed-point accumulators, norm.cu)
+    float* ws = bd.gn_ws;
+    const size_t bytes = groupnorm_ws_bytes(B);
+    bd.add("groupnorm.zero_statistics", [=](cudaStream_t st) { LDN_CUDA(cudaMemsetAsync(ws, 0, bytes, st)); }, 0);
+  }
   bd.ln_parts = A.get<float2>((size_t)B * H * W * 16, true);
   bd.ln_final = A.get<float2>((size_t)B * H * W + 16, true);
   bd.temb = A.get<float>((size_t)B * U.model_ch);

@@ -74,6 +74,7 @@ struct VB {
   int B;
   bf16 *sA = nullptr, *sB = nullptr, *sC = nullptr;
   float* gn_ws = nullptr;
+  int gn_slots = 0;
 
   void add(const std::string& name, Step s, int launches = 1) {
     P.steps.push_back(std::move(s));
@@ -92,7 +93,9 @@ struct VB {
     const float* b = e->W(1, wp + ".bias").f();
     float* ws = gn_ws;
     const int Bn = B;
-    add(name, [=](cudaStream_t st) { launch_groupnorm(x, C, nullptr, 0, Bn, HW, 32, 1e-6f, g, b, silu, out, ws, st); }, 2);
+    const int slot = gn_slots++;
+    LDN_CHECK(slot < LDN_GN_SLOTS, "too many GroupNorm instances for the statistics workspace");
+    add(name, [=](cudaStream_t st) { launch_groupnorm(x, C, nullptr, 0, Bn, HW, 32, 1e-6f, g, b, silu, out, ws, slot, st); }, 2);
   }
   void conv(const std::string& name, const std::string& wp, const bf16* x, int H, int W, int Cin, int Cout,
             const bf16* residual, bf16* out) {
@@ -213,6 +216,11 @@ static Program* build_vae_program(ldn_engine* e, int B, int h, int w) {
   vb.sB = A.get<bf16>(max_act);
   vb.sC = A.get<bf16>(max_act);
   vb.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B), true));
+  {  // first node of the program: zero the GroupNorm statistics slots
+    float* ws = vb.gn_ws;
+    const size_t bytes = groupnorm_ws_bytes(B);
+    vb.add("groupnorm.zero_statistics", [=](cudaStream_t st) { LDN_CUDA(cudaMemsetAsync(ws, 0, bytes, st)); }, 0);
+  }
   prog->io_elems = (size_t)B * V.zc * h * w;
   prog->in_x = A.get<float>(prog->io_elems);
   float* zq = A.get<float>(prog->io_elems);
@@ -327,6 +335,11 @@ static Program* build_vae_enc_program(ldn_engine* e, int B, int H, int W) {
   vb.sC = A.get<bf16>(max_act);
   bf16* col = A.get<bf16>(std::max<size_t>(max_col, 16));
   vb.gn_ws = reinterpret_cast<float*>(A.alloc(groupnorm_ws_bytes(B), true));
+  {  // first node of the program: zero the GroupNorm statistics slots
+    float* ws = vb.gn_ws;
+    const size_t bytes = groupnorm_ws_bytes(B);
+    vb.add("groupnorm.zero_statistics", [=](cudaStream_t st) { LDN_CUDA(cudaMemsetAsync(ws, 0, bytes, st)); }, 0);
+  }
   prog->io_elems = (size_t)B * 3 * H * W;
   prog->in_x = A.get<float>(prog->io_elems);
 
