@@ -147,6 +147,14 @@ int ldn_attention_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, c
 /* GroupNorm (+SiLU) over NHWC bf16, input may be a channel concat of x0 (C0) and x1 (C1, may be NULL/0). */
 int ldn_groupnorm_bf16(const void* x0, int C0, const void* x1, int C1, int B, int HW, int groups, float eps,
                        const float* gamma, const float* beta, int silu, void* out, void* stream);
+/* The ResBlock pair conv3x3 -> GroupNorm(32 groups)(+SiLU) as the UNet program runs it (src/AutoEncoders/ResBlock.py:251-292:
+ * in_layers[2] -> out_layers[0..1]): where the plan allows (whole 128-pixel tiles of one image, Cout 320 / 640 /
+ * 1280, no split-K) the conv's epilogue accumulates the GroupNorm statistics of its own output and only the apply kernel
+ * follows; otherwise the statistics kernel runs.  conv_out: the conv result (NHWC bf16), gn_out: the normalised result;
+ * *fused (host int, may be NULL) reports which of the two happened. */
+int ldn_conv3x3_groupnorm_bf16(const void* x, const void* Wt, int B, int H, int W, int Cin, int Cout, const float* bias,
+                               const float* rowbias, int ld_rowbias, const void* residual, float eps, const float* gamma,
+                               const float* beta, int silu, void* conv_out, void* gn_out, int* fused, void* stream);
 int ldn_layernorm_bf16(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
                        void* stream);
 

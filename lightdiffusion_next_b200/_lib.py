@@ -60,6 +60,7 @@ SIGNATURES = {
     "ldn_attention_bf16": [_p, _l, _p, _l, _p, _l, _l, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _l, _p],
     "ldn_groupnorm_bf16": [_p, _i, _p, _i, _i, _i, _i, _f, _p, _p, _i, _p, _p],
     "ldn_layernorm_bf16": [_p, _i, _i, _f, _p, _p, _p, _p],
+    "ldn_conv3x3_groupnorm_bf16": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _f, _p, _p, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {"ldn_last_error": C.c_char_p, "ldn_destroy": None}
 

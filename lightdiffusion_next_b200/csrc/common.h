@@ -73,6 +73,10 @@ struct GemmParams {
   const float* ln_d;
   float2* ln_final_out;       // row mode, optional: n-tile 0 / half 0 stores (rstd, -rstd * mean) per row for a later column-mode GEMM
   const float2* ln_final_in;  // column mode (operand-swapped V^T GEMM: output COLUMNS are tokens): per column (rstd, -rstd * mean)
+  // GroupNorm statistics of the OUTPUT taken in this conv's epilogue (gemm_epilogue_tile_lean_pf_gn): the
+  // 64-bit fixed-point (batch, group) accumulators of the consuming GroupNorm instance (norm.cu), or null
+  unsigned long long* gn_acc;
+  int gn_cpg;                 // output channels per group (10 / 20 / 40)
   int acc_stages;    // persistent kernel: accumulator stages in TMEM (2, or 1 when two CTAs share the SM and BN > 128)
   int epi_opt;       // bit 0: 256-bit epilogue accesses, bit 1: packed-pair GEGLU arithmetic, bit 2: MUFU-free polynomial Phi in the packed GEGLU
   int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77),
@@ -92,6 +96,7 @@ struct GemmPlan {
   dim3 grid;
   int smem_bytes;
   bool persistent = false;
+  int gn_cpg = 0;  // > 0: the lean one-tile kernel variant that also accumulates GroupNorm statistics of its output
   bool lean = false;  // plain bf16 epilogue (bias / rowbias / residual only): compile-time lean variant of the kernels
   int pgrid = 0;  // CTAs of the persistent kernel (<= SM count x persist_occ)
   int persist_occ = 1;  // persistent CTAs per SM (1 or 2)
@@ -139,6 +144,9 @@ struct GemmArgs {
   const float* ln_d = nullptr;
   float2* ln_final_out = nullptr;
   const float2* ln_final_in = nullptr;
+  // optional: accumulate the GroupNorm statistics (32 groups) of the output into these (batch, group) fixed-point
+  // accumulators; make_gemm_plan reports in GemmPlan::gn_cpg whether the plan does it (else the caller runs gn_stats)
+  unsigned long long* gn_acc = nullptr;
   int BN = 0;  // 0 = choose
   long long wt_ld = 0;  // leading dimension of Wt in elements (0 = K)
   int wt_rows = 0;  // valid rows of Wt if fewer than N (the rest are zero-filled by TMA)
@@ -215,10 +223,17 @@ void launch_attn(const AttnPlan& plan, cudaStream_t stream);
 // stats_ws: workspace of groupnorm_ws_bytes(B) bytes: LDN_GN_SLOTS statistics slots ([B][32] x two 64-bit fixed-point totals).
 // Every GroupNorm instance of a program uses its own slot; the whole workspace is zeroed once per program execution.
 #define LDN_GN_SLOTS 160
+// fixed-point scales of the accumulators: sum * 2^16, sum of squares * 2^12 (range: see norm.cu)
+#define LDN_GN_SUM_SCALE 65536.0
+#define LDN_GN_SQ_SCALE 4096.0
 inline size_t groupnorm_ws_bytes(int B) { return (size_t)LDN_GN_SLOTS * B * 64 * sizeof(unsigned long long); }
 void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
                       const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws, int slot,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool have_stats = false);  // have_stats: the slot already holds the totals (taken in the
+                                                                      // producing conv's epilogue): only the apply kernel runs
+inline unsigned long long* groupnorm_slot(float* stats_ws, int slot, int B) {
+  return reinterpret_cast<unsigned long long*>(stats_ws) + (size_t)slot * B * 64;
+}
 void launch_layernorm(const bf16* x, int rows, int C, float eps, const float* gamma, const float* beta, bf16* out,
                       cudaStream_t stream, float* out_f32 = nullptr);
 // out[b, n] = act_in(x[b, :]) . W[n, :] + bias[n]   (tiny-M linear; W bf16 [N, K], x fp32 [Bn, K])

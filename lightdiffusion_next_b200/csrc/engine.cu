@@ -354,6 +354,40 @@ int ldn_groupnorm_bf16(const void* x0, int C0, const void* x1, int C1, int B, in
   LDN_API_END
 }
 
+int ldn_conv3x3_groupnorm_bf16(const void* x, const void* Wt, int B, int H, int W, int Cin, int Cout, const float* bias,
+                               const float* rowbias, int ld_rowbias, const void* residual, float eps, const float* gamma,
+                               const float* beta, int silu, void* conv_out, void* gn_out, int* fused, void* stream) {
+  LDN_API_BEGIN
+  LDN_CHECK(x && Wt && gamma && beta && conv_out && gn_out && B > 0 && H > 0 && W > 0, "ldn_conv3x3_groupnorm_bf16: bad argument");
+  static thread_local float* ws = nullptr;
+  static thread_local int ws_b = 0;
+  static thread_local float* sk = nullptr;
+  const size_t sk_bytes = (size_t)64 << 20;
+  if (ws_b < B) {
+    if (ws) cudaFree(ws);
+    LDN_CUDA(cudaMalloc(&ws, groupnorm_ws_bytes(B)));
+    ws_b = B;
+  }
+  if (!sk) LDN_CUDA(cudaMalloc(&sk, sk_bytes));
+  LDN_CUDA(cudaMemsetAsync(ws, 0, (size_t)B * 64 * sizeof(unsigned long long), (cudaStream_t)stream));  // statistics slot 0
+  GemmArgs a;
+  a.conv = true;
+  a.A0 = (const bf16*)x; a.B = B; a.H = H; a.W = W; a.Cin = Cin;
+  a.Wt = (const bf16*)Wt; a.N = Cout; a.M = B * H * W;
+  a.bias = bias; a.rowbias = rowbias; a.ld_rowbias = ld_rowbias;
+  a.residual = (const bf16*)residual; a.ldr = Cout;
+  a.out = (bf16*)conv_out; a.ldo = Cout;
+  a.splitk_ws = sk; a.splitk_ws_bytes = sk_bytes;
+  a.gn_acc = groupnorm_slot(ws, 0, B);
+  GemmPlan plan = make_gemm_plan(a);
+  launch_gemm(plan, (cudaStream_t)stream);
+  const bool have = plan.gn_cpg > 0;
+  if (fused) *fused = have ? 1 : 0;
+  launch_groupnorm((const bf16*)conv_out, Cout, nullptr, 0, B, H * W, 32, eps, gamma, beta, silu != 0, (bf16*)gn_out, ws, 0,
+                   (cudaStream_t)stream, have);
+  LDN_API_END
+}
+
 int ldn_layernorm_bf16(const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out,
                        void* stream) {
   LDN_API_BEGIN

@@ -27,9 +27,17 @@
 
 namespace ldn {
 
-template <bool kLean>
+// kMode: 0 general epilogue; 1 lean epilogue (bias / row bias / residual, bf16 out); 10 / 20 / 40: lean epilogue that also
+// accumulates the GroupNorm statistics of the output (kMode = channels per group; gemm_epilogue.cuh).
+template <int kMode>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  constexpr bool kLean = kMode != 0;
+  constexpr bool kGn = kMode >= 2;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ unsigned long long gn_s[kGn ? 32 : 1];  // this tile's (group, {sum, sum of squares}) fixed-point partials
+  if constexpr (kGn) {
+    if (threadIdx.x < 32) gn_s[threadIdx.x] = 0ull;  // visible to the epilogue warps after the __syncthreads below
+  }
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
@@ -176,7 +184,17 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       lean_prefetch_residual<kPf>(p, BN, n0, out_row, ehalf, wres);
       mbar_wait(acc_bar, 0);
       tc_fence_after();
-      gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
+      if constexpr (kGn) {
+        gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, gn_s);
+        // all eight epilogue warps have added their groups: one thread per (group, moment) adds the tile's partial to the
+        // GroupNorm instance's (batch, group) accumulator.  The tile's 128 pixels belong to image b0 (BB = 1).
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int e = (int)threadIdx.x - 64;
+        if (e < 2 * (160 / kMode))
+          atomicAdd(&p.gn_acc[((size_t)b0 * 32 + (size_t)(n0 / kMode)) * 2 + (size_t)e], gn_s[e]);
+      } else {
+        gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
+      }
     } else {
       gemm_epilogue_tile<0>(p, BN, n0, out_row, batch, t_lane, ehalf, (int)blockIdx.z, m_row);
     }
@@ -640,8 +658,11 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
     }
   }
   // CTA-pair variant (gemm_pair.cu): 256 x BN tiles, each CTA loads half of the B tile
-  static const int pair_mode = getenv("LDN_GEMM_PAIR") ? atoi(getenv("LDN_GEMM_PAIR")) : 0;
-  // 1: every eligible GEMM; 2: only those that would otherwise run the one-tile-per-CTA kernel (long K: convs)
+  // 0: never; 1: every eligible GEMM; 2: long-K problems (those that would otherwise run the one-tile-per-CTA kernel: the 3x3
+  // convs) on the persistent pair kernel; 4 (default since round 2, profiles/r2_experiments.md section 24): long-K problems,
+  // one 256 x BN tile per pair, two CTAs of different pairs per SM -- with the lean prefetching epilogue and the GroupNorm
+  // statistics in it, 15.26 -> 14.94 ms per step on one box.
+  static const int pair_mode = getenv("LDN_GEMM_PAIR") ? atoi(getenv("LDN_GEMM_PAIR")) : 4;
   const bool pair_ok = BN >= 32 && BN % 16 == 0 && plan.grid.y >= 2 && !force_v1;
   plan.pair = pair_ok && (pair_mode == 1 || (pair_mode == 2 && !plan.persistent) || (pair_mode == 3 && plan.persistent) ||
                           (pair_mode == 4 && !plan.persistent));
@@ -669,14 +690,28 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
       plan.pgrid = 2 * (total_pairs < 74 ? total_pairs : 74);
     }
   }
+  // GroupNorm statistics of the output in the epilogue: the lean one-tile-per-CTA kernel on BN = 160 tiles whose
+  // 128 pixels belong to one image, N / 32 channels per group dividing the tile (10 / 20 / 40).  Anything else: the caller
+  // runs the statistics kernel (GemmPlan::gn_cpg stays 0).
+  const int gn_fuse = getenv("LDN_GN_FUSE") ? atoi(getenv("LDN_GN_FUSE")) : 1;  // read per plan (tests build both programs in one process)
+  if (gn_fuse && a.gn_acc && a.conv && plan.lean && !plan.persistent && (!plan.pair || plan.pair_occ2) && p.splits == 1 &&
+      BN == 160 && a.N % 160 == 0 && p.BB == 1 && (a.N == 320 || a.N == 640 || a.N == 1280) &&
+      ((plan.pair ? plan.pair_smem_bytes : plan.smem_bytes) + 512 <= 112 * 1024)) {
+    plan.gn_cpg = a.N / 32;
+    p.gn_acc = a.gn_acc;
+    p.gn_cpg = plan.gn_cpg;
+  }
   return plan;
 }
 
 void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));  // + 256 B static
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));  // + 256 B static
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));  // + 256 B static
     attr_set = true;
   }
   if (plan.pair) {
@@ -718,10 +753,16 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
     }
   } else {
     LDN_CHECK(!plan.p.ln_parts && !plan.p.ln_final_in && !plan.p.rowstat_out, "gemm: folded LayerNorm runs on the persistent kernel only (K <= 1280)");
-    if (plan.lean)
-      gemm_tc_kernel<true><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    if (plan.gn_cpg == 10)
+      gemm_tc_kernel<10><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    else if (plan.gn_cpg == 20)
+      gemm_tc_kernel<20><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    else if (plan.gn_cpg == 40)
+      gemm_tc_kernel<40><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+    else if (plan.lean)
+      gemm_tc_kernel<1><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
     else
-      gemm_tc_kernel<false><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
+      gemm_tc_kernel<0><<<plan.grid, kGemmThreads, plan.smem_bytes, stream>>>(plan.p);
   }
   LDN_CUDA(cudaGetLastError());
   if (plan.p.splits > 1) {

@@ -193,6 +193,108 @@ __device__ __forceinline__ void gemm_epilogue_tile_lean_pf(const GemmParams& p, 
   for (int c = ehalf * 16 + kPf * 32; c < BN; c += 32) chunk(c, nullptr);
 }
 
+// Lean epilogue that also takes the GroupNorm statistics of the tile it stores (statistics in the producer's
+// epilogue).  The consumer of a ResBlock conv's output is a GroupNorm over the same 32-group channel split, whose statistics
+// kernel re-read the whole tensor; here every epilogue thread (one output pixel) adds the fp32 values it is about to round
+// and store to a running (sum, sum of squares) of the current group, a finished group is folded over the warp's 32 pixels
+// with shuffles (fixed order) and added, as 64-bit FIXED-POINT integers (the format of norm.cu's accumulators: integer
+// addition is associative, so the totals stay bit-deterministic), to the CTA's accumulators in shared memory; the kernel
+// adds those to the (batch, group) accumulators of the GroupNorm instance once per tile.  Compile-time shape: BN = 160
+// (every SD1.5 conv: N = 320 / 640 / 1280) and kCpg = N / 32 channels per group (10 / 20 / 40, all dividing 160), so that
+// which group a column belongs to -- and where a group ends -- is known after unrolling.  All 128 rows of the tile belong
+// to one image (the plan checks BB = 1).
+template <int kPf, int kCpg, int kEh>
+__device__ __forceinline__ void lean_pf_gn_half(const GemmParams& p, const int n0, const long long out_row, const int batch,
+                                                const uint32_t t_lane, uint32_t (&wres)[kPf][8], unsigned long long* gn_s) {
+  const float* rb = p.rowbias ? p.rowbias + (long long)batch * p.ld_rowbias : nullptr;
+  const int lane = threadIdx.x & 31;
+  const bool ok = out_row >= 0;
+  float gs = 0.f, gq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int c = kEh * 16 + k * 32;
+    uint32_t v[16];
+    tmem_ld16(t_lane + (uint32_t)c, v);
+    const int n = n0 + c;
+    uint32_t wl[8];
+    float4 b4[4];
+    if (ok) {
+      if (p.residual && k >= kPf) ld_global_256(p.residual + out_row * p.ldr + n, wl);
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (rb) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + n) + i);
+          b4[i].x += r4.x; b4[i].y += r4.y; b4[i].z += r4.z; b4[i].w += r4.w;
+        }
+      }
+    }
+    tmem_ld_wait();
+    float f[16];
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[4 * i] = __uint_as_float(v[4 * i]) + b4[i].x;
+        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4[i].y;
+        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4[i].z;
+        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4[i].w;
+      }
+      if (p.residual) {
+        const uint32_t* w = k < kPf ? wres[k < kPf ? k : 0] : wl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[2 * i] += bf16_lo(w[i]);
+          f[2 * i + 1] += bf16_hi(w[i]);
+        }
+      }
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      st_global_256(p.out + out_row * p.ldo + n, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = 0.f;  // pixels past the image edge count for nothing
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      gs += f[i];
+      gq = fmaf(f[i], f[i], gq);
+      // the next column this warp accumulates: the neighbour, the first column of its next chunk, or none
+      const int next = i < 15 ? c + i + 1 : (k < 4 ? c + 32 : -1);
+      if (next < 0 || next / kCpg != (c + i) / kCpg) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          gs += __shfl_xor_sync(0xffffffffu, gs, o);
+          gq += __shfl_xor_sync(0xffffffffu, gq, o);
+        }
+        if (lane == 0) {
+          const int g = (c + i) / kCpg;
+          atomicAdd(&gn_s[2 * g], (unsigned long long)__float2ll_rn(gs * (float)LDN_GN_SUM_SCALE));
+          atomicAdd(&gn_s[2 * g + 1], (unsigned long long)__float2ll_rn(gq * (float)LDN_GN_SQ_SCALE));
+        }
+        gs = 0.f;
+        gq = 0.f;
+      }
+    }
+  }
+}
+template <int kPf, int kCpg>
+__device__ __forceinline__ void gemm_epilogue_tile_lean_pf_gn(const GemmParams& p, const int n0, const long long out_row,
+                                                              const int batch, const uint32_t t_lane, const int ehalf,
+                                                              uint32_t (&wres)[kPf][8], unsigned long long* gn_s) {
+  if (ehalf == 0)
+    lean_pf_gn_half<kPf, kCpg, 0>(p, n0, out_row, batch, t_lane, wres, gn_s);
+  else
+    lean_pf_gn_half<kPf, kCpg, 1>(p, n0, out_row, batch, t_lane, wres, gn_s);
+}
+
 // GEGLU without the MUFU: Phi(x) = 0.5 + x Q(min(x^2, 16)), Q a degree-7 minimax polynomial (max |dPhi| 3.2e-5 -- the
 // cut-off at |x| = 4, where 1 - Phi = 3.2e-5 --, max |dGELU| 1.3e-4, an order of magnitude below the bf16 rounding of the
 // output), saturated to [0, 1] by the FMA itself.  The level-0 GEGLU projection (K = 320) was bound by the epilogue's four MUFU

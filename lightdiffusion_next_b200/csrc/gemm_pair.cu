@@ -23,10 +23,18 @@ namespace ldn {
 
 // kOcc = 1: persistent (one pair per TPC walks a tile list, two accumulator stages); kOcc = 2: one tile per pair, two CTAs
 // (of different pairs) per SM overlap each other's epilogue and main loop -- the arrangement that wins for long-K convs.
-template <int kOcc>
+// kMode: 0 general epilogue; 1 lean epilogue with the residual prefetched behind the main loop; 10 / 20 / 40 (kOcc = 2 only):
+// lean epilogue that also accumulates the GroupNorm statistics of the output (gemm.cu / gemm_epilogue.cuh).
+template <int kOcc, int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
     gemm_tc_pair_kernel(const __grid_constant__ GemmParams p) {
+  constexpr bool kGn = kMode >= 2;
+  static_assert(!kGn || kOcc == 2, "GroupNorm statistics: one tile per CTA pair");
   extern __shared__ uint8_t smem_raw[];
+  __shared__ unsigned long long gn_s[kGn ? 32 : 1];  // this CTA's (group, {sum, sum of squares}) fixed-point partials
+  if constexpr (kGn) {
+    if (threadIdx.x < 32) gn_s[threadIdx.x] = 0ull;  // visible to the epilogue warps after the cluster barrier below
+  }
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,10 +200,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
         batch = p.rows_per_batch > 0 ? m / p.rows_per_batch : 0;
       }
       const int acc = tl & 1;
-      mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
-      tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
+      if constexpr (kMode == 0) {
+        mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
+        tc_fence_after();
+        gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
+      } else {
+        constexpr int kPf = 2;  // (three spill under this kernel's 96-register budget)
+        uint32_t wres[kPf][8];
+        lean_prefetch_residual<kPf>(p, BN, n0, out_row, ehalf, wres);  // in flight while the main loop runs
+        mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
+        tc_fence_after();
+        if constexpr (kGn) {
+          gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, gn_s);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // one thread per (group, moment): this CTA's 128 pixels belong to image tb (BB = 1; the odd tail tile of a pair
+          // lies past the last image and stored nothing)
+          const int tb = mt / (p.tiles_x * p.tiles_y);
+          const int e = (int)threadIdx.x - 64;
+          if (tb < p.B && e < 2 * (160 / kMode))
+            atomicAdd(&p.gn_acc[((size_t)tb * 32 + (size_t)(n0 / kMode)) * 2 + (size_t)e], gn_s[e]);
+        } else {
+          gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
@@ -213,14 +241,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
 void launch_gemm_pair(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));  // + 256 B static
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr = true;
   }
-  if (plan.pair_occ2)
-    gemm_tc_pair_kernel<2><<<plan.pgrid, kGemmThreads, plan.pair_smem_bytes, stream>>>(plan.p);
-  else
-    gemm_tc_pair_kernel<1><<<plan.pgrid, kGemmThreads, plan.pair_smem_bytes, stream>>>(plan.p);
+  auto go = [&](auto kern) { kern<<<plan.pgrid, kGemmThreads, plan.pair_smem_bytes, stream>>>(plan.p); };
+  static const int pair_lean = getenv("LDN_GEMM_PAIR_LEAN") ? atoi(getenv("LDN_GEMM_PAIR_LEAN")) : 1;
+  const bool lean = plan.lean && pair_lean;
+  if (plan.pair_occ2) {
+    if (plan.gn_cpg == 10) go(gemm_tc_pair_kernel<2, 10>);
+    else if (plan.gn_cpg == 20) go(gemm_tc_pair_kernel<2, 20>);
+    else if (plan.gn_cpg == 40) go(gemm_tc_pair_kernel<2, 40>);
+    else if (lean) go(gemm_tc_pair_kernel<2, 1>);
+    else go(gemm_tc_pair_kernel<2, 0>);
+  } else {
+    if (lean) go(gemm_tc_pair_kernel<1, 1>);
+    else go(gemm_tc_pair_kernel<1, 0>);
+  }
   LDN_CUDA(cudaGetLastError());
 }
 

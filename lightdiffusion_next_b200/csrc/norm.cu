@@ -21,8 +21,7 @@ namespace ldn {
 // first version ended with (a ~3 us tail on a ~6 us kernel).  The apply kernel converts the totals itself.  Accumulators
 // live in per-instance slots of the workspace, zeroed once per program execution (one memset node at its start).
 // Range: |sum| < 1.4e14, sum of squares < 2.2e15 per (batch, group) -- an RMS of ~67 000 over a 491 520-element group.
-#define LDN_GN_SUM_SCALE 65536.0
-#define LDN_GN_SQ_SCALE 4096.0
+// (LDN_GN_SUM_SCALE / LDN_GN_SQ_SCALE: common.h -- the conv epilogues that take the statistics themselves use them too)
 
 __global__ void __launch_bounds__(640, 2) gn_stats_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
                                 int cpg, int rows_per_block, int R, unsigned long long* __restrict__ acc) {
@@ -218,7 +217,7 @@ __global__ void __launch_bounds__(640, 2) gn_apply_kernel(const bf16* __restrict
 
 void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int HW, int groups, float eps,
                       const float* gamma, const float* beta, bool silu, bf16* out, float* stats_ws, int slot,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool have_stats) {
   const int C = C0 + C1;
   LDN_CHECK(groups == 32, "groupnorm: only 32 groups supported");
   LDN_CHECK(C % 32 == 0 && C % 8 == 0 && C0 % 8 == 0, "groupnorm: channel counts must be multiples of 8/32");
@@ -226,7 +225,7 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   LDN_CHECK(slot >= 0 && slot < LDN_GN_SLOTS, "groupnorm: statistics slot out of range");
   const int cpg = C / groups;
   // workspace: [slot][B][32] x (sum, sum of squares) as 64-bit fixed point; the slot must be zero when the statistics run
-  unsigned long long* acc = reinterpret_cast<unsigned long long*>(stats_ws) + (size_t)slot * B * 64;
+  unsigned long long* acc = groupnorm_slot(stats_ws, slot, B);
   const int nvec = C / 8;
   // R pixel rows per block pass; every thread should see >= 4 pixels (>= 8 when the tensor is large) so that its
   // 16-byte loads overlap, and the grid should still cover the 148 SMs where the tensor is big enough for that.
@@ -243,8 +242,10 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
     rows_per_block = (HW + 1023) / 1024;
     splits = (HW + rows_per_block - 1) / rows_per_block;
   }
-  gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, R, acc);
-  LDN_CUDA(cudaGetLastError());
+  if (!have_stats) {
+    gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, R, acc);
+    LDN_CUDA(cudaGetLastError());
+  }
   gn_apply_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, gamma, beta, silu ? 1 : 0, acc, eps, out,
                                                            rows_per_block, R);
   LDN_CUDA(cudaGetLastError());

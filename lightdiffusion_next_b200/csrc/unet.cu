@@ -441,12 +441,23 @@ struct Builder {
     P.names.push_back(name);
     P.launches += launches;
   }
+  // GroupNorm statistics taken in the producing conv's epilogue: `stats_of` is the tensor whose 32-group
+  // statistics slot `stats_slot` already holds (or will hold when the program reaches the consumer); a GroupNorm over exactly
+  // that tensor (no concat) then runs its apply kernel only.
+  const bf16* stats_of = nullptr;
+  int stats_slot = -1, stats_c = 0;
+  bool last_gemm_took_stats = false;
+  int new_gn_slot() {
+    LDN_CHECK(gn_slots < LDN_GN_SLOTS, "too many GroupNorm instances for the statistics workspace");
+    return gn_slots++;
+  }
   // returns the number of row-statistics partials per row the plan writes (meaningful when a0.rowstat_out is set)
   int gemm(const std::string& name, const GemmArgs& a0) {
     GemmArgs a = a0;
     a.splitk_ws = splitk_ws;
     a.splitk_ws_bytes = splitk_ws_bytes;
     GemmPlan plan = make_gemm_plan(a);
+    last_gemm_took_stats = plan.gn_cpg > 0;
     const long long Mm = a.conv ? (long long)a.B * a.H * a.W : a.M;
     const long long Kk = a.conv ? 9LL * a.Cin : (long long)a.K0 + a.K1;
     add(name + " [M=" + std::to_string(Mm) + " N=" + std::to_string(a.N) + " K=" + std::to_string(Kk) + "]",
@@ -460,9 +471,11 @@ struct Builder {
     const float* b = e->W(0, wprefix + ".bias").f();
     float* ws = gn_ws;
     int Bn = B;
-    const int slot = gn_slots++;  // every GroupNorm instance accumulates its statistics in its own (pre-zeroed) slot
-    LDN_CHECK(slot < LDN_GN_SLOTS, "too many GroupNorm instances for the statistics workspace");
-    add(name, [=](cudaStream_t st) { launch_groupnorm(x0, C0, x1, C1, Bn, HW, 32, eps, g, b, silu, out, ws, slot, st); }, 2);  // stats + apply
+    // every GroupNorm instance accumulates its statistics in its own (pre-zeroed) slot -- unless the conv that produced its
+    // input already did (then only the apply kernel runs, on the producer's slot)
+    const bool have = x1 == nullptr && x0 == stats_of && C0 == stats_c && stats_slot >= 0;
+    const int slot = have ? stats_slot : new_gn_slot();
+    add(name, [=](cudaStream_t st) { launch_groupnorm(x0, C0, x1, C1, Bn, HW, 32, eps, g, b, silu, out, ws, slot, st, have); }, have ? 1 : 2);  // (stats +) apply
   }
   void layernorm(const std::string& name, const bf16* x, int rows, int C, const std::string& wprefix, bf16* out) {
     const float* g = e->W(0, wprefix + ".weight").f();
@@ -483,7 +496,12 @@ struct Builder {
       a.bias = e->W(0, r.prefix + ".in_layers.2.bias").f();
       a.rowbias = emb_all + r.emb_off; a.ld_rowbias = U.emb_total;
       a.out = sB; a.ldo = r.cout;
+      const int slot = new_gn_slot();  // statistics of conv1's output for gn2, taken in conv1's epilogue where the plan allows
+      a.gn_acc = groupnorm_slot(gn_ws, slot, B);
       gemm(r.prefix + ".conv1", a);
+      stats_of = last_gemm_took_stats ? sB : nullptr;
+      stats_slot = slot;
+      stats_c = r.cout;
     }
     groupnorm(r.prefix + ".gn2", sB, r.cout, nullptr, 0, HW, 1e-5f, r.prefix + ".out_layers.0", true, sA);
     const bf16* res = x;
@@ -507,7 +525,12 @@ struct Builder {
       a.bias = e->W(0, r.prefix + ".out_layers.3.bias").f();
       a.residual = res; a.ldr = r.cout;
       a.out = out; a.ldo = r.cout;
+      const int slot = new_gn_slot();  // statistics of the block's output for a GroupNorm that reads exactly it (transformer.norm,
+      a.gn_acc = groupnorm_slot(gn_ws, slot, B);  // the next ResBlock's gn1 where nothing is concatenated)
       gemm(r.prefix + ".conv2", a);
+      stats_of = last_gemm_took_stats ? out : nullptr;
+      stats_slot = slot;
+      stats_c = r.cout;
     }
     return out;
   }

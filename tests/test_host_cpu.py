@@ -212,6 +212,7 @@ def test_entry_points_reject_null_arguments_with_an_error_code():
         "ldn_t5_encode": (None, None, None, 1, 16, None, None),
         "ldn_resample_bilinear": (None, None, 1, 8, 8, 4, 4, None),
         "ldn_bislerp": (None, None, None, 1, 4, 8, 8, 16, 16, None),
+        "ldn_conv3x3_groupnorm_bf16": (None, None, 1, 8, 8, 64, 320, None, None, 0, None, 1e-5, None, None, 1, None, None, None, None),
     }
     for name, args in calls.items():
         rc = getattr(lib, name)(*args)

@@ -100,6 +100,53 @@ def test_conv3x3(lib, B, H, W, Cin, Cout):
     assert rel(out.permute(0, 3, 1, 2), ref) < TOL
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,res,expect_fused", [
+    (2, 64, 64, 320, 320, False, True),     # conv1 -> gn2 at level 0 of a 512^2 image: 10 channels per group
+    (2, 64, 32, 640, 640, True, True),      # conv2 (+ residual) -> transformer.norm, 20 channels per group
+    (2, 100, 24, 320, 320, True, True),     # tiles hang over the right image edge: masked pixels count for nothing
+    (2, 50, 48, 320, 320, False, True),     # ... and over the bottom edge
+    (2, 32, 32, 640, 1280, False, True),    # 40 channels per group
+    (3, 32, 32, 960, 640, False, True),     # odd batch, Cin != Cout
+    (1, 40, 24, 320, 320, True, False),     # few tiles -> split-K: the statistics kernel runs
+    (2, 8, 8, 1280, 1280, False, False),    # split-K: the statistics kernel runs
+    (2, 16, 16, 320, 64, False, False),     # not a UNet width: the statistics kernel runs
+])
+def test_conv3x3_groupnorm_statistics_in_the_epilogue(lib, B, H, W, Cin, Cout, res, expect_fused):
+    """SURVEY K4 / ResBlock.py:251-292: conv3x3 (+ time-embedding row bias, + residual) -> GroupNorm(32) + SiLU with the
+    statistics taken in the conv's epilogue, against torch fp32 (conv2d -> group_norm -> silu on the bf16-rounded conv
+    output, as the engine's two-kernel path and the reference's fp16 path do).  Bit-deterministic."""
+    import ctypes
+    L, l = lib
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    b = torch.randn(Cout, device="cuda", generator=g)
+    rb = torch.randn(B, Cout, device="cuda", generator=g) * 2
+    R = (torch.randn(B, H, W, Cout, device="cuda", generator=g) * 3 + 1).bfloat16() if res else None
+    gamma = torch.randn(Cout, device="cuda", generator=g)
+    beta = torch.randn(Cout, device="cuda", generator=g)
+    conv_out = torch.zeros(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    gn_out = torch.zeros_like(conv_out)
+    fused = ctypes.c_int(-1)
+
+    def run():
+        L.check(l.ldn_conv3x3_groupnorm_bf16(x.data_ptr(), w.data_ptr(), B, H, W, Cin, Cout, b.data_ptr(), rb.data_ptr(), Cout,
+                                             R.data_ptr() if res else 0, 1e-5, gamma.data_ptr(), beta.data_ptr(), 1,
+                                             conv_out.data_ptr(), gn_out.data_ptr(), ctypes.addressof(fused), L.cur_stream()))
+        torch.cuda.synchronize()
+    run()
+    assert bool(fused.value) == expect_fused, fused.value
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b, padding=1) + rb[:, :, None, None]
+    if res:
+        ref = ref + R.float().permute(0, 3, 1, 2)
+    assert rel(conv_out.permute(0, 3, 1, 2), ref) < TOL
+    gn_ref = F.silu(F.group_norm(conv_out.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
+    assert rel(gn_out.permute(0, 3, 1, 2), gn_ref) < TOL
+    first = gn_out.clone()
+    run()
+    assert torch.equal(first, gn_out)  # integer accumulators: bit-deterministic
+
+
 @pytest.mark.parametrize("B,H,Nq,Nk,d,causal,ones", [(1, 1, 128, 128, 64, False, False), (2, 8, 1024, 1024, 40, False, False),
                                                      (2, 8, 1024, 77, 40, False, False), (2, 8, 256, 256, 160, False, False),
                                                      (2, 8, 1024, 1024, 80, False, False), (2, 8, 256, 77, 160, False, False),
