@@ -664,8 +664,9 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   // statistics in it, 15.26 -> 14.94 ms per step on one box.
   static const int pair_mode = getenv("LDN_GEMM_PAIR") ? atoi(getenv("LDN_GEMM_PAIR")) : 4;
   const bool pair_ok = BN >= 32 && BN % 16 == 0 && plan.grid.y >= 2 && !force_v1;
+  // (5, experiment: 4 plus the persistent pair kernel for the short-K problems)
   plan.pair = pair_ok && (pair_mode == 1 || (pair_mode == 2 && !plan.persistent) || (pair_mode == 3 && plan.persistent) ||
-                          (pair_mode == 4 && !plan.persistent));
+                          (pair_mode == 4 && !plan.persistent) || pair_mode == 5);
   if (plan.pair) {
     p.tmB2 = make_tmap_2d(a.Wt, a.wt_rows > 0 ? a.wt_rows : a.N, K, a.wt_ld > 0 ? a.wt_ld : K, BN / 2);
     int acc_stride = 32;
@@ -673,7 +674,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
     const int stage2 = kBM * kBK * 2 + (BN / 2) * kBK * 2;
     const int m_pairs = ((int)plan.grid.y + 1) / 2;
     const int total_pairs = (int)plan.grid.x * m_pairs * (int)plan.grid.z;
-    plan.pair_occ2 = pair_mode == 4;
+    plan.pair_occ2 = pair_mode == 4 || (pair_mode == 5 && !plan.persistent);
     if (plan.pair_occ2) {
       p.tmem_cols = acc_stride;  // <= 256: two CTAs per SM share the 512 columns
       int pst = (113 * 1024 - 1024 - 512) / stage2;

@@ -224,6 +224,8 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
   LDN_CHECK(C / 8 <= 640, "groupnorm: too many channels");
   LDN_CHECK(slot >= 0 && slot < LDN_GN_SLOTS, "groupnorm: statistics slot out of range");
   const int cpg = C / groups;
+  for (int c = 0; c < C; c += 8)  // a thread's 8 channels may touch two groups, not more (cpg >= 7, or 4)
+    LDN_CHECK((c + 7) / cpg - c / cpg <= 1, "groupnorm: channels per group too small for the 8-channel vectors");
   // workspace: [slot][B][32] x (sum, sum of squares) as 64-bit fixed point; the slot must be zero when the statistics run
   unsigned long long* acc = groupnorm_slot(stats_ws, slot, B);
   const int nvec = C / 8;
