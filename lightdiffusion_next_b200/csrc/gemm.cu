@@ -35,9 +35,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   constexpr bool kGn = kMode >= 2;
   extern __shared__ uint8_t smem_raw[];
   __shared__ unsigned long long gn_s[kGn ? 32 : 1];  // this tile's (group, {sum, sum of squares}) fixed-point partials
-  if constexpr (kGn) {
-    if (threadIdx.x < 32) gn_s[threadIdx.x] = 0ull;  // visible to the epilogue warps after the __syncthreads below
-  }
+
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
@@ -153,6 +151,13 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int ehalf = (warp - 2) >> 2;  // the two warps of a quarter take alternate 16-column chunks
     const int r = q * 32 + lane;
+    if constexpr (kGn) {
+      // the epilogue warps zero the tile's statistics partials themselves (after the block-wide barrier above) and meet on
+      // their own named barrier: the main loop they then wait for hides it
+      const int e0 = (int)threadIdx.x - 64;
+      if (e0 < 32) gn_s[e0] = 0ull;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     if constexpr (!kLean) {
       mbar_wait(acc_bar, 0);
       tc_fence_after();

@@ -32,9 +32,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
   static_assert(!kGn || kOcc == 2, "GroupNorm statistics: one tile per CTA pair");
   extern __shared__ uint8_t smem_raw[];
   __shared__ unsigned long long gn_s[kGn ? 32 : 1];  // this CTA's (group, {sum, sum of squares}) fixed-point partials
-  if constexpr (kGn) {
-    if (threadIdx.x < 32) gn_s[threadIdx.x] = 0ull;  // visible to the epilogue warps after the cluster barrier below
-  }
+
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,6 +169,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
     const int q = warp & 3;
     const int ehalf = (warp - 2) >> 2;
     const int r = q * 32 + lane;
+    if constexpr (kGn) {
+      // the epilogue warps zero the tile's statistics partials themselves (after the block-wide barrier above) and meet on
+      // their own named barrier: the main loop they then wait for hides it
+      const int e0 = (int)threadIdx.x - 64;
+      if (e0 < 32) gn_s[e0] = 0ull;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     int tl = 0;
     for (int w = cluster_id; w < total; w += n_clusters, ++tl) {
       const int z = w / mn_tiles, rem = w - z * mn_tiles;
