@@ -481,7 +481,26 @@ def hbm_roofline(eng, dev, bs: int, lat: int, peaks: dict) -> dict:
                                                          L.cur_stream())))
     nbytes = 2.0 * x.numel() * 2
     gn, ln = nbytes / (gn_ms * 1e-3) / 1e9, nbytes / (ln_ms * 1e-3) / 1e9
+    # GroupNorm as the UNet runs it behind a ResBlock conv: the conv's epilogue takes the statistics, only the apply
+    # kernel follows.  Its cost = (conv + GroupNorm through ldn_conv3x3_groupnorm_bf16) - (the same conv alone).
+    import ctypes
+    xi = x.view(B2, lat, lat, C)
+    w = (torch.randn(C, 3, 3, C, device=dev) / (9 * C) ** 0.5).bfloat16()
+    bias = torch.zeros(C, device=dev)
+    co = torch.empty_like(xi)
+    fused = ctypes.c_int(-1)
+    conv_ms = timed(lambda: L.check(lib.ldn_conv3x3_bf16(xi.data_ptr(), w.data_ptr(), B2, lat, lat, C, C, bias.data_ptr(), None, 0, None,
+                                                         co.data_ptr(), L.cur_stream())))
+    both_ms = timed(lambda: L.check(lib.ldn_conv3x3_groupnorm_bf16(xi.data_ptr(), w.data_ptr(), B2, lat, lat, C, C, bias.data_ptr(), None, 0,
+                                                                   None, 1e-5, gam.data_ptr(), bet.data_ptr(), 1, co.data_ptr(),
+                                                                   y.data_ptr(), ctypes.addressof(fused), L.cur_stream())))
+    inc_ms = max(both_ms - conv_ms, 1e-6)
+    after_conv = {"what": "GroupNorm + SiLU behind a 3x3 conv whose epilogue took the statistics (ldn_conv3x3_groupnorm_bf16): "
+                          "(conv + GroupNorm) - (conv alone)", "statistics_in_conv_epilogue": bool(fused.value),
+                  "conv_ms": conv_ms, "conv_groupnorm_ms": both_ms, "groupnorm_incremental_ms": inc_ms,
+                  "achieved": nbytes / (inc_ms * 1e-3) / 1e9, "frac": nbytes / (inc_ms * 1e-3) / 1e9 / peaks["hbm"]}
     return {"bound": "hbm", "kernel": "gn_stats + gn_apply (GroupNorm 32 + SiLU, [%d, %d] bf16)" % (B2 * HW, C), "achieved": gn,
+            "after_conv": after_conv,
             "peak": peaks["hbm"], "unit": "GB/s", "frac": gn / peaks["hbm"], "ms_per_launch": gn_ms,
             "algorithmic_bytes": nbytes, "note": "the tensor (%.0f MB) fits the 126 MB L2, back-to-back repeats may hit it" % (x.numel() * 2 / 1e6),
             "layernorm": {"kernel": "layernorm_kernel", "achieved": ln, "frac": ln / peaks["hbm"], "ms_per_launch": ln_ms},
