@@ -34,7 +34,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   constexpr bool kLean = kMode != 0;
   constexpr bool kGn = kMode >= 2;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ unsigned long long gn_s[kGn ? 32 : 1];  // this tile's (group, {sum, sum of squares}) fixed-point partials
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -151,13 +150,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int ehalf = (warp - 2) >> 2;  // the two warps of a quarter take alternate 16-column chunks
     const int r = q * 32 + lane;
-    if constexpr (kGn) {
-      // the epilogue warps zero the tile's statistics partials themselves (after the block-wide barrier above) and meet on
-      // their own named barrier: the main loop they then wait for hides it
-      const int e0 = (int)threadIdx.x - 64;
-      if (e0 < 32) gn_s[e0] = 0ull;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
     if constexpr (!kLean) {
       mbar_wait(acc_bar, 0);
       tc_fence_after();
@@ -190,13 +182,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       mbar_wait(acc_bar, 0);
       tc_fence_after();
       if constexpr (kGn) {
-        gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, gn_s);
-        // all eight epilogue warps have added their groups: one thread per (group, moment) adds the tile's partial to the
-        // GroupNorm instance's (batch, group) accumulator.  The tile's 128 pixels belong to image b0 (BB = 1).
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int e = (int)threadIdx.x - 64;
-        if (e < 2 * (160 / kMode))
-          atomicAdd(&p.gn_acc[((size_t)b0 * 32 + (size_t)(n0 / kMode)) * 2 + (size_t)e], gn_s[e]);
+        // the accumulator is complete: every MMA has read its operands, the ring (>= 3 stages of 36 KB) is free scratch space
+        gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, smem);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+        gn_flush_tile<kMode>(p, n0, b0, smem);  // the tile's 128 pixels belong to image b0 (BB = 1)
       } else {
         gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
       }
@@ -702,7 +691,7 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
   const int gn_fuse = getenv("LDN_GN_FUSE") ? atoi(getenv("LDN_GN_FUSE")) : 1;  // read per plan (tests build both programs in one process)
   if (gn_fuse && a.gn_acc && a.conv && plan.lean && !plan.persistent && (!plan.pair || plan.pair_occ2) && p.splits == 1 &&
       BN == 160 && a.N % 160 == 0 && p.BB == 1 && (a.N == 320 || a.N == 640 || a.N == 1280) &&
-      ((plan.pair ? plan.pair_smem_bytes : plan.smem_bytes) + 512 <= 112 * 1024)) {
+      (size_t)p.stages * (plan.pair ? (kBM * kBK * 2 + (BN / 2) * kBK * 2) : stage_bytes) >= (size_t)kGnScratchBytes) {
     plan.gn_cpg = a.N / 32;
     p.gn_acc = a.gn_acc;
     p.gn_cpg = plan.gn_cpg;
@@ -715,9 +704,9 @@ void launch_gemm(const GemmPlan& plan, cudaStream_t stream) {
   if (!attr_set) {
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));  // + 256 B static
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));  // + 256 B static
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));  // + 256 B static
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   if (plan.pair) {

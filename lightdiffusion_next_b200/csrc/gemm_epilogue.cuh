@@ -196,16 +196,33 @@ __device__ __forceinline__ void gemm_epilogue_tile_lean_pf(const GemmParams& p, 
 // Lean epilogue that also takes the GroupNorm statistics of the tile it stores (statistics in the producer's
 // epilogue).  The consumer of a ResBlock conv's output is a GroupNorm over the same 32-group channel split, whose statistics
 // kernel re-read the whole tensor; here every epilogue thread (one output pixel) adds the fp32 values it is about to round
-// and store to a running (sum, sum of squares) of the current group, a finished group is folded over the warp's 32 pixels
-// with shuffles (fixed order) and added, as 64-bit FIXED-POINT integers (the format of norm.cu's accumulators: integer
-// addition is associative, so the totals stay bit-deterministic), to the CTA's accumulators in shared memory; the kernel
-// adds those to the (batch, group) accumulators of the GroupNorm instance once per tile.  Compile-time shape: BN = 160
-// (every SD1.5 conv: N = 320 / 640 / 1280) and kCpg = N / 32 channels per group (10 / 20 / 40, all dividing 160), so that
-// which group a column belongs to -- and where a group ends -- is known after unrolling.  All 128 rows of the tile belong
-// to one image (the plan checks BB = 1).
+// and store to a running (sum, sum of squares) of the current group.  Compile-time shape: BN = 160 (every SD1.5 conv:
+// N = 320 / 640 / 1280) and kCpg = N / 32 channels per group (10 / 20 / 40, all dividing 160), so that which group a column
+// belongs to -- and where a group ends -- is known after unrolling.  A finished group's partial goes to a per-warp scratch
+// matrix [entry = group * 2 + moment][lane] in shared memory -- the operand ring, which is dead once the accumulator is
+// complete (one tile per CTA) --; at the end lane e of the warp adds up the 32 pixels of entry e in a fixed order and leaves
+// the total as 64-bit FIXED-POINT (the format of norm.cu's accumulators: integer addition is associative, so the totals stay
+// bit-deterministic) in the warp's row of a small table; the kernel adds the eight rows and then the tile's partial to the
+// (batch, group) accumulators of the GroupNorm instance.  No shuffles, no shared-memory atomics (a 64-bit shared-memory add is
+// a compare-and-swap loop): the first version, built on both, cost ~6 us per level-0 conv (profiles/r2_experiments.md section 25).
+// All 128 rows of the tile belong to one image (the plan checks BB = 1).
+constexpr int kGnScratchStride = 33;                                   // floats per entry: 32 lanes + 1 (bank-conflict-free both ways)
+constexpr int kGnScratchWarpBytes = 32 * kGnScratchStride * 4;          // 4224 B per epilogue warp
+constexpr int kGnScratchBytes = 8 * kGnScratchWarpBytes + 8 * 32 * 8;   // + the [8 warps][32 entries] table of 64-bit totals
+
+// bit g set: this warp (epilogue half kEh) stores columns of group g of the tile
+template <int kCpg, int kEh>
+__host__ __device__ constexpr uint32_t gn_group_mask() {
+  uint32_t m = 0;
+  for (int k = 0; k < 5; ++k)
+    for (int i = 0; i < 16; ++i) m |= 1u << ((kEh * 16 + k * 32 + i) / kCpg);
+  return m;
+}
+
 template <int kPf, int kCpg, int kEh>
 __device__ __forceinline__ void lean_pf_gn_half(const GemmParams& p, const int n0, const long long out_row, const int batch,
-                                                const uint32_t t_lane, uint32_t (&wres)[kPf][8], unsigned long long* gn_s) {
+                                                const uint32_t t_lane, uint32_t (&wres)[kPf][8], float* scratch,
+                                                unsigned long long* table_row) {
   const float* rb = p.rowbias ? p.rowbias + (long long)batch * p.ld_rowbias : nullptr;
   const int lane = threadIdx.x & 31;
   const bool ok = out_row >= 0;
@@ -269,30 +286,58 @@ __device__ __forceinline__ void lean_pf_gn_half(const GemmParams& p, const int n
       // the next column this warp accumulates: the neighbour, the first column of its next chunk, or none
       const int next = i < 15 ? c + i + 1 : (k < 4 ? c + 32 : -1);
       if (next < 0 || next / kCpg != (c + i) / kCpg) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          gs += __shfl_xor_sync(0xffffffffu, gs, o);
-          gq += __shfl_xor_sync(0xffffffffu, gq, o);
-        }
-        if (lane == 0) {
-          const int g = (c + i) / kCpg;
-          atomicAdd(&gn_s[2 * g], (unsigned long long)__float2ll_rn(gs * (float)LDN_GN_SUM_SCALE));
-          atomicAdd(&gn_s[2 * g + 1], (unsigned long long)__float2ll_rn(gq * (float)LDN_GN_SQ_SCALE));
-        }
+        const int e = 2 * ((c + i) / kCpg);  // a warp meets every group at most once (its columns ascend)
+        scratch[e * kGnScratchStride + lane] = gs;
+        scratch[(e + 1) * kGnScratchStride + lane] = gq;
         gs = 0.f;
         gq = 0.f;
       }
     }
   }
+  __syncwarp();
+  // lane e: entry e = (group e / 2, moment e % 2) over the warp's 32 pixels, in a fixed order
+  constexpr uint32_t kMask = gn_group_mask<kCpg, kEh>();
+  unsigned long long total = 0ull;
+  if ((kMask >> (lane >> 1)) & 1u) {
+    const float* col = scratch + lane * kGnScratchStride;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int l = 0; l < 32; l += 4) {
+      a0 += col[l];
+      a1 += col[l + 1];
+      a2 += col[l + 2];
+      a3 += col[l + 3];
+    }
+    const float t = (a0 + a1) + (a2 + a3);
+    total = (unsigned long long)__float2ll_rn(t * ((lane & 1) ? (float)LDN_GN_SQ_SCALE : (float)LDN_GN_SUM_SCALE));
+  }
+  table_row[lane] = total;
 }
+// scratch_base: kGnScratchBytes of shared memory nobody else touches any more (1024-byte aligned start of the operand ring)
 template <int kPf, int kCpg>
 __device__ __forceinline__ void gemm_epilogue_tile_lean_pf_gn(const GemmParams& p, const int n0, const long long out_row,
                                                               const int batch, const uint32_t t_lane, const int ehalf,
-                                                              uint32_t (&wres)[kPf][8], unsigned long long* gn_s) {
+                                                              uint32_t (&wres)[kPf][8], uint8_t* scratch_base) {
+  const int ew = (int)(threadIdx.x >> 5) - 2;  // epilogue warp 0..7
+  float* scratch = reinterpret_cast<float*>(scratch_base + ew * kGnScratchWarpBytes);
+  unsigned long long* table_row = reinterpret_cast<unsigned long long*>(scratch_base + 8 * kGnScratchWarpBytes) + ew * 32;
   if (ehalf == 0)
-    lean_pf_gn_half<kPf, kCpg, 0>(p, n0, out_row, batch, t_lane, wres, gn_s);
+    lean_pf_gn_half<kPf, kCpg, 0>(p, n0, out_row, batch, t_lane, wres, scratch, table_row);
   else
-    lean_pf_gn_half<kPf, kCpg, 1>(p, n0, out_row, batch, t_lane, wres, gn_s);
+    lean_pf_gn_half<kPf, kCpg, 1>(p, n0, out_row, batch, t_lane, wres, scratch, table_row);
+}
+// after a barrier over the 256 epilogue threads: thread e < 2 * groups-per-tile adds the eight warps' totals of entry e and then
+// the tile's partial to the (batch, group) accumulators
+template <int kCpg>
+__device__ __forceinline__ void gn_flush_tile(const GemmParams& p, const int n0, const int image, const uint8_t* scratch_base) {
+  const int e = (int)threadIdx.x - 64;
+  if (e < 2 * (160 / kCpg)) {
+    const unsigned long long* table = reinterpret_cast<const unsigned long long*>(scratch_base + 8 * kGnScratchWarpBytes);
+    unsigned long long t = 0ull;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += table[w * 32 + e];
+    atomicAdd(&p.gn_acc[((size_t)image * 32 + (size_t)(n0 / kCpg)) * 2 + (size_t)e], t);
+  }
 }
 
 // GEGLU without the MUFU: Phi(x) = 0.5 + x Q(min(x^2, 16)), Q a degree-7 minimax polynomial (max |dPhi| 3.2e-5 -- the

@@ -31,7 +31,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
   constexpr bool kGn = kMode >= 2;
   static_assert(!kGn || kOcc == 2, "GroupNorm statistics: one tile per CTA pair");
   extern __shared__ uint8_t smem_raw[];
-  __shared__ unsigned long long gn_s[kGn ? 32 : 1];  // this CTA's (group, {sum, sum of squares}) fixed-point partials
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -124,6 +123,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
             ph ^= 1u;
           }
         }
+        if constexpr (kOcc == 2) break;  // one tile per pair: tells the compiler the loop state dies here
       }
     }
   } else if (warp == 1) {
@@ -162,6 +162,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
             ph ^= 1u;
           }
         }
+        if constexpr (kOcc == 2) break;
       }
     }
   } else {
@@ -169,13 +170,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
     const int q = warp & 3;
     const int ehalf = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    if constexpr (kGn) {
-      // the epilogue warps zero the tile's statistics partials themselves (after the block-wide barrier above) and meet on
-      // their own named barrier: the main loop they then wait for hides it
-      const int e0 = (int)threadIdx.x - 64;
-      if (e0 < 32) gn_s[e0] = 0ull;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
     int tl = 0;
     for (int w = cluster_id; w < total; w += n_clusters, ++tl) {
       const int z = w / mn_tiles, rem = w - z * mn_tiles;
@@ -211,20 +205,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
         tc_fence_after();
         gemm_epilogue_tile(p, BN, n0, out_row, batch, t_lane, ehalf, z);
       } else {
-        constexpr int kPf = 2;  // (three spill under this kernel's 96-register budget)
+        constexpr int kPf = 3;
         uint32_t wres[kPf][8];
         lean_prefetch_residual<kPf>(p, BN, n0, out_row, ehalf, wres);  // in flight while the main loop runs
         mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
         tc_fence_after();
         if constexpr (kGn) {
-          gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, gn_s);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          // one thread per (group, moment): this CTA's 128 pixels belong to image tb (BB = 1; the odd tail tile of a pair
-          // lies past the last image and stored nothing)
+          // the pair's accumulator is complete (multicast commit): every MMA has read both CTAs' operands, this CTA's ring
+          // (>= 3 stages of 26 KB) is free scratch space
+          gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, smem);
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+          // this CTA's 128 pixels belong to image tb (BB = 1; the odd tail tile of a pair lies past the last image and stored nothing)
           const int tb = mt / (p.tiles_x * p.tiles_y);
-          const int e = (int)threadIdx.x - 64;
-          if (tb < p.B && e < 2 * (160 / kMode))
-            atomicAdd(&p.gn_acc[((size_t)tb * 32 + (size_t)(n0 / kMode)) * 2 + (size_t)e], gn_s[e]);
+          if (tb < p.B) gn_flush_tile<kMode>(p, n0, tb, smem);
         } else {
           gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
         }
@@ -232,6 +225,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      if constexpr (kOcc == 2) break;
     }
   }
 
@@ -250,9 +244,9 @@ void launch_gemm_pair(const GemmPlan& plan, cudaStream_t stream) {
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));  // + 256 B static
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr = true;
   }
   auto go = [&](auto kern) { kern<<<plan.pgrid, kGemmThreads, plan.pair_smem_bytes, stream>>>(plan.p); };
