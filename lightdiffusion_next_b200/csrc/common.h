@@ -77,6 +77,7 @@ struct GemmParams {
   // 64-bit fixed-point (batch, group) accumulators of the consuming GroupNorm instance (norm.cu), or null
   unsigned long long* gn_acc;
   int gn_cpg;                 // output channels per group (10 / 20 / 40)
+  int bias_smem;              // one-tile lean kernels: bias + row bias of the tile's columns staged in shared memory (gemm_epilogue.cuh)
   int acc_stages;    // persistent kernel: accumulator stages in TMEM (2, or 1 when two CTAs share the SM and BN > 128)
   int epi_opt;       // bit 0: 256-bit epilogue accesses, bit 1: packed-pair GEGLU arithmetic, bit 2: MUFU-free polynomial Phi in the packed GEGLU
   int act;  // epi 0 only: 0 none, 1 quick_gelu x*sigmoid(1.702x) applied after the bias (CLIP MLP, src/clip/Clip.py:74-77),

@@ -179,15 +179,20 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       constexpr int kPf = 3;
       uint32_t wres[kPf][8];
       lean_prefetch_residual<kPf>(p, BN, n0, out_row, ehalf, wres);
+      float* bsum = nullptr;
+      if (p.bias_smem) {  // (uniform) behind the barriers: plan reserved 1 KB there
+        bsum = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes + 256);
+        lean_stage_bias(p, BN, n0, b0, bsum);
+      }
       mbar_wait(acc_bar, 0);
       tc_fence_after();
       if constexpr (kGn) {
         // the accumulator is complete: every MMA has read its operands, the ring (>= 3 stages of 36 KB) is free scratch space
-        gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, smem);
+        gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, smem, bsum);
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
         gn_flush_tile<kMode>(p, n0, b0, smem);  // the tile's 128 pixels belong to image b0 (BB = 1)
       } else {
-        gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
+        gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres, bsum);
       }
     } else {
       gemm_epilogue_tile<0>(p, BN, n0, out_row, batch, t_lane, ehalf, (int)blockIdx.z, m_row);
@@ -684,6 +689,15 @@ GemmPlan make_gemm_plan(const GemmArgs& a) {
       plan.pair_smem_bytes = pst * stage2 + 1024 + 512;
       plan.pgrid = 2 * (total_pairs < 74 ? total_pairs : 74);
     }
+  }
+  // One-tile lean kernels: bias + row bias of the tile's columns staged in shared memory by the idle epilogue warps (needs one
+  // row bias for the whole tile: conv tiles of one image, or no row bias) -- 1 KB more shared memory behind the barriers.
+  static const int bias_smem_on = getenv("LDN_GEMM_BIAS_SMEM") ? atoi(getenv("LDN_GEMM_BIAS_SMEM")) : 1;
+  if (bias_smem_on && plan.lean && !plan.persistent && (!plan.pair || plan.pair_occ2) && p.splits == 1 && (a.bias || a.rowbias) &&
+      (a.rowbias == nullptr || (a.conv && p.BB == 1))) {
+    p.bias_smem = 1;
+    plan.smem_bytes += 1024;
+    plan.pair_smem_bytes += 1024;
   }
   // GroupNorm statistics of the output in the epilogue: the lean one-tile-per-CTA kernel on BN = 160 tiles whose
   // 128 pixels belong to one image, N / 32 channels per group dividing the tile (10 / 20 / 40).  Anything else: the caller

@@ -121,6 +121,23 @@ __device__ __forceinline__ void gemm_epilogue_tile_lean(const GemmParams& p, con
 // every warp had one 32-byte-per-lane residual read in flight at a time (16 KB per SM against ~1 us of latency = the
 // 2.5 TB/s the K = 320 projections reach).  The persistent kernel's epilogue warps request the residual of the first kPf
 // chunks of their NEXT tile before they wait for its accumulator, so the reads overlap that tile's main loop.
+// One-tile kernels: the 256 epilogue threads (idle while the main loop runs) leave bias[n] + rowbias[image][n] of the tile's BN
+// columns in shared memory (`bsum`, behind the barriers) and meet on their named barrier.  Valid when every row of the tile takes
+// the same row bias (GemmParams::bias_smem: conv tiles of one image, or no row bias at all).
+__device__ __forceinline__ void lean_stage_bias(const GemmParams& p, const int BN, const int n0, int image, float* bsum) {
+  if (p.conv && image >= p.B) image = p.B - 1;  // the odd tail tile of a CTA pair lies past the last image (it stores nothing)
+  const int e = (int)threadIdx.x - 64;
+  if (e < BN) {
+    const int n = n0 + e;
+    float v = 0.f;
+    if (n < p.N) {
+      if (p.bias) v = __ldg(p.bias + n);
+      if (p.rowbias) v += __ldg(p.rowbias + (long long)image * p.ld_rowbias + n);
+    }
+    bsum[e] = v;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
 template <int kPf>
 __device__ __forceinline__ void lean_prefetch_residual(const GemmParams& p, const int BN, const int n0, const long long out_row,
                                                        const int ehalf, uint32_t (&wres)[kPf][8]) {
@@ -134,7 +151,9 @@ __device__ __forceinline__ void lean_prefetch_residual(const GemmParams& p, cons
 template <int kPf>
 __device__ __forceinline__ void gemm_epilogue_tile_lean_pf(const GemmParams& p, const int BN, const int n0, const long long out_row,
                                                            const int batch, const uint32_t t_lane, const int ehalf,
-                                                           uint32_t (&wres)[kPf][8]) {
+                                                           uint32_t (&wres)[kPf][8], const float* bsum = nullptr) {
+  // bsum (one-tile kernels): bias + time-embedding row bias of the tile's columns, summed into shared memory by the epilogue
+  // warps while the main loop ran (lean_stage_bias) -- a broadcast LDS instead of eight L2-latency loads per chunk
   const float* rb = p.rowbias ? p.rowbias + (long long)batch * p.ld_rowbias : nullptr;
   auto chunk = [&](const int c, uint32_t* wpre) {
     uint32_t v[16];
@@ -143,7 +162,11 @@ __device__ __forceinline__ void gemm_epilogue_tile_lean_pf(const GemmParams& p, 
     const bool ok = out_row >= 0 && n < p.N;
     uint32_t wl[8];
     float4 b4[4];
-    if (ok) {
+    if (bsum != nullptr) {
+      if (ok && p.residual && wpre == nullptr) ld_global_256(p.residual + out_row * p.ldr + n, wl);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b4[i] = *reinterpret_cast<const float4*>(bsum + c + 4 * i);
+    } else if (ok) {
       if (p.residual && wpre == nullptr) ld_global_256(p.residual + out_row * p.ldr + n, wl);
       if (p.bias) {
 #pragma unroll
@@ -222,7 +245,7 @@ __host__ __device__ constexpr uint32_t gn_group_mask() {
 template <int kPf, int kCpg, int kEh>
 __device__ __forceinline__ void lean_pf_gn_half(const GemmParams& p, const int n0, const long long out_row, const int batch,
                                                 const uint32_t t_lane, uint32_t (&wres)[kPf][8], float* scratch,
-                                                unsigned long long* table_row) {
+                                                unsigned long long* table_row, const float* bsum) {
   const float* rb = p.rowbias ? p.rowbias + (long long)batch * p.ld_rowbias : nullptr;
   const int lane = threadIdx.x & 31;
   const bool ok = out_row >= 0;
@@ -235,7 +258,11 @@ __device__ __forceinline__ void lean_pf_gn_half(const GemmParams& p, const int n
     const int n = n0 + c;
     uint32_t wl[8];
     float4 b4[4];
-    if (ok) {
+    if (bsum != nullptr) {
+      if (ok && p.residual && k >= kPf) ld_global_256(p.residual + out_row * p.ldr + n, wl);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b4[i] = *reinterpret_cast<const float4*>(bsum + c + 4 * i);
+    } else if (ok) {
       if (p.residual && k >= kPf) ld_global_256(p.residual + out_row * p.ldr + n, wl);
       if (p.bias) {
 #pragma unroll
@@ -317,14 +344,15 @@ __device__ __forceinline__ void lean_pf_gn_half(const GemmParams& p, const int n
 template <int kPf, int kCpg>
 __device__ __forceinline__ void gemm_epilogue_tile_lean_pf_gn(const GemmParams& p, const int n0, const long long out_row,
                                                               const int batch, const uint32_t t_lane, const int ehalf,
-                                                              uint32_t (&wres)[kPf][8], uint8_t* scratch_base) {
+                                                              uint32_t (&wres)[kPf][8], uint8_t* scratch_base,
+                                                              const float* bsum = nullptr) {
   const int ew = (int)(threadIdx.x >> 5) - 2;  // epilogue warp 0..7
   float* scratch = reinterpret_cast<float*>(scratch_base + ew * kGnScratchWarpBytes);
   unsigned long long* table_row = reinterpret_cast<unsigned long long*>(scratch_base + 8 * kGnScratchWarpBytes) + ew * 32;
   if (ehalf == 0)
-    lean_pf_gn_half<kPf, kCpg, 0>(p, n0, out_row, batch, t_lane, wres, scratch, table_row);
+    lean_pf_gn_half<kPf, kCpg, 0>(p, n0, out_row, batch, t_lane, wres, scratch, table_row, bsum);
   else
-    lean_pf_gn_half<kPf, kCpg, 1>(p, n0, out_row, batch, t_lane, wres, scratch, table_row);
+    lean_pf_gn_half<kPf, kCpg, 1>(p, n0, out_row, batch, t_lane, wres, scratch, table_row, bsum);
 }
 // after a barrier over the 256 epilogue threads: thread e < 2 * groups-per-tile adds the eight warps' totals of entry e and then
 // the tile's partial to the (batch, group) accumulators

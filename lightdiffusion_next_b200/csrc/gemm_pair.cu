@@ -208,18 +208,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, kOcc)
         constexpr int kPf = 3;
         uint32_t wres[kPf][8];
         lean_prefetch_residual<kPf>(p, BN, n0, out_row, ehalf, wres);  // in flight while the main loop runs
+        float* bsum = nullptr;
+        if (kOcc == 2 && p.bias_smem) {  // (uniform) behind the barriers: plan reserved 1 KB there
+          bsum = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes + 512);
+          lean_stage_bias(p, BN, n0, p.conv ? mt / (p.tiles_x * p.tiles_y) : 0, bsum);
+        }
         mbar_wait(&tfull_bar[acc], ((uint32_t)tl >> 1) & 1u);
         tc_fence_after();
         if constexpr (kGn) {
           // the pair's accumulator is complete (multicast commit): every MMA has read both CTAs' operands, this CTA's ring
           // (>= 3 stages of 26 KB) is free scratch space
-          gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, smem);
+          gemm_epilogue_tile_lean_pf_gn<kPf, kMode>(p, n0, out_row, batch, t_lane, ehalf, wres, smem, bsum);
           asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
           // this CTA's 128 pixels belong to image tb (BB = 1; the odd tail tile of a pair lies past the last image and stored nothing)
           const int tb = mt / (p.tiles_x * p.tiles_y);
           if (tb < p.B) gn_flush_tile<kMode>(p, n0, tb, smem);
         } else {
-          gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres);
+          gemm_epilogue_tile_lean_pf<kPf>(p, BN, n0, out_row, batch, t_lane, ehalf, wres, bsum);
         }
       }
       tc_fence_before();
@@ -242,11 +247,11 @@ void launch_gemm_pair(const GemmPlan& plan, cudaStream_t stream) {
   if (!attr) {
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
+    LDN_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<2, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
     attr = true;
   }
   auto go = [&](auto kern) { kern<<<plan.pgrid, kGemmThreads, plan.pair_smem_bytes, stream>>>(plan.p); };
