@@ -315,3 +315,17 @@ def test_gemm_cta_pair_kernel_subprocess():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PAIR_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("env", [{"LDN_GEMM_PAIR": "0"}, {"LDN_GEMM_PAIR": "0", "LDN_GEMM_BIAS_SMEM": "0"}, {"LDN_GEMM_BIAS_SMEM": "0"}])
+def test_one_cta_long_k_kernel_stays_green(env):
+    """Since round 2 the long-K problems (3x3 convs) run on the CTA-pair kernel by default.  The one-CTA kernel (gemm_tc_kernel:
+    LDN_GEMM_PAIR=0) carries the same lean epilogue, GroupNorm statistics and bias staging; the switches are read once per
+    process, so the conv tests of this file run again in a child process under each setting."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_ops_gpu.py"), "-m", "gpu", "-q", "-x",
+                        "-p", "no:cacheprovider", "-k", "conv3x3"], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-3000:]
