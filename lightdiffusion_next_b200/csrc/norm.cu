@@ -78,11 +78,11 @@ __global__ void __launch_bounds__(640, 2) gn_stats_kernel(const bf16* __restrict
         q[2 * i + 1] += bb * bb;
       }
     }
-    const int g_lo = c / cpg;
+    const int g_hi_begin = (c / cpg + 1) * cpg;  // first channel of the second group this thread touches
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if ((c + i) / cpg == g_lo) {
+      if (c + i < g_hi_begin) {
         a0 += s[i];
         a1 += q[i];
       } else {
@@ -145,7 +145,7 @@ __device__ __forceinline__ float silu_f(float x) {
 __global__ void __launch_bounds__(640, 2) gn_apply_kernel(const bf16* __restrict__ x0, int C0, const bf16* __restrict__ x1, int C1, int HW,
                                 int cpg, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 const unsigned long long* __restrict__ acc, float eps, bf16* __restrict__ out,
-                                int rows_per_block, int R) {
+                                int rows_per_block, int R, double inv_sum, double inv_sq) {
   const int C = C0 + C1;
   const int nvec = C >> 3;
   if ((int)threadIdx.x >= nvec * R) return;  // the block is padded to whole warps
@@ -153,27 +153,28 @@ __global__ void __launch_bounds__(640, 2) gn_apply_kernel(const bf16* __restrict
   const int prow = threadIdx.x / nvec;
   const int b = blockIdx.y;
   const int c = cv * 8;
-  // (mean, rstd) of the (at most two) groups this thread's 8 channels touch, from the fixed-point totals
+  // (mean, rstd) of the (at most two) groups this thread's 8 channels touch, from the fixed-point totals.  The totals are
+  // converted and scaled in double (two multiplications by host-computed reciprocals and one FMA: E[x^2] - mean^2 needs the
+  // width), the rest runs in fp32: rsqrt.approx + one Newton step (~1 ulp).  The first version divided and took the square root
+  // in double in every thread -- ~110 FP64 instructions per thread in front of a ~10 us kernel.
   const int g_lo = c / cpg;
+  const int g_hi_begin = (g_lo + 1) * cpg;  // first channel of the second group
   float mean2[2], rstd2[2];
-  {
-    const double n = (double)HW * cpg;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int g = min(g_lo + k, 31);
-      const double sum = (double)(long long)acc[(b * 32 + g) * 2] * (1.0 / LDN_GN_SUM_SCALE);
-      const double sq = (double)(long long)acc[(b * 32 + g) * 2 + 1] * (1.0 / LDN_GN_SQ_SCALE);
-      const double mean = sum / n;
-      double var = sq / n - mean * mean;
-      if (var < 0) var = 0;
-      mean2[k] = (float)mean;
-      rstd2[k] = (float)(1.0 / sqrt(var + (double)eps));
-    }
+  for (int k = 0; k < 2; ++k) {
+    const int g = min(g_lo + k, 31);
+    const double mean = (double)(long long)acc[(b * 32 + g) * 2] * inv_sum;
+    const double ex2 = (double)(long long)acc[(b * 32 + g) * 2 + 1] * inv_sq;
+    const float var = fmaxf((float)fma(-mean, mean, ex2), 0.f) + eps;
+    float r = rsqrtf(var);
+    r = r * fmaf(-0.5f * var, r * r, 1.5f);
+    mean2[k] = (float)mean;
+    rstd2[k] = r;
   }
   float a[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int k = ((c + i) / cpg == g_lo) ? 0 : 1;
+    const int k = (c + i < g_hi_begin) ? 0 : 1;
     a[i] = rstd2[k] * gamma[c + i];
     sh[i] = beta[c + i] - mean2[k] * a[i];
   }
@@ -248,8 +249,10 @@ void launch_groupnorm(const bf16* x0, int C0, const bf16* x1, int C1, int B, int
     gn_stats_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, rows_per_block, R, acc);
     LDN_CUDA(cudaGetLastError());
   }
+  const double n_elems = (double)HW * cpg;  // per (batch, group)
   gn_apply_kernel<<<dim3(splits, B), threads, 0, stream>>>(x0, C0, x1, C1, HW, cpg, gamma, beta, silu ? 1 : 0, acc, eps, out,
-                                                           rows_per_block, R);
+                                                           rows_per_block, R, 1.0 / (LDN_GN_SUM_SCALE * n_elems),
+                                                           1.0 / (LDN_GN_SQ_SCALE * n_elems));
   LDN_CUDA(cudaGetLastError());
 }
 
